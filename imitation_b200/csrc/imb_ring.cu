@@ -1,0 +1,190 @@
+// imb_ring.cu -- stage 2 of the GAIL/AIRL round: transition tables, the generator ring buffer,
+// index sampling and the gather that assembles discriminator batches.
+//
+// Replaces (reference, /root/reference/src/imitation): data/buffer.py:147-232 (Buffer.store with
+// wrap-around + truncation, Buffer.sample = np.random.randint + fancy-index gather),
+// data/buffer.py:385-412 (ReplayBuffer facade), algorithms/base.py:272-282 + util/util.py:215-241
+// (expert DataLoader(shuffle, drop_last) re-iterated forever) and the np.concatenate of
+// algorithms/adversarial/common.py:592-595.
+//
+// All of these are HBM-bound byte movers: tables are AoS rows so a random gather reads whole
+// contiguous rows (one warp per row, lanes = consecutive floats); batches are feature-major so
+// the consumer streams them.  The 32-row x tw tile is transposed through padded shared memory so
+// both the reads and the writes are coalesced.
+#include "imb_common.cuh"
+
+namespace {
+
+// ---- table rows from separate row-major arrays --------------------------------------------------
+// one warp per transition; lanes walk the row.  Ring placement follows Buffer.store: only the last
+// min(n, capacity) rows are kept and written at (idx0 + i) mod capacity.
+__global__ void __launch_bounds__(256) k_table_store(float* __restrict__ table, int64_t capacity, int d_obs,
+                                                    int d_act, const float* __restrict__ obs,
+                                                    const float* __restrict__ acts_f,
+                                                    const int64_t* __restrict__ acts_i,
+                                                    const float* __restrict__ next_obs,
+                                                    const uint8_t* __restrict__ dones, int64_t n, int use_ring,
+                                                    const int64_t* __restrict__ state) {
+  const int tw = 2 * d_obs + d_act + 1;
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t skip = (use_ring && n > capacity) ? n - capacity : 0;
+  const int64_t idx0 = use_ring ? state[IMB_ST_RING_IDX] : 0;
+  for (int64_t i = gw + skip; i < n; i += nwarps) {
+    int64_t pos = i - skip;
+    if (use_ring) pos = (idx0 + pos) % capacity;
+    float* row = table + pos * tw;
+    const int64_t a_idx = acts_i ? acts_i[i] : 0;
+    for (int c = lane; c < tw; c += 32) {
+      float v;
+      if (c < d_obs)
+        v = obs[i * d_obs + c];
+      else if (c < d_obs + d_act)
+        v = acts_f ? acts_f[i * d_act + (c - d_obs)] : ((c - d_obs) == a_idx ? 1.f : 0.f);
+      else if (c < 2 * d_obs + d_act)
+        v = next_obs[i * d_obs + (c - d_obs - d_act)];
+      else
+        v = dones[i] ? 1.f : 0.f;
+      row[c] = v;
+    }
+  }
+}
+
+__global__ void k_ring_advance(int64_t* state, int64_t capacity, int64_t n_stored) {
+  const int64_t kept = n_stored < capacity ? n_stored : capacity;
+  state[IMB_ST_RING_IDX] = (state[IMB_ST_RING_IDX] + kept) % capacity;
+  int64_t nd = state[IMB_ST_RING_N] + kept;
+  state[IMB_ST_RING_N] = nd < capacity ? nd : capacity;
+}
+
+// ---- index generation (perf mode) -----------------------------------------------------------------
+// kind 0: Philox randint with replacement in [0, ring size)   (twin: oracle/philox.randint)
+// kind 1: endless Feistel permutations with drop_last          (twin: ExpertStreamPort in tests)
+__global__ void __launch_bounds__(256) k_sample_indices(int kind, int64_t* __restrict__ out, int64_t n,
+                                                       int64_t size_arg, uint64_t seed,
+                                                       const int64_t* __restrict__ state) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (kind == 0) {
+    const int64_t size = state[IMB_ST_RING_N];
+    const uint64_t draw = (uint64_t)state[IMB_ST_REPLAY_DRAW];
+    uint32_t k0, k1;
+    philox_key(seed, IMB_STREAM_REPLAY, k0, k1);
+    const Philox4 r = philox4x32((uint32_t)(i >> 2), (uint32_t)draw, (uint32_t)(draw >> 32), 0u, k0, k1);
+    const uint32_t w = ((i & 3) == 0) ? r.x : ((i & 3) == 1) ? r.y : ((i & 3) == 2) ? r.z : r.w;
+    out[i] = (int64_t)(((uint64_t)w * (uint64_t)size) >> 32);
+  } else {
+    // position `pos` inside epoch `ep`; a batch never straddles an epoch (drop_last): the host/
+    // advance kernel guarantees pos + n <= size_arg - (size_arg % n).
+    const int64_t pos = state[IMB_ST_EXPERT_POS];
+    const uint64_t ep = (uint64_t)state[IMB_ST_EXPERT_EPOCH];
+    const FeistelKey f = feistel_key(seed, IMB_STREAM_EXPERT, ep, (uint64_t)size_arg);
+    out[i] = (int64_t)feistel_perm(f, (uint64_t)(pos + i), (uint64_t)size_arg);
+  }
+}
+__global__ void k_sample_advance(int kind, int64_t n, int64_t size, int64_t* state) {
+  if (kind == 0) {
+    state[IMB_ST_REPLAY_DRAW] += 1;
+  } else {
+    int64_t pos = state[IMB_ST_EXPERT_POS] + n;
+    if (pos + n > size) {  // the next batch would not fit: drop the tail, start a new permutation
+      pos = 0;
+      state[IMB_ST_EXPERT_EPOCH] += 1;
+    }
+    state[IMB_ST_EXPERT_POS] = pos;
+  }
+}
+
+// ---- gather table rows into the feature-major batch --------------------------------------------------
+// Block = 8 warps, each warp owns 32 consecutive batch columns per iteration: it loads its 32 indices
+// with one coalesced read, walks them with __shfl_sync so that every row is read by consecutive
+// lanes (coalesced AoS read), parks the 32 x tw tile in padded shared memory and writes it back
+// transposed, 32 consecutive columns (128 B) per feature row.
+constexpr int G_WARPS = 8;
+__global__ void __launch_bounds__(G_WARPS * 32) k_gather_rows(const float* __restrict__ table, int64_t capacity,
+                                                              int tw, const int64_t* __restrict__ idx, int64_t n,
+                                                              float* __restrict__ batch, int64_t ld,
+                                                              int64_t col0) {
+  extern __shared__ float tile_all[];  // [G_WARPS][tw][33]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tile = tile_all + (size_t)warp * tw * 33;
+  const int64_t ngroups = (n + 31) / 32;
+  for (int64_t grp = (int64_t)blockIdx.x * G_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * G_WARPS) {
+    const int64_t b0 = grp * 32;
+    const int64_t mine = b0 + lane;
+    int64_t my_idx = 0;
+    if (mine < n) {
+      my_idx = idx ? idx[mine] : mine;
+      if (my_idx < 0) my_idx = 0;
+      if (my_idx >= capacity) my_idx = capacity - 1;
+    }
+    const int cnt = (int)min((int64_t)32, n - b0);
+    for (int j = 0; j < cnt; ++j) {
+      const int64_t r = __shfl_sync(0xffffffffu, my_idx, j);
+      const float* src = table + r * tw;
+      for (int c = lane; c < tw; c += 32) tile[c * 33 + j] = src[c];
+    }
+    __syncwarp();
+    if (lane < cnt) {
+      for (int c = 0; c < tw; ++c) batch[(int64_t)c * ld + col0 + b0 + lane] = tile[c * 33 + lane];
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+extern "C" int imb_table_store(float* table, int64_t capacity, int32_t d_obs, int32_t d_act, const float* obs,
+                               const float* acts_f, const int64_t* acts_i, const float* next_obs,
+                               const uint8_t* dones, int64_t n, int use_ring, const int64_t* state, void* stream) {
+  IMB_REQUIRE(n >= 1, "Trying to store empty data.");
+  IMB_REQUIRE((acts_f != nullptr) != (acts_i != nullptr), "exactly one of acts_f / acts_i must be given");
+  IMB_REQUIRE(use_ring || n <= capacity, "Not enough capacity to store data.");
+  int64_t warps = n < capacity ? n : capacity;
+  int64_t blocks = (warps * 32 + 255) / 256;
+  const int64_t cap = (int64_t)imb_num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  k_table_store<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(table, capacity, d_obs, d_act, obs, acts_f, acts_i,
+                                                                next_obs, dones, n, use_ring, state);
+  IMB_CHECK_LAUNCH("k_table_store");
+  return 0;
+}
+
+extern "C" int imb_ring_advance(int64_t* state, int64_t capacity, int64_t n_stored, void* stream) {
+  k_ring_advance<<<1, 1, 0, (cudaStream_t)stream>>>(state, capacity, n_stored);
+  IMB_CHECK_LAUNCH("k_ring_advance");
+  return 0;
+}
+
+extern "C" int imb_sample_indices(int kind, int64_t* idx_out, int64_t n, int64_t size, uint64_t seed,
+                                  int64_t* state, void* stream) {
+  IMB_REQUIRE(n >= 1, "n must be positive");
+  if (kind == 1) IMB_REQUIRE(size >= n, "Number of transitions in `demonstrations` %lld is smaller than batch size %lld.",
+                             (long long)size, (long long)n);
+  k_sample_indices<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(kind, idx_out, n, size, seed, state);
+  IMB_CHECK_LAUNCH("k_sample_indices");
+  k_sample_advance<<<1, 1, 0, (cudaStream_t)stream>>>(kind, n, size, state);
+  IMB_CHECK_LAUNCH("k_sample_advance");
+  return 0;
+}
+
+extern "C" int imb_gather_rows(const float* table, int64_t capacity, int32_t tw, const int64_t* idx, int64_t n,
+                               float* batch, int64_t ld, int64_t col0, void* stream) {
+  if (n <= 0) return 0;
+  IMB_REQUIRE(capacity >= 1 && tw >= 1, "bad table shape");
+  const size_t smem = (size_t)G_WARPS * tw * 33 * sizeof(float);
+  IMB_REQUIRE(smem <= 200 * 1024, "table row too wide for the gather tile");
+  static bool attr_set = false;
+  if (!attr_set && smem > 48 * 1024) {
+    cudaFuncSetAttribute(k_gather_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  int64_t blocks = ((n + 31) / 32 + G_WARPS - 1) / G_WARPS;
+  const int64_t cap = (int64_t)imb_num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  k_gather_rows<<<(int)blocks, G_WARPS * 32, smem, (cudaStream_t)stream>>>(table, capacity, tw, idx, n, batch, ld,
+                                                                            col0);
+  IMB_CHECK_LAUNCH("k_gather_rows");
+  return 0;
+}
