@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- GAIL env-steps/sec of the disc+gen round (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference]
+
+A "step" is one GAIL ROUND of the reference's hot path (AdversarialTrainer.train body,
+algorithms/adversarial/common.py:453-461): generator rollout of E*T env steps with learned-
+reward relabel -> PPO update (n_epochs x minibatches) -> replay store -> n_disc discriminator
+updates.  Workload (BASELINE.json north_star / configs): GAIL on the
+synthetic HalfCheetah-shaped env (obs 17 / act 6, horizon 1000), hyper-parameters of
+scripts/config/tuned_hps/gail_seals_half_cheetah_best_hp_eval.json (demo_batch 8192, replay
+capacity 512, 8 disc updates/round, PPO batch 4096 / minibatch 64 / 5 epochs, BasicRewardNet
+32x32 + RunningNorm input, FeedForward32Policy + NormalizeFeaturesExtractor), E = 1024 envs per
+GPU (so n_steps = 4096 / 1024 = 4), weak scaling: every extra GPU adds 1024 envs.
+
+value   whole-job env-steps/s with everything resident in HBM (the captured-graph round).
+e2e     the same metric through the reference-facing API with HOST expert batches: every
+        train_disc() gets `expert_samples` from pinned host memory (H2D inside the timed
+        region) and returns its Mapping[str, float] (D2H inside the timed region).
+roofline  dominant kernel by time share (the persistent PPO update) + the fused discriminator
+        kernel on a 2^20-row sweep point, against MEASURED_PEAKS.json.
+cpu_baseline / --impl reference  the CPU restatement of the reference's loop (oracle/gail_port.py:
+        reference data plane + SB3-PPO restatement, torch-CPU eager) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch as th
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(d_obs=17, d_act=6, horizon=1000, envs_per_gpu=1024, ppo_batch=4096, ppo_minibatch=64, ppo_epochs=5,
+           demo_batch=8192, replay_capacity=512, n_disc=8, n_expert_episodes=60, seed=0,
+           ppo=dict(clip_range=0.1, ent_coef=3.992371122209408e-6, gae_lambda=0.95, gamma=0.95,
+                    learning_rate=0.00026250519057717037, max_grad_norm=0.8, vf_coef=0.11483689492120866))
+
+
+# -------------------------------------------------------------------------------------------------
+def synth_expert(env_params: np.ndarray, d_obs, d_act, horizon, n_episodes, seed):
+    """Synthetic expert: fixed random linear-tanh policy + small noise, rolled out in the env."""
+    rng = np.random.default_rng(seed + 1000)
+    A = env_params[:d_obs * d_obs].reshape(d_obs, d_obs)
+    Bm = env_params[d_obs * d_obs:d_obs * d_obs + d_obs * d_act].reshape(d_obs, d_act)
+    c = env_params[d_obs * d_obs + d_obs * d_act:d_obs * d_obs + d_obs * d_act + d_obs]
+    K = rng.standard_normal((d_act, d_obs)).astype(np.float32) * 0.7
+    obs = (0.1 * rng.standard_normal((n_episodes, d_obs))).astype(np.float32)
+    O, Ac, NO, D = [], [], [], []
+    for t in range(horizon):
+        act = np.tanh(obs @ K.T) + 0.1 * rng.standard_normal((n_episodes, d_act)).astype(np.float32)
+        u = np.clip(act, -1, 1).astype(np.float32)
+        nobs = np.tanh(obs @ A.T + u @ Bm.T + c).astype(np.float32)
+        O.append(obs), Ac.append(u), NO.append(nobs), D.append(np.full(n_episodes, t == horizon - 1))
+        obs = nobs
+    # episode-major order like flatten_trajectories
+    sw = lambda x: np.ascontiguousarray(np.swapaxes(np.stack(x), 0, 1)).reshape(n_episodes * horizon, *x[0].shape[1:])
+    return dict(obs=sw(O), acts=sw(Ac), next_obs=sw(NO), dones=sw(D).astype(bool))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self._stop = index, [], threading.Event()
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.t.join(timeout=3)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "samples": len(self.rows), "reasons": reasons}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# -------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the CPU restatement of the reference's loop
+# -------------------------------------------------------------------------------------------------
+def build_cpu_port(n_envs, cfg, env_id_offset=0):
+    from oracle import gail_port, nets_port, ppo_port, synth_env
+
+    th.manual_seed(cfg["seed"])
+    np.random.seed(cfg["seed"])
+    spec = synth_env.SynthEnvSpec(cfg["d_obs"], cfg["d_act"], horizon=cfg["horizon"], seed=cfg["seed"])
+    venv = synth_env.SynthVecEnv(spec, n_envs, env_id_offset=env_id_offset)
+    env_params = np.concatenate([spec.A.ravel(), spec.Bm.ravel(), spec.c, spec.w])
+    expert = synth_expert(env_params, cfg["d_obs"], cfg["d_act"], cfg["horizon"], cfg["n_expert_episodes"], cfg["seed"])
+    pol = ppo_port.ActorCriticPort(cfg["d_obs"], cfg["d_act"], normalize_features=True)
+    gen = ppo_port.PPOPort(pol, venv, n_steps=cfg["ppo_batch"] // n_envs, batch_size=cfg["ppo_minibatch"],
+                           n_epochs=cfg["ppo_epochs"], **cfg["ppo"])
+    net = nets_port.BasicRewardNetPort(cfg["d_obs"], cfg["d_act"], normalize_input=True)
+    tr = gail_port.AdversarialPort(venv=venv, expert=expert, demo_batch_size=cfg["demo_batch"], gen=gen,
+                                   reward_net=net, n_disc_updates_per_round=cfg["n_disc"],
+                                   gen_replay_buffer_capacity=cfg["replay_capacity"])
+    return tr
+
+
+def time_cpu_port(cfg, n_envs, steps, warmup):
+    th.set_num_threads(os.cpu_count() or 1)
+    tr = build_cpu_port(n_envs, cfg)
+    per = tr.gen_train_timesteps
+    if warmup:
+        tr.train(per * warmup)
+    t0 = time.perf_counter()
+    tr.train(per * steps)
+    dt = time.perf_counter() - t0
+    return per * steps / dt, dt / steps, th.get_num_threads()
+
+
+# -------------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------------
+def build_trainer(cfg, rank, world, device):
+    from imitation_b200 import _desc
+    from imitation_b200.algorithms import ppo
+    from imitation_b200.algorithms.adversarial import gail
+    from imitation_b200.envs import synth
+    from imitation_b200.rewards import reward_nets
+    from imitation_b200.util import networks
+
+    E = cfg["envs_per_gpu"]
+    th.manual_seed(cfg["seed"])
+    venv = synth.DeviceVecEnv(cfg["d_obs"], cfg["d_act"], E, horizon=cfg["horizon"], seed=cfg["seed"],
+                              env_id_offset=rank * E, device=device)
+    expert = synth_expert(_desc.synth_env_params(cfg["d_obs"], cfg["d_act"], cfg["seed"]), cfg["d_obs"], cfg["d_act"],
+                          cfg["horizon"], cfg["n_expert_episodes"], cfg["seed"])
+    gen = ppo.DevicePPO("FeedForward32Policy", venv, n_steps=cfg["ppo_batch"] // E, batch_size=cfg["ppo_minibatch"],
+                        n_epochs=cfg["ppo_epochs"], policy_kwargs=dict(normalize_features=True), seed=cfg["seed"] + rank,
+                        device=device, **cfg["ppo"])
+    net = reward_nets.BasicRewardNet(venv.observation_space, venv.action_space,
+                                     normalize_input_layer=networks.RunningNorm)
+    tr = gail.GAIL(demonstrations=expert, demo_batch_size=cfg["demo_batch"], venv=venv, gen_algo=gen, reward_net=net,
+                   n_disc_updates_per_round=cfg["n_disc"], gen_replay_buffer_capacity=cfg["replay_capacity"],
+                   sampling="device", seed=cfg["seed"] + 17 * rank)
+    return tr, expert
+
+
+def cuda_time_ms(fn, stream=None):
+    a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+    a.record()
+    fn()
+    b.record()
+    b.synchronize()
+    return a.elapsed_time(b)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-rounds", type=int, default=12, help="rounds of the CPU baseline sample (rank 0, N=1)")
+    args = ap.parse_args()
+    cfg = CFG
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    E, T = cfg["envs_per_gpu"], cfg["ppo_batch"] // cfg["envs_per_gpu"]
+    config = {"workload": "GAIL HalfCheetah-shaped synthetic env (obs17/act6, H=1000), tuned HPs "
+                          "gail_seals_half_cheetah_best_hp_eval.json: demo_batch 8192, replay 512, 8 disc updates/round, "
+                          "PPO batch 4096 / mb 64 / 5 epochs; BasicRewardNet 32x32 + RunningNorm; FeedForward32Policy + "
+                          "NormalizeFeaturesExtractor",
+              "envs_per_gpu": E, "n_steps": T, "env_steps_per_round_per_gpu": E * T, "parallelism": f"dp{world}",
+              "sync": "one all-reduce per round (params+Adam moments averaged, RunningNorm merged exactly)",
+              "l2_policy": "working set (rollout 0.5 MB, ring 84 KB, disc batch 2.8 MB, expert table 9.8 MB) is L2-resident "
+                           "by construction at the tuned sizes; roofline sweep point uses 2^20 rows (176 MB > L2)"}
+
+    # ------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps, warmup = max(1, args.steps), max(0, args.warmup)
+        v, spr, cores = time_cpu_port(cfg, E, steps, warmup)
+        line = {"impl": "reference", "metric": "GAIL env-steps/sec (disc+gen loop)", "value": v, "unit": "env-steps/s",
+                "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": spr * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                 "sample": f"{steps} rounds of {E * T} env steps (E={E} envs on one host process; "
+                                           "oracle/gail_port.py = reference data plane + SB3-PPO restatement, torch-CPU)"},
+                "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------ our arm
+    import torch.distributed as dist
+
+    th.cuda.set_device(local)
+    device = th.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from imitation_b200 import _lib, distributed
+
+    tr, expert = build_trainer(cfg, rank, world, device)
+    sync = distributed.trainer_round_sync(tr) if world > 1 else None
+    if sync:
+        sync.broadcast_initial(0)
+
+    def round_eager():
+        if sync:
+            sync.begin_round()
+        tr.train_gen()
+        tr.disc_train_mode = True
+        for _ in range(cfg["n_disc"]):
+            tr.train_disc_async(check_ring=False)
+        tr.disc_train_mode = False
+        if sync:
+            sync.end_round()
+
+    for _ in range(max(3, args.warmup)):
+        round_eager()
+    th.cuda.synchronize()
+    tr.capture_round()
+
+    def round_graph():
+        if sync:
+            sync.begin_round()
+        tr.replay_round()
+        if sync:
+            sync.end_round()
+
+    for _ in range(3):
+        round_graph()
+    th.cuda.synchronize()
+
+    # ---- value: K graph-replayed rounds, device timed, max over ranks ---------------------------------------
+    K = args.steps
+    with ClockSampler(local) as clocks:
+        if world > 1:
+            dist.barrier()
+        th.cuda.synchronize()
+        l0 = _lib.LAUNCHES["count"]
+        ms = cuda_time_ms(lambda: [round_graph() for _ in range(K)])
+        launches = _lib.LAUNCHES["count"] - l0
+        th.cuda.synchronize()
+        if world > 1:
+            t = th.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+            dist.barrier()
+    value = world * E * T * K / (ms / 1e3)
+
+    # ---- e2e: reference-facing API, host expert batches, stats read back every update ---------------------------
+    B = cfg["demo_batch"]
+    n_exp = len(expert["obs"])
+    pinned = {k: th.as_tensor(np.ascontiguousarray(v.astype(np.float32) if v.dtype != bool else v)).pin_memory()
+              for k, v in expert.items()}
+    host_rng = np.random.default_rng(rank)
+    staging = {k: th.empty((B,) + tuple(v.shape[1:]), dtype=v.dtype).pin_memory() for k, v in pinned.items()}
+    h2d = cfg["n_disc"] * sum(staging[k].numel() * staging[k].element_size() for k in staging)
+    d2h = cfg["n_disc"] * 9 * 4
+    from imitation_b200.util import networks
+
+    def round_e2e():
+        if sync:
+            sync.begin_round()
+        tr.train_gen()
+        for _ in range(cfg["n_disc"]):
+            idx = th.as_tensor(host_rng.integers(0, n_exp, B))
+            for k in staging:
+                th.index_select(pinned[k], 0, idx, out=staging[k])  # host-side batch assembly (DataLoader's job)
+            with networks.training(tr.reward_train):
+                tr.train_disc(expert_samples=staging)                # H2D copy + update + 9-float D2H
+        if sync:
+            sync.end_round()
+
+    Ke = max(3, min(K, 30))
+    for _ in range(2):
+        round_e2e()
+    th.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_e = cuda_time_ms(lambda: [round_e2e() for _ in range(Ke)])
+    if world > 1:
+        t = th.tensor([ms_e], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e = float(t)
+    e2e_value = world * E * T * Ke / (ms_e / 1e3)
+
+    # ---- roofline: dominant kernel (PPO update) + fused disc kernel sweep point (rank 0) ------------------------------
+    roof, roof_disc, cpu_base = None, None, None
+    if rank == 0:
+        peak, peak_src = peaks()
+        gen = tr.gen_algo
+        gen.collect_rollouts()
+        th.cuda.synchronize()
+        reps = 10
+        ms_ppo = cuda_time_ms(lambda: [gen.train() for _ in range(reps)]) / reps
+        rw = _lib.rollout_row_width(gen.policy.desc)
+        n_rows = E * T
+        ppo_bytes = cfg["ppo_epochs"] * n_rows * (cfg["d_obs"] + cfg["d_act"] + 3) * 4 + 6 * gen.policy.desc.n_params * 4
+        ach = ppo_bytes / (ms_ppo / 1e3) / 1e9
+        roof = {"kernel": "k_ppo_update<32> (persistent single-CTA PPO.train: 320 sequential minibatch steps)",
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "ms_per_launch": ms_ppo, "share_of_step": ms_ppo / (ms / K),
+                "algorithmic_bytes_per_launch": ppo_bytes,
+                "note": "latency-bound by construction: 320 dependent optimiser steps of 64 rows each; the roofline "
+                        "fraction is reported as required but the figure of merit is us per minibatch step = "
+                        f"{ms_ppo * 1e3 / (cfg['ppo_epochs'] * n_rows / cfg['ppo_minibatch']):.2f}"}
+        # fused discriminator fwd/bwd at 2^20 rows (inputs 92 MB + logits 4 MB > L2 when iterated over 4 buffers)
+        eng = tr._fused_net.engine()
+        n_big = 1 << 20
+        from imitation_b200 import _desc
+        ld = _desc.batch_ld(n_big)
+        bufs = [th.randn(eng.bw, ld, device=device) for _ in range(3)]  # 3 x 176 MB: rotating inputs defeat L2
+        logits = th.empty(n_big, device=device)
+        for b in bufs:
+            eng.fwd_bwd(b, ld, n_big, n_big // 2, 1.0 / n_big, None, logits, True, False)
+        th.cuda.synchronize()
+        reps = 9
+        ms_d = cuda_time_ms(lambda: [eng.fwd_bwd(bufs[i % 3], ld, n_big, n_big // 2, 1.0 / n_big, None, logits, True,
+                                                 False) for i in range(reps)]) / reps
+        disc_bytes = n_big * 96
+        ach_d = disc_bytes / (ms_d / 1e3) / 1e9
+        roof_disc = {"kernel": "k_disc_fwdbwd<32> (fused BasicRewardNet fwd + BCE + bwd), 2^20 rows, Din 23, 32x32",
+                     "bound": "hbm", "achieved": ach_d, "peak": peak, "unit": "GB/s", "frac": ach_d / peak,
+                     "traffic": None, "ms_per_launch": ms_d, "algorithmic_bytes_per_row": 96,
+                     "fp32_tflops": n_big * 9280 / (ms_d / 1e3) / 1e12,
+                     "note": "includes the memset+meta launches (<3 us); fp32 FFMA path: compute-bound at "
+                             "9280 flop/row (AI 97 flop/B) -- see DESIGN.md"}
+        del bufs
+        if world == 1:
+            v, spr, cores = time_cpu_port(cfg, E, args.cpu_rounds, 1)
+            cpu_base = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_rounds} rounds x {E * T} env steps after 1 warm-up round "
+                                  f"({spr * args.cpu_rounds:.1f} s); oracle/gail_port.py on the host cores"}
+
+    if rank == 0:
+        line = {"metric": "GAIL env-steps/sec (disc+gen loop)", "value": value, "unit": "env-steps/s",
+                "n_gpus": world, "steps": K, "warmup": max(3, args.warmup) + 3, "ms_per_step": ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "clocks": clocks.summary(),
+                "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": Ke, "ms_per_step": ms_e / Ke,
+                        "path": "GAIL.train_gen() + GAIL.train_disc(expert_samples=<pinned host batch>) -> Mapping[str,float]"},
+                "gpu_launches": launches, "roofline": roof, "roofline_disc": roof_disc, "cpu_baseline": cpu_base}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

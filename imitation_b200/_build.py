@@ -35,15 +35,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
     os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
     procs = []
+    hdr_t = max(os.path.getmtime(p) for p in glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "imb.h")])
     for src in sources():
         obj = os.path.join(HERE, "_obj", os.path.basename(src) + ".o")
+        objs.append(obj)
+        if (not force and not verbose and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t)):
+            continue  # object is up to date
         cmd = [nvcc, "-c", src, "-o", obj, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
                "-Xcompiler", "-fPIC", "-DIMB_BUILDING"]
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-        objs.append(obj)
     failed = False
     for src, p in procs:
         out, _ = p.communicate()

@@ -89,7 +89,18 @@ def lib() -> C.CDLL:
     return _lib
 
 
-def _check(rc: int, what: str):
+# kernel launches issued through this binding (bench.py reports them as `gpu_launches`)
+LAUNCHES = {"count": 0}
+_KERNELS_PER_CALL = {
+    "imb_state_init": 0, "imb_disc_norm_update": None, "imb_disc_fwd_bwd": 2, "imb_disc_reduce": 1,
+    "imb_disc_adam": 2, "imb_reward_forward": 1, "imb_reward_norm_scan": 1, "imb_table_store": 1,
+    "imb_ring_advance": 1, "imb_sample_indices": 2, "imb_gather_rows": 1, "imb_rollout": 1, "imb_gae": 1,
+    "imb_rollout_advance": 1, "imb_env_reset": 1, "imb_ppo_update": 1, "imb_policy_logp": 1,
+}
+
+
+def _check(rc: int, what: str, n_kernels: Optional[int] = None):
+    LAUNCHES["count"] += _KERNELS_PER_CALL.get(what, 1) if n_kernels is None else n_kernels
     if rc != 0:
         raise ImbError(f"{what}: {lib().imb_last_error().decode()} (rc={rc})")
 
@@ -122,7 +133,8 @@ def state_init(state):
 def disc_norm_update(d, batch, ld, n, norm_state, norm_count, ws):
     _check(lib().imb_disc_norm_update(C.byref(d), _p(batch, th.float32), C.c_int64(ld), C.c_int64(n),
                                       _p(norm_state, th.float32), _p(norm_count, th.int32), _p(ws, th.float32),
-                                      _stream()), "imb_disc_norm_update")
+                                      _stream()), "imb_disc_norm_update",
+           int(d.base.has_norm) + (2 if (d.shaped and d.potential.has_norm) else 0))
 
 
 def disc_fwd_bwd(d, params, norm_state, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, flags, ws):

@@ -7,6 +7,9 @@
 
 #include "imb.h"
 
+// opt-in dynamic shared memory ceiling: 227 KB per CTA minus room for static __shared__ data
+#define IMB_SMEM_MAX (226 * 1024)
+
 // ---- error plumbing (thread-local text, negative codes) ------------------------------------
 extern thread_local char g_imb_err[512];
 #define IMB_FAIL(code, ...)                                   \

@@ -759,15 +759,15 @@ static int launch_fwdbwd(const DiscLaunch& L, const float* params, const float* 
   constexpr int R = TileCfg<H>::R;
   const SmemPlan<H> s = plan_smem<H>(L, true);
   const size_t bytes = (size_t)s.total_floats * 4;
-  IMB_REQUIRE(bytes <= 227 * 1024, "discriminator too large for the fused kernel (%zu B smem)", bytes);
+  IMB_REQUIRE(bytes <= IMB_SMEM_MAX, "discriminator too large for the fused kernel (%zu B smem)", bytes);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_disc_fwdbwd<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_disc_fwdbwd<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, IMB_SMEM_MAX);
     if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int64_t ntiles = (n + R - 1) / R;
-  int per_sm = (int)((227 * 1024) / (bytes + 1024));
+  int per_sm = (int)((IMB_SMEM_MAX) / (bytes + 1024));
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 2) per_sm = 2;
   int64_t G = (int64_t)imb_num_sms() * per_sm;
@@ -843,10 +843,10 @@ static int launch_fwd(const DiscLaunch& L, const float* params, const float* bat
                       int out_mode, float* out, cudaStream_t st) {
   const SmemPlan<H> s = plan_smem<H>(L, false);
   const size_t bytes = (size_t)s.total_floats * 4;
-  IMB_REQUIRE(bytes <= 227 * 1024, "reward net too large for the fused kernel (%zu B smem)", bytes);
+  IMB_REQUIRE(bytes <= IMB_SMEM_MAX, "reward net too large for the fused kernel (%zu B smem)", bytes);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_reward_fwd<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_reward_fwd<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, IMB_SMEM_MAX);
     if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }

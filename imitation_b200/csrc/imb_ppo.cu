@@ -651,14 +651,14 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
   A.mbr = (A.hp.batch_size + 31) / 32 * 32;
   A.moments_in_smem = 1;
   size_t fl = ppo_smem_floats<HP>(A.pol, 1, A.mbr);
-  if (fl * 4 > 220 * 1024) {
+  if (fl * 4 > IMB_SMEM_MAX) {
     A.moments_in_smem = 0;
     fl = ppo_smem_floats<HP>(A.pol, 0, A.mbr);
   }
-  IMB_REQUIRE(fl * 4 <= 220 * 1024, "PPO kernel needs %zu B of shared memory", fl * 4);
+  IMB_REQUIRE(fl * 4 <= IMB_SMEM_MAX, "PPO kernel needs %zu B of shared memory", fl * 4);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_ppo_update<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_ppo_update<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, IMB_SMEM_MAX);
     if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -705,10 +705,10 @@ static int launch_logp(const imb_policy_desc* pol, const float* params, const fl
   const int xn_off = al(o);
   o = xn_off + al(128 * xn_ld);
   const size_t bytes = (size_t)o * 4;
-  IMB_REQUIRE(bytes <= 227 * 1024, "policy too large");
+  IMB_REQUIRE(bytes <= IMB_SMEM_MAX, "policy too large");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_policy_logp<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_policy_logp<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, IMB_SMEM_MAX);
     attr_set = true;
   }
   int64_t blocks = (n + 127) / 128;

@@ -174,10 +174,10 @@ extern "C" int imb_gather_rows(const float* table, int64_t capacity, int32_t tw,
   if (n <= 0) return 0;
   IMB_REQUIRE(capacity >= 1 && tw >= 1, "bad table shape");
   const size_t smem = (size_t)G_WARPS * tw * 33 * sizeof(float);
-  IMB_REQUIRE(smem <= 200 * 1024, "table row too wide for the gather tile");
+  IMB_REQUIRE(smem <= IMB_SMEM_MAX, "table row too wide for the gather tile");
   static bool attr_set = false;
   if (!attr_set && smem > 48 * 1024) {
-    cudaFuncSetAttribute(k_gather_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_gather_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, IMB_SMEM_MAX);
     attr_set = true;
   }
   int64_t blocks = ((n + 31) / 32 + G_WARPS - 1) / G_WARPS;

@@ -222,7 +222,8 @@ int imb_rollout(const imb_env_desc* env, const float* env_params, float* env_obs
                 float* rollout, float* ring, int64_t ring_capacity, float* flat_out, float* aux,
                 const float* noise, const int64_t* state, void* stream);
 /* floats per rollout row: d_obs + (discrete ? 1 : d_act) + 5 (logp, value, reward, adv, ret);
- * aux needs 2*E + E*T floats (V(last obs), last done, per-step time-limit bootstrap). */
+ * aux needs 2*E + 2*E*T floats (V(last obs), last done, per-step time-limit bootstrap,
+ * per-step ground-truth env reward). */
 int imb_rollout_row_width(const imb_policy_desc* pol);
 /* GAE over the rollout table once rewards are final (SB3 RolloutBuffer.compute_returns_and_
  * advantage); call BEFORE imb_rollout_advance (it needs the pre-rollout episode step). */

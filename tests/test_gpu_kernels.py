@@ -414,7 +414,7 @@ def test_rollout_gae_matches_oracle(L, cfg):
     for rnd in range(n_rounds):
         tbl = th.zeros(E * T, rw, device="cuda")
         flat = th.zeros(E * T, tw, device="cuda")
-        aux = th.zeros(2 * E + E * T, device="cuda")
+        aux = th.zeros(2 * E + 2 * E * T, device="cuda")
         nz = dev(noise[rnd * T:(rnd + 1) * T])
         L.rollout(env, EP, obs, pd, PP, PN, dd, DP, DN, cfg["reward_mode"], hp, E, T, tbl, ring, cap, flat, aux, nz, st)
         L.gae(tbl, rw, Do + da_store + 1, E, T, aux, 0.97, 0.9, st, H)
