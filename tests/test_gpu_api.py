@@ -1,0 +1,367 @@
+"""GPU tests through the reference-shaped Python API (imitation_b200.*), written like the
+reference's own tests (tests/algorithms/test_adversarial.py, tests/data/test_buffer.py,
+tests/rewards/test_reward_nets.py) plus golden/oracle parity at the API level."""
+import io
+
+import numpy as np
+import pytest
+import torch as th
+
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(Do=17, Da=6, E=16, T=8, H=1000, discrete=False, B=64, mb=None, algo="gail", net_kwargs=None, seed=0,
+        sampling="device", cap=None, n_disc=2, norm_features=False, **gen_kw):
+    from imitation_b200.algorithms import ppo
+    from imitation_b200.algorithms.adversarial import airl, gail
+    from imitation_b200.envs import synth
+    from imitation_b200.rewards import reward_nets
+    from imitation_b200.util import networks
+
+    th.manual_seed(seed)
+    venv = synth.DeviceVecEnv(Do, Da, E, discrete=discrete, horizon=H, seed=seed)
+    gen = ppo.DevicePPO("FeedForward32Policy", venv, n_steps=T, batch_size=32, n_epochs=2, seed=seed,
+                        policy_kwargs=dict(normalize_features=norm_features), **gen_kw)
+    kw = dict(normalize_input_layer=networks.RunningNorm) if net_kwargs is None else net_kwargs
+    cls = reward_nets.BasicShapedRewardNet if algo == "airl" else reward_nets.BasicRewardNet
+    net = cls(venv.observation_space, venv.action_space, **kw)
+    rng = np.random.default_rng(seed)
+    n = 4 * B
+    demos = dict(obs=rng.standard_normal((n, Do)).astype(np.float32),
+                 acts=(rng.integers(0, Da, n) if discrete else rng.uniform(-1, 1, (n, Da)).astype(np.float32)),
+                 next_obs=rng.standard_normal((n, Do)).astype(np.float32), dones=rng.random(n) < 0.05)
+    tcls = airl.AIRL if algo == "airl" else gail.GAIL
+    tr = tcls(demonstrations=demos, demo_batch_size=B, demo_minibatch_size=mb, venv=venv, gen_algo=gen, reward_net=net,
+              n_disc_updates_per_round=n_disc, gen_replay_buffer_capacity=cap, sampling=sampling, seed=seed)
+    return tr, demos
+
+
+# ---- reference-style behavioural tests -------------------------------------------------------------------------
+def test_train_disc_improve_D():
+    """tests/algorithms/test_adversarial.py:256-282: loss decreases over a few steps on fixed data."""
+    tr, demos = _mk(B=128)
+    rng = np.random.default_rng(1)
+    ex = {k: v[:128] for k, v in demos.items()}
+    ge = dict(obs=rng.standard_normal((128, 17)).astype(np.float32) + 1.0,
+              acts=rng.uniform(-1, 1, (128, 6)).astype(np.float32),
+              next_obs=rng.standard_normal((128, 17)).astype(np.float32), dones=np.zeros(128, bool))
+    init = tr.train_disc(expert_samples=ex, gen_samples=ge)["disc_loss"]
+    for _ in range(3):
+        final = tr.train_disc(expert_samples=ex, gen_samples=ge)["disc_loss"]
+    assert final < init
+    st = tr.train_disc(expert_samples=ex, gen_samples=ge)
+    assert set(st) == {"disc_loss", "disc_acc", "disc_acc_expert", "disc_acc_gen", "disc_entropy",
+                       "disc_proportion_expert_true", "disc_proportion_expert_pred", "n_expert", "n_generated"}
+    assert all(isinstance(v, float) for v in st.values())
+    assert st["n_expert"] == 128 and st["n_generated"] == 128
+
+
+def test_gradient_accumulation():
+    """tests/algorithms/test_adversarial.py:285-343: minibatch 3 vs batch 6 give the same parameters."""
+    trs = []
+    for mb in (6, 3):
+        tr, demos = _mk(Do=5, Da=2, B=6, mb=mb, net_kwargs={}, seed=3)
+        trs.append(tr)
+    rng = np.random.default_rng(0)
+    for step in range(8):
+        ex = dict(obs=rng.standard_normal((6, 5)).astype(np.float32), acts=rng.uniform(-1, 1, (6, 2)).astype(np.float32),
+                  next_obs=rng.standard_normal((6, 5)).astype(np.float32), dones=np.zeros(6, bool))
+        ge = dict(obs=rng.standard_normal((6, 5)).astype(np.float32), acts=rng.uniform(-1, 1, (6, 2)).astype(np.float32),
+                  next_obs=rng.standard_normal((6, 5)).astype(np.float32), dones=np.zeros(6, bool))
+        for tr in trs:
+            tr.train_disc(expert_samples=ex, gen_samples=ge)
+        for p1, p2 in zip(trs[0]._reward_net.parameters(), trs[1]._reward_net.parameters()):
+            th.testing.assert_close(p1, p2, atol=(1 + step) * 2e-4, rtol=(1 + step) * 1e-5)
+
+
+def test_error_paths():
+    from imitation_b200.algorithms.adversarial import airl
+
+    with pytest.raises(ValueError, match="Batch size must be a multiple of minibatch size."):
+        _mk(B=8, mb=3)
+    tr, demos = _mk(B=8)
+    with pytest.raises(RuntimeError, match="No generator samples for training"):
+        tr.train_disc()
+    ex = {k: v[:7] for k, v in demos.items()}
+    with pytest.raises(ValueError, match="n_expert"):
+        tr.train_disc(expert_samples=ex, gen_samples={k: v[:8] for k, v in demos.items()})
+    with pytest.raises(ValueError, match="smaller than batch size"):
+        tr.set_demonstrations({k: v[:4] for k, v in demos.items()})
+    tr2, _ = _mk(algo="airl", B=8, net_kwargs={})
+    z = th.zeros(4, 17, device="cuda")
+    with pytest.raises(TypeError, match="Non-None `log_policy_act_prob` is required"):
+        tr2.logits_expert_is_high(z, th.zeros(4, 6, device="cuda"), z, th.zeros(4, device="cuda"))
+
+
+def test_train_gen_train_disc_and_fixed_horizon():
+    tr, _ = _mk(E=8, T=5, H=10, B=16, cap=24)
+    tr.train(3 * 8 * 5)
+    assert tr._global_step == 3 and tr._disc_step == 6
+    assert tr._gen_replay_buffer.size() == 24
+    assert tr._horizon == 10
+    tr.venv_buffering._ep_lens = [7]
+    with pytest.raises(ValueError, match="Episodes of different length detected"):
+        tr._check_fixed_horizon(tr.venv_buffering._ep_lens)
+
+
+# ---- golden parity at the API level (the reference's own train_disc call sequence) ---------------------------------
+@pytest.mark.parametrize("name", ["disc_gail_hc", "disc_gail_hc_minibatch", "disc_gail_cartpole"])
+def test_gail_train_disc_matches_reference_golden(name):
+    from imitation_b200.util import networks
+
+    z = G.load(name)
+    _, _, kw = G.DISC_CASES[name]
+    d_obs, d_act, discrete, B, mb, steps, seed = [int(v) for v in z["meta"]]
+    nk = dict(hid_sizes=kw["hid_sizes"])
+    if kw["normalize_input"]:
+        nk["normalize_input_layer"] = networks.RunningNorm
+    tr, _ = _mk(Do=d_obs, Da=d_act, discrete=bool(discrete), B=B, mb=mb, net_kwargs=nk)
+    sd = {k: th.as_tensor(np.array(v)) for k, v in G.sub(z, "init").items()}
+    tr._reward_net.load_state_dict(sd)  # same keys as the reference's state_dict
+    keys = [str(k) for k in z["stats_keys"]]
+    for s in range(steps):
+        with networks.training(tr.reward_train):
+            stats = tr.train_disc(expert_samples=G.sub(z, f"step{s}/expert"), gen_samples=G.sub(z, f"step{s}/gen"))
+        want = dict(zip(keys, z[f"step{s}/stats"]))
+        for k in keys:
+            np.testing.assert_allclose(stats[k], want[k], rtol=2e-5, atol=1e-6, err_msg=f"{k} step {s}")
+        got = {k: v.detach().cpu().numpy() for k, v in tr._reward_net.state_dict().items()}
+        for k, v in G.sub(z, f"step{s}/state").items():
+            np.testing.assert_allclose(got[k], v, rtol=1e-5, atol=2e-6, err_msg=f"{k} step {s}")
+        q = G.sub(z, f"step{s}/query")
+        np.testing.assert_allclose(tr.reward_train.predict_processed(q["obs"], q["acts"], q["next_obs"], q["dones"]),
+                                   z[f"step{s}/reward_train"], rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(tr.reward_test.predict(q["obs"], q["acts"], q["next_obs"], q["dones"]),
+                                   z[f"step{s}/reward_test"], rtol=1e-4, atol=2e-5)
+
+
+def test_airl_train_disc_matches_oracle_port():
+    """AIRL through the API (log pi from the generator policy kernel) vs the CPU restatement."""
+    from imitation_b200.util import networks
+    from oracle import disc_port, nets_port, ppo_port
+
+    tr, demos = _mk(algo="airl", B=32, mb=16, net_kwargs=dict(normalize_input_layer=networks.RunningNorm), seed=4)
+    net = nets_port.ShapedRewardNetPort(17, 6, normalize_input=True)
+    sd = {G.port_key(k): v.detach().cpu().clone() for k, v in tr._reward_net.state_dict().items()}
+    net.load_state_dict(sd)
+    pol = ppo_port.ActorCriticPort(17, 6)
+    psd = tr.policy.state_dict()
+    pol.load_state_dict({
+        "pi.0.weight": psd["mlp_extractor.policy_net.0.weight"], "pi.0.bias": psd["mlp_extractor.policy_net.0.bias"],
+        "pi.2.weight": psd["mlp_extractor.policy_net.2.weight"], "pi.2.bias": psd["mlp_extractor.policy_net.2.bias"],
+        "vf.0.weight": psd["mlp_extractor.value_net.0.weight"], "vf.0.bias": psd["mlp_extractor.value_net.0.bias"],
+        "vf.2.weight": psd["mlp_extractor.value_net.2.weight"], "vf.2.bias": psd["mlp_extractor.value_net.2.bias"],
+        "action_net.weight": psd["action_net.weight"], "action_net.bias": psd["action_net.bias"],
+        "value_net.weight": psd["value_net.weight"], "value_net.bias": psd["value_net.bias"],
+        "log_std": psd["log_std"]} | {})
+    pol = pol.cpu()
+    pol.load_state_dict({k: v.cpu() for k, v in pol.state_dict().items()})
+    port = disc_port.DiscTrainerPort(net, 32, 16, airl=True,
+                                     logp_fn=lambda o, a: pol.evaluate_actions(o.float(), a.float())[1])
+    rng = np.random.default_rng(9)
+    for s in range(3):
+        ex = {k: v[32 * s:32 * s + 32] for k, v in demos.items()}
+        ge = dict(obs=rng.standard_normal((32, 17)).astype(np.float32) * 0.5,
+                  acts=rng.uniform(-1, 1, (32, 6)).astype(np.float32),
+                  next_obs=rng.standard_normal((32, 17)).astype(np.float32), dones=rng.random(32) < 0.2)
+        with networks.training(tr.reward_train):
+            got = tr.train_disc(expert_samples=ex, gen_samples=ge)
+        net.train()
+        want = port.train_disc(ex, ge)
+        net.eval()
+        for k in want:
+            np.testing.assert_allclose(got[k], want[k], rtol=5e-5, atol=2e-6, err_msg=f"{k} step {s}")
+        for k, v in net.state_dict().items():
+            ours = {G.port_key(kk): vv for kk, vv in tr._reward_net.state_dict().items()}[k]
+            np.testing.assert_allclose(ours.cpu().numpy(), v.numpy(), rtol=2e-5, atol=3e-6, err_msg=f"{k} step {s}")
+
+
+# ---- reward nets: forward / autograd / pickling ------------------------------------------------------------------
+def test_reward_net_forward_and_autograd_match_port():
+    from imitation_b200 import spaces
+    from imitation_b200.rewards import reward_nets
+    from imitation_b200.util import networks
+    from oracle import nets_port
+
+    th.manual_seed(0)
+    net = reward_nets.BasicShapedRewardNet(spaces.Box(-1, 1, (5,)), spaces.Box(-1, 1, (2,)), use_next_state=True,
+                                           use_done=True, normalize_input_layer=networks.RunningNorm)
+    port = nets_port.ShapedRewardNetPort(5, 2, use_next_state=True, use_done=True, normalize_input=True)
+    port.load_state_dict({G.port_key(k): v.clone() for k, v in net.state_dict().items()})
+    net = net.to("cuda")
+    s, a, ns = th.randn(40, 5), th.randn(40, 2), th.randn(40, 5)
+    d = (th.rand(40) < 0.3).float()
+    for mode in (True, False):  # training (updates RunningNorm, twice for the potential) and eval
+        net.train(mode), port.train(mode)
+        out = net(s.cuda(), a.cuda(), ns.cuda(), d.cuda())
+        want = port(s, a, ns, d)
+        np.testing.assert_allclose(out.detach().cpu().numpy(), want.detach().numpy(), rtol=1e-4, atol=2e-5)
+        net.zero_grad(), port.zero_grad()
+        (out * th.linspace(-1, 1, 40, device="cuda")).sum().backward()
+        (want * th.linspace(-1, 1, 40)).sum().backward()
+        pg = {G.port_key(k): p.grad for k, p in net.named_parameters()}
+        for k, p in port.named_parameters():
+            np.testing.assert_allclose(pg[k].cpu().numpy(), p.grad.numpy(), rtol=2e-4, atol=2e-5, err_msg=k)
+    assert int(net.potential._potential_net.normalize_input.count) == 80
+    assert int(net._base.mlp.normalize_input.count) == 40
+    # any torch optimiser can drive the parameters (they alias the flat vector the kernels read)
+    opt = th.optim.SGD(net.parameters(), lr=0.1)
+    before = net(s.cuda(), a.cuda(), ns.cuda(), d.cuda()).detach().clone()
+    opt.step()
+    after = net(s.cuda(), a.cuda(), ns.cuda(), d.cuda()).detach()
+    assert not th.allclose(before, after)
+    # th.save / th.load of the whole module (scripts/train_adversarial.py:30-31)
+    buf = io.BytesIO()
+    th.save(net, buf)
+    buf.seek(0)
+    net2 = th.load(buf, weights_only=False)
+    np.testing.assert_allclose(net2(s.cuda(), a.cuda(), ns.cuda(), d.cuda()).detach().cpu().numpy(),
+                               after.cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_cpu_module_raises_no_fallback():
+    from imitation_b200 import _lib, spaces
+    from imitation_b200.rewards import reward_nets
+
+    net = reward_nets.BasicRewardNet(spaces.Box(-1, 1, (3,)), spaces.Box(-1, 1, (1,)))
+    with pytest.raises(_lib.ImbError, match="CUDA only"):
+        net(th.zeros(2, 3), th.zeros(2, 1), th.zeros(2, 3), th.zeros(2))
+
+
+def test_normalized_reward_net_and_ensemble_known_answers():
+    """tests/rewards/test_reward_nets.py:696-714 (mean 1 / var 8) and NormalizedRewardNet stats update."""
+    from imitation_b200 import spaces
+    from imitation_b200.rewards import reward_nets
+    from imitation_b200.util import networks
+
+    osp, asp = spaces.Box(-1, 1, (3,)), spaces.Box(-1, 1, (1,))
+
+    class Const(reward_nets.RewardNet):
+        def __init__(self, v):
+            super().__init__(osp, asp)
+            self.v = v
+            self.p = th.nn.Parameter(th.zeros(1))
+
+        def forward(self, s, a, ns, d):
+            return th.full((s.shape[0],), float(self.v), device=s.device)
+
+    ens = reward_nets.RewardEnsemble(osp, asp, [Const(3), Const(-1)]).cuda()
+    args = (np.zeros((10, 3), np.float32), np.zeros((10, 1), np.float32), np.zeros((10, 3), np.float32), np.zeros(10, bool))
+    mean, var = ens.predict_reward_moments(*args)
+    assert np.isclose(mean, 1).all() and np.isclose(var, 8).all()
+    add = reward_nets.AddSTDRewardWrapper(ens, default_alpha=0.5)
+    np.testing.assert_allclose(add.predict_processed(*args), 1 + 0.5 * np.sqrt(8), rtol=1e-6)
+    base = reward_nets.BasicRewardNet(osp, asp).cuda()
+    nn_ = reward_nets.NormalizedRewardNet(base, networks.RunningNorm).cuda()
+    r0 = nn_.predict_processed(*args, update_stats=False)
+    np.testing.assert_allclose(r0, base.predict(*args), rtol=1e-5, atol=1e-6)  # identity stats
+    nn_.predict_processed(*args)
+    assert int(nn_.normalize_output_layer.count) == 10
+    with pytest.raises(ValueError, match="ForwardWrapper cannot be applied"):
+        reward_nets.ShapedRewardNet(nn_, lambda s: s[:, 0], 0.9)
+
+
+# ---- replay buffer (tests/data/test_buffer.py) ------------------------------------------------------------------------
+def test_replay_buffer_reference_semantics():
+    from imitation_b200.data import buffer, types
+
+    z = G.load("replay_buffer")
+    np.random.seed(11)
+    buf = buffer.ReplayBuffer(10, obs_shape=(3,), act_shape=(2,), obs_dtype=np.float32, act_dtype=np.float32)
+    for i in range(5):
+        t = G.sub(z, f"store{i}")
+        n = len(t["obs"])
+        buf.store(types.Transitions(obs=t["obs"], acts=t["acts"], next_obs=t["next_obs"], dones=t["dones"],
+                                    infos=np.array([{}] * n)))
+        assert [buf._idx, buf.size()] == list(z[f"store{i}/idx"])
+        s = buf.sample(6)  # np.random.randint on the global RNG, like the reference
+        np.testing.assert_array_equal(s.obs, z[f"sample{i}/obs"])
+        np.testing.assert_array_equal(s.acts, z[f"sample{i}/acts"])
+        np.testing.assert_array_equal(s.dones, z[f"sample{i}/dones"])
+    with pytest.raises(ValueError, match="Not enough capacity"):
+        buf.store(dict(obs=np.zeros((11, 3), np.float32), acts=np.zeros((11, 2), np.float32),
+                       next_obs=np.zeros((11, 3), np.float32), dones=np.zeros(11, bool)), truncate_ok=False)
+    with pytest.raises(ValueError, match="Buffer is empty"):
+        buffer.ReplayBuffer(4, obs_shape=(3,), act_shape=(2,), obs_dtype=np.float32, act_dtype=np.float32).sample(1)
+
+
+def test_buffering_wrapper_pop_matches_oracle_order():
+    """pop_transitions()/pop_trajectories() of the device BufferingWrapper vs the CPU restatement of
+    data/wrappers.py + data/rollout.py on the same env, policy noise and steps."""
+    from oracle import data_port, ppo_port, synth_env
+
+    E, T, H, Do, Da = 6, 9, 4, 5, 2
+    tr, _ = _mk(Do=Do, Da=Da, E=E, T=T, H=H, B=16, net_kwargs={}, seed=2)
+    gen = tr.gen_algo
+    rng = np.random.default_rng(0)
+    noise = rng.standard_normal((T, E, Da)).astype(np.float32)
+    gen.noise = th.as_tensor(noise).cuda()
+    gen.collect_rollouts()
+    got = tr.venv_buffering.pop_transitions()
+    spec = synth_env.SynthEnvSpec(Do, Da, horizon=H, seed=2)
+    venv = synth_env.SynthVecEnv(spec, E)
+    bw = data_port.BufferingPort(venv)
+    pol = ppo_port.ActorCriticPort(Do, Da)
+    psd = {k: v.cpu() for k, v in tr.policy.state_dict().items()}
+    pol.load_state_dict({"pi.0.weight": psd["mlp_extractor.policy_net.0.weight"],
+                         "pi.0.bias": psd["mlp_extractor.policy_net.0.bias"],
+                         "pi.2.weight": psd["mlp_extractor.policy_net.2.weight"],
+                         "pi.2.bias": psd["mlp_extractor.policy_net.2.bias"],
+                         "vf.0.weight": psd["mlp_extractor.value_net.0.weight"],
+                         "vf.0.bias": psd["mlp_extractor.value_net.0.bias"],
+                         "vf.2.weight": psd["mlp_extractor.value_net.2.weight"],
+                         "vf.2.bias": psd["mlp_extractor.value_net.2.bias"],
+                         "action_net.weight": psd["action_net.weight"], "action_net.bias": psd["action_net.bias"],
+                         "value_net.weight": psd["value_net.weight"], "value_net.bias": psd["value_net.bias"],
+                         "log_std": psd["log_std"]})
+    g = ppo_port.PPOPort(pol, bw, n_steps=T, noise_fn=lambda s: noise[s])
+    g._last_obs = bw.reset()
+    g._last_starts = np.ones(E, bool)
+    g.collect_rollouts()
+    want = data_port.flatten_port(bw.pop_trajectories()[0])
+    np.testing.assert_array_equal(got.dones, want["dones"])
+    np.testing.assert_allclose(got.obs, want["obs"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(got.acts, want["acts"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(got.next_obs, want["next_obs"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(got.rews, want["rews"], rtol=1e-4, atol=2e-5)  # ground-truth env rewards
+    with pytest.raises(RuntimeError, match="empty BufferingWrapper"):
+        tr.venv_buffering.pop_transitions()
+
+
+# ---- whole round: graph replay == eager; device sampling twins -------------------------------------------------------
+def test_graph_round_equals_eager_round():
+    a, _ = _mk(E=64, T=4, H=50, B=128, cap=96, n_disc=3, norm_features=True, seed=5)
+    b, _ = _mk(E=64, T=4, H=50, B=128, cap=96, n_disc=3, norm_features=True, seed=5)
+    for tr in (a, b):
+        tr.train(2 * 64 * 4)  # two eager rounds
+    b.capture_round()
+    for _ in range(4):
+        a.train(64 * 4)
+        b.replay_round()
+    th.cuda.synchronize()
+    for p, q in zip(a._reward_net.parameters(), b._reward_net.parameters()):
+        th.testing.assert_close(p, q, rtol=0, atol=0)
+    for p, q in zip(a.policy.parameters(), b.policy.parameters()):
+        th.testing.assert_close(p, q, rtol=0, atol=0)
+    th.testing.assert_close(a.venv.state, b.venv.state, rtol=0, atol=0)
+    assert a._disc_step == b._disc_step and a._global_step == b._global_step
+    assert a._gen_replay_buffer.size() == b._gen_replay_buffer.size() == 96
+
+
+def test_host_compat_sampling_is_bit_exact_with_reference_streams():
+    """sampling='host_compat': expert batches follow the reference's DataLoader index stream and the
+    replay indices np.random.randint (golden: expert_loader.npz / replay_buffer.npz)."""
+    from imitation_b200.algorithms.adversarial import common
+
+    z = G.load("expert_loader")
+    for c in range(3):
+        n, B, seed = [int(v) for v in z[f"case{c}/cfg"]]
+        th.manual_seed(seed)
+        it = common._TorchCompatExpertIndices(n, B)
+        for want in z[f"case{c}/idx"]:
+            np.testing.assert_array_equal(it.next().numpy(), want)
+    z = G.load("replay_buffer")
+    np.random.seed(5)
+    np.testing.assert_array_equal(np.random.randint(512, size=8192), z["randint_512_x8192"])

@@ -1,0 +1,134 @@
+"""CPU tests of the host-side logic (no GPU, no compute through libimb.so): data types,
+hierarchical logger, descriptor builders, env-parameter twin, fixed-horizon check, and the
+multi-GPU round synchronisation on a world_size-2 gloo group."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch as th
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_transitions_validation_and_flatten():
+    from imitation_b200.data import types
+
+    obs = np.arange(12, dtype=np.float32).reshape(4, 3)
+    t = types.TrajectoryWithRew(obs=obs, acts=np.zeros((3, 2), np.float32), infos=None, terminal=True,
+                                rews=np.ones(3, np.float32))
+    tr = types.flatten_trajectories_with_rew([t, t])
+    assert len(tr) == 6 and tr.dones.tolist() == [False, False, True] * 2
+    np.testing.assert_array_equal(tr.next_obs[:3], obs[1:])
+    assert not tr.obs.flags.writeable  # read-only like the reference (data/types.py:524-526)
+    with pytest.raises(ValueError, match="dones must be boolean"):
+        types.Transitions(obs=obs[:3], acts=np.zeros((3, 2)), infos=np.array([{}] * 3), next_obs=obs[1:],
+                          dones=np.zeros(3))
+    with pytest.raises(ValueError, match="expected one more observations"):
+        types.Trajectory(obs=obs, acts=np.zeros((4, 2)), infos=None, terminal=True)
+    arrs = types.as_transition_arrays([t])
+    assert set(arrs) == {"obs", "acts", "next_obs", "dones"}
+
+
+def test_hierarchical_logger_accumulate_means():
+    from imitation_b200.util import logger
+
+    lg = logger.configure()
+    for v in (1.0, 3.0):
+        with lg.accumulate_means("disc"):
+            lg.record("disc_loss", v)
+            lg.dump(0)
+    assert lg.name_to_value["mean/disc/disc_loss"] == 2.0
+    assert lg.history[0][1] == {"raw/disc/disc_loss": 1.0}
+    lg.dump(1)
+    assert "mean/disc/disc_loss" in lg.history[-1][1] and not lg.name_to_value
+    with pytest.raises(RuntimeError, match="Nested"):
+        with lg.accumulate_means("a"):
+            with lg.accumulate_means("b"):
+                pass
+
+
+def test_descriptors_and_layouts():
+    from imitation_b200 import _desc
+
+    d = _desc.disc_desc(17, 6)
+    assert d.base.din == 23 and d.n_params == 23 * 32 + 32 + 32 * 32 + 32 + 32 + 1 == 1857
+    d = _desc.disc_desc(17, 6, hid_sizes=(32,), shaped=True, potential_hid_sizes=(32, 32), normalize_input=True)
+    assert d.n_params == 801 + 1665 and d.potential.param_off == 801 and d.potential.norm_off == 46
+    assert _desc.batch_ld(1) == 128 and _desc.batch_ld(129) == 256
+    pd = _desc.policy_desc(17, 6, False, 32)
+    assert pd.n_params == 2 * (17 * 32 + 32 + 32 * 32 + 32) + 6 * 32 + 6 + 32 + 1 + 6
+    with pytest.raises(NotImplementedError):
+        _desc.disc_desc(17, 6, hid_sizes=(32, 32, 32))
+    with pytest.raises(NotImplementedError):
+        _desc.disc_desc(70, 6)
+
+
+def test_env_params_twin_matches_oracle_spec():
+    from imitation_b200 import _desc
+    from oracle import synth_env
+
+    for Do, Da, seed in ((17, 6, 0), (4, 2, 7)):
+        spec = synth_env.SynthEnvSpec(Do, Da, seed=seed)
+        want = np.concatenate([spec.A.ravel(), spec.Bm.ravel(), spec.c, spec.w])
+        np.testing.assert_array_equal(_desc.synth_env_params(Do, Da, seed), want)
+
+
+def test_state_dict_keys_match_reference_names():
+    from imitation_b200 import spaces
+    from imitation_b200.rewards import reward_nets
+    from imitation_b200.util import networks
+    from tests import golden_util as G
+
+    net = reward_nets.BasicShapedRewardNet(spaces.Box(-1, 1, (17,)), spaces.Box(-1, 1, (6,)),
+                                           normalize_input_layer=networks.RunningNorm)
+    ref_keys = set(G.sub(G.load("disc_airl_hc"), "init"))
+    assert set(net.state_dict()) == ref_keys
+    net = reward_nets.BasicRewardNet(spaces.Box(-1, 1, (4,)), spaces.Discrete(2), hid_sizes=(64, 64))
+    assert set(net.state_dict()) == set(G.sub(G.load("disc_gail_cartpole"), "init"))
+    with pytest.raises(NotImplementedError):
+        reward_nets.BasicRewardNet(spaces.Box(-1, 1, (4,)), spaces.Discrete(2), dropout_prob=0.5)
+
+
+def _sync_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    from imitation_b200 import distributed
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    th.manual_seed(0)
+    params = th.arange(6, dtype=th.float32) + 10 * rank
+    mean, var, count = th.zeros(3), th.ones(3), th.zeros(1, dtype=th.int32)
+    # common start state with data already in it
+    start = th.randn(20, 3, generator=th.Generator().manual_seed(1))
+    mean.copy_(start.mean(0)), var.copy_(start.var(0, unbiased=False)), count.fill_(20)
+    sync = distributed.RoundSync([params], [distributed.NormStat(mean, var, count)])
+    sync.begin_round()
+    local = th.randn(7 + rank, 3, generator=th.Generator().manual_seed(2 + rank)) * (1 + rank)
+    allx = th.cat([start, local])
+    mean.copy_(allx.mean(0)), var.copy_(allx.var(0, unbiased=False)), count.fill_(len(allx))
+    sync.end_round()
+    out[rank] = (params.clone(), mean.clone(), var.clone(), int(count))
+    assert distributed.env_slice(4096, rank, world) == (rank * 2048, 2048)
+    dist.destroy_process_group()
+
+
+def test_round_sync_world2_gloo():
+    """N>1 path on CPU: parameters averaged, RunningNorm merged exactly (= stats of the union)."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_sync_worker, args=(world, port, out), nprocs=world, join=True)
+    start = th.randn(20, 3, generator=th.Generator().manual_seed(1))
+    locs = [th.randn(7 + r, 3, generator=th.Generator().manual_seed(2 + r)) * (1 + r) for r in range(world)]
+    union = th.cat([start] + locs)
+    for r in range(world):
+        p, m, v, c = out[r]
+        th.testing.assert_close(p, th.arange(6, dtype=th.float32) + 5.0)
+        th.testing.assert_close(m, union.mean(0), rtol=1e-5, atol=1e-6)
+        th.testing.assert_close(v, union.var(0, unbiased=False), rtol=1e-5, atol=1e-6)
+        assert c == len(union)
