@@ -357,7 +357,7 @@ def main():
                      "note": "includes the memset+meta launches (<3 us); fp32 FFMA path: compute-bound at "
                              "9280 flop/row (AI 97 flop/B) -- see DESIGN.md"}
         del bufs
-        if world == 1:
+        if world == 1 and args.cpu_rounds > 0:
             v, spr, cores = time_cpu_port(cfg, E, args.cpu_rounds, 1)
             cpu_base = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                         "sample": f"{args.cpu_rounds} rounds x {E * T} env steps after 1 warm-up round "
