@@ -132,8 +132,35 @@ def build_cpu_port(n_envs, cfg, env_id_offset=0):
     return tr
 
 
+def pick_cpu_threads(cfg, n_envs):
+    """The reference's tensors are tiny (MLPs of width 32, minibatches of 64): oversubscribing a
+    many-core host makes torch-CPU *slower* (measured: 128 threads -> 87 s/round vs ~1 s/round at 8).
+    Give the baseline the thread count it runs fastest with: time one PPO-minibatch-sized and one
+    disc-batch-sized step at a few candidates and keep the best (the reference's own CI pins 1)."""
+    import time as _t
+
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (1, 2, 4, 8, 16, 32) if c <= ncpu})
+    mlp = th.nn.Sequential(th.nn.Linear(23, 32), th.nn.ReLU(), th.nn.Linear(32, 32), th.nn.ReLU(), th.nn.Linear(32, 1))
+    opt = th.optim.Adam(mlp.parameters())
+    xs, xb = th.randn(64, 23), th.randn(2 * cfg["demo_batch"], 23)
+    best, best_t = 1, float("inf")
+    for c in cands:
+        th.set_num_threads(c)
+        t0 = _t.perf_counter()
+        for x, reps in ((xs, 40), (xb, 2)):
+            for _ in range(reps):
+                opt.zero_grad()
+                mlp(x).square().mean().backward()
+                opt.step()
+        dt = _t.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+    return best
+
+
 def time_cpu_port(cfg, n_envs, steps, warmup):
-    th.set_num_threads(os.cpu_count() or 1)
+    th.set_num_threads(pick_cpu_threads(cfg, n_envs))
     tr = build_cpu_port(n_envs, cfg)
     per = tr.gen_train_timesteps
     if warmup:
@@ -215,7 +242,9 @@ def main():
                 "config": config,
                 "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                  "sample": f"{steps} rounds of {E * T} env steps (E={E} envs on one host process; "
-                                           "oracle/gail_port.py = reference data plane + SB3-PPO restatement, torch-CPU)"},
+                                           "oracle/gail_port.py = reference data plane + SB3-PPO restatement, torch-CPU; "
+                                           f"torch threads auto-picked = {cores} of {os.cpu_count()} host cores, the "
+                                           "fastest setting for these tiny tensors)"},
                 "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -361,7 +390,8 @@ def main():
             v, spr, cores = time_cpu_port(cfg, E, args.cpu_rounds, 1)
             cpu_base = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                         "sample": f"{args.cpu_rounds} rounds x {E * T} env steps after 1 warm-up round "
-                                  f"({spr * args.cpu_rounds:.1f} s); oracle/gail_port.py on the host cores"}
+                                  f"({spr * args.cpu_rounds:.1f} s); oracle/gail_port.py, torch threads auto-picked = "
+                                  f"{cores} of {os.cpu_count()} host cores (fastest for these tiny tensors)"}
 
     if rank == 0:
         line = {"metric": "GAIL env-steps/sec (disc+gen loop)", "value": value, "unit": "env-steps/s",

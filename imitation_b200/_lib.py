@@ -195,12 +195,13 @@ def rollout_row_width(pol: PolicyDesc) -> int:
 
 
 def rollout(env, env_params, env_obs, pol, pol_params, pol_norm, disc, disc_params, disc_norm, reward_mode, hp,
-            n_envs, n_steps, rollout_tbl, ring, ring_capacity, flat_out, aux, noise, state):
+            n_envs, n_steps, rollout_tbl, ring, ring_capacity, flat_out, aux, noise, state, flags=0):
     _check(lib().imb_rollout(C.byref(env), _p(env_params, th.float32), _p(env_obs, th.float32), C.byref(pol),
                              _p(pol_params, th.float32), _p(pol_norm), C.byref(disc) if disc is not None else None,
                              _p(disc_params), _p(disc_norm), C.c_int(reward_mode), C.byref(hp), C.c_int64(n_envs),
                              C.c_int64(n_steps), _p(rollout_tbl, th.float32), _p(ring), C.c_int64(ring_capacity),
-                             _p(flat_out), _p(aux, th.float32), _p(noise), _p(state, th.int64), _stream()),
+                             _p(flat_out), _p(aux, th.float32), _p(noise), C.c_int(flags), _p(state, th.int64),
+                             _stream()),
            "imb_rollout")
 
 

@@ -20,7 +20,7 @@ extern "C" int imb_rollout(const imb_env_desc* env, const float* env_params, flo
                            const imb_disc_desc* disc, const float* disc_params, const float* disc_norm,
                            int reward_mode, const imb_ppo_hparams* hp, int64_t n_envs, int64_t n_steps,
                            float* rollout, float* ring, int64_t ring_capacity, float* flat_out, float* aux,
-                           const float* noise, const int64_t* state, void* stream) {
+                           const float* noise, int flags, const int64_t* state, void* stream) {
   IMB_REQUIRE(n_envs >= 1 && n_steps >= 1, "rollout needs n_envs, n_steps >= 1");
   IMB_REQUIRE(env->d_obs == pol->d_obs && env->d_act == pol->d_act && env->discrete == pol->discrete,
               "env / policy space mismatch");
@@ -31,6 +31,7 @@ extern "C" int imb_rollout(const imb_env_desc* env, const float* env_params, flo
   A.pol = *pol;
   A.hp = *hp;
   A.reward_mode = reward_mode;
+  A.deterministic = (flags & IMB_RF_DETERMINISTIC) ? 1 : 0;
   A.E = n_envs;
   A.T = n_steps;
   A.rw = imb_rollout_row_width(pol);

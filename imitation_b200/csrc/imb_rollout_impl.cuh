@@ -149,6 +149,7 @@ struct RolloutArgs {
   imb_policy_desc pol;
   imb_ppo_hparams hp;
   int reward_mode;
+  int deterministic;  // 1: act = mean (Box) / argmax (Discrete), like policy.predict(deterministic=True)
   int64_t E, T;
   int rw;             // rollout row width
   int64_t ring_capacity;
@@ -246,8 +247,9 @@ __global__ void __launch_bounds__(RT) k_rollout(const RolloutArgs A, const DiscL
         float m = psm[S.ba + a];
 #pragma unroll
         for (int j = 0; j < HP; ++j) m = fmaf(psm[S.wa + a * HP + j], lat[j], m);
-        const float z = noise ? noise[(t * E + e) * Da + a]
-                              : philox_normal(A.env.seed, IMB_STREAM_ACT_NOISE, egid, (uint32_t)(gstep0 + t), a);
+        const float z = A.deterministic ? 0.f
+                        : noise   ? noise[(t * E + e) * Da + a]
+                                  : philox_normal(A.env.seed, IMB_STREAM_ACT_NOISE, egid, (uint32_t)(gstep0 + t), a);
         const float ls = psm[S.lstd + a];
         const float sd = expf(ls);
         const float act = fmaf(sd, z, m);
@@ -286,6 +288,11 @@ __global__ void __launch_bounds__(RT) k_rollout(const RolloutArgs A, const DiscL
           chosen = a;
           found = true;
         }
+      }
+      if (A.deterministic) {
+        chosen = 0;
+        for (int a = 1; a < Da; ++a)
+          if (s_u[a] > s_u[chosen]) chosen = a;
       }
       logp = s_u[chosen] - lse;
       for (int a = 0; a < Da; ++a) s_u[a] = (a == chosen) ? 1.f : 0.f;

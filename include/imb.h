@@ -41,7 +41,8 @@ extern "C" {
 #define IMB_MAX_HIDDEN 64   /* hidden widths 1..64, at most 2 hidden layers */
 #define IMB_MAX_DIN 64      /* MLP input width 1..64 */
 #define IMB_F_ZERO_GRAD 1    /* imb_disc_fwd_bwd: clear the gradient accumulator first */
-#define IMB_F_TRAIN_NORM 2   /* imb_disc_fwd_bwd: Phi(s') uses the mid-update norm snapshot */
+#define IMB_F_TRAIN_NORM 2
+#define IMB_RF_DETERMINISTIC 1 /* imb_rollout flags: act = mean / argmax (policy.predict(deterministic=True)) */   /* imb_disc_fwd_bwd: Phi(s') uses the mid-update norm snapshot */
 
 /* One MLP: [RunningNorm?] -> Linear(din,h1) -> act -> [Linear(h1,h2) -> act] -> Linear(h_last,n_out).
  * util/networks.py:204-283 (build_mlp).  Parameter block (at `param_off` floats into the
@@ -214,13 +215,14 @@ typedef struct imb_ppo_hparams {
  * straight into the generator ring with Buffer.store truncation (buffer.py:174-192).
  * reward_mode: 0 = env reward (debug_use_ground_truth), 1 = GAIL -logsigmoid(-logit),
  * 2 = raw reward-net output (AIRL; normalise afterwards with imb_reward_norm_scan).
- * noise (optional, [T][E][d_act] normals or [T][E] uniforms) pins sampling for parity. */
+ * noise (optional, [T][E][d_act] normals or [T][E] uniforms) pins sampling for parity;
+ * flags: IMB_RF_DETERMINISTIC for evaluation rollouts (data/rollout.py:382-506). */
 int imb_rollout(const imb_env_desc* env, const float* env_params, float* env_obs,
                 const imb_policy_desc* pol, const float* pol_params, const float* pol_norm,
                 const imb_disc_desc* disc, const float* disc_params, const float* disc_norm,
                 int reward_mode, const imb_ppo_hparams* hp, int64_t n_envs, int64_t n_steps,
                 float* rollout, float* ring, int64_t ring_capacity, float* flat_out, float* aux,
-                const float* noise, const int64_t* state, void* stream);
+                const float* noise, int flags, const int64_t* state, void* stream);
 /* floats per rollout row: d_obs + (discrete ? 1 : d_act) + 5 (logp, value, reward, adv, ret);
  * aux needs 2*E + 2*E*T floats (V(last obs), last done, per-step time-limit bootstrap,
  * per-step ground-truth env reward). */
