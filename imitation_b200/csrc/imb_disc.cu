@@ -20,6 +20,7 @@
 //   k_disc_adam    torch.optim.Adam step + the 9 train statistics.
 #include "imb_common.cuh"
 #include "imb_mlp.cuh"
+#include "imb_tile.cuh"
 
 thread_local char g_imb_err[512] = {0};
 
@@ -28,7 +29,7 @@ extern "C" const char* imb_last_error(void) { return g_imb_err; }
 
 namespace {
 
-constexpr int NORM_CHUNK = 2048;      // rows per CTA in k_norm_stats
+constexpr int NORM_CHUNK = 512;       // rows per CTA in k_norm_stats
 constexpr int MAXG = 296;             // max CTAs of k_disc_fwdbwd (2 per SM)
 
 // ---- workspace layout (floats) -----------------------------------------------------------------
@@ -42,7 +43,7 @@ struct WsLayout {
   int64_t partial;   // [MAXG][P + 16]
   int64_t total;
 };
-constexpr int MAXCHUNKS = 4096;  // up to 8M rows per norm launch
+constexpr int MAXCHUNKS = 16384;  // up to 8M rows per norm launch
 __host__ __device__ inline int64_t part_stride(int P) { return (int64_t)((P + 16 + 31) / 32) * 32; }
 inline WsLayout ws_layout(int P) {
   WsLayout w;
@@ -148,115 +149,227 @@ __global__ void __launch_bounds__(256) k_norm_stats(NormLaunch L, const float* _
   }
 }
 
-template <int H>
-struct TileCfg {
-  static constexpr int R = (H == 32) ? 128 : 64;  // rows per tile
-  static constexpr int LD = H + 1;                // activation tile row stride (odd -> conflict-free)
+// ---- the fused forward / BCE / backward kernel (tiled-GEMM form, see imb_tile.cuh) ------------------
+// Shared-memory image of one MLP, hidden widths padded to JP (32 or 64), everything zero padded:
+//   W1t[din][JP] b1[JP] W2t[JP][JP] W2[JP][JP] b2[JP] wf[64] bf,pad[4] mean[64] istd[64]
+struct TImg {
+  __host__ __device__ static int w1t(int, int) { return 0; }
+  __host__ __device__ static int b1(int din, int JP) { return din * JP; }
+  __host__ __device__ static int w2t(int din, int JP) { return din * JP + JP; }
+  __host__ __device__ static int w2(int din, int JP) { return din * JP + JP + JP * JP; }
+  __host__ __device__ static int b2(int din, int JP) { return din * JP + JP + 2 * JP * JP; }
+  __host__ __device__ static int wf(int din, int JP) { return din * JP + 2 * JP + 2 * JP * JP; }
+  __host__ __device__ static int bf(int din, int JP) { return wf(din, JP) + 64; }
+  __host__ __device__ static int mean(int din, int JP) { return bf(din, JP) + 4; }
+  __host__ __device__ static int istd(int din, int JP) { return mean(din, JP) + 64; }
+  __host__ __device__ static int size(int din, int JP) { return istd(din, JP) + 64; }
 };
 
-// ---- the fused forward / BCE / backward kernel ---------------------------------------------------
-// Dynamic shared memory carve-up (floats):
-//   [mlp images for each distinct MLP][AW: P accumulators][xs: 2 stages x nstage x 128]
-//   [XN: R x xn_ld][H1: R x LD][H2: R x LD][DZ1: R x LD][gv: R][red: 32]
-template <int H>
-__global__ void __launch_bounds__(NT) k_disc_fwdbwd(const DiscLaunch L, const float* __restrict__ params,
-                                                   const float* __restrict__ batch, int64_t ld, int64_t n,
-                                                   int64_t n_expert, float loss_scale,
-                                                   const float* __restrict__ grad_out,
-                                                   float* __restrict__ logits_out, float* __restrict__ partial,
-                                                   int n_mlp_images, int img1_off, int aw_off, int xs_off,
-                                                   int xn_off, int xn_ld, int tiles_off) {
-  constexpr int R = TileCfg<H>::R;
-  constexpr int LD = TileCfg<H>::LD;
-  extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bars[2];
-  float* img[MAX_PASS];
-  img[0] = smem;
-  img[1] = smem + img1_off;  // potential image using pass-1 norm (Phi(s'))
-  img[2] = smem + img1_off;  // pass 2 shares weights; its norm constants live right after (see below)
-  float* AW = smem + aw_off;
-  float* xs = smem + xs_off;
-  float* XN = smem + xn_off;
-  float* H1 = smem + tiles_off;
-  float* H2 = H1 + R * LD;
-  float* DZ1 = H2 + R * LD;
-  float* gv = DZ1 + R * LD;
-  float* red = gv + R;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-  // -- one-time: weights -> smem, zero accumulators, init barriers -------------------------------
-  load_mlp<H>(img[0], L.pass[0], params);
-  // second normalisation table for Phi(s) (pass 2): stored after image 1
-  float* mean2 = nullptr;
-  float* istd2 = nullptr;
-  if (L.npass == 3) {
-    load_mlp<H>(img[1], L.pass[1], params);
-    const int din = L.pass[2].din;
-    mean2 = img[1] + MlpSm<H>::size(din);
-    istd2 = mean2 + IMB_MAX_DIN;
-    for (int i = tid; i < din; i += NT) {
-      if (L.pass[2].has_norm) {
-        mean2[i] = L.pass[2].norm[i];
-        istd2[i] = 1.0f / sqrtf(L.pass[2].norm[din + i] + L.pass[2].eps);
-      } else {
-        mean2[i] = 0.f;
-        istd2[i] = 1.f;
-      }
+__device__ void load_timg(float* sm, const PassDesc& p, int JP, const float* __restrict__ params,
+                          const float* __restrict__ norm, float eps) {
+  const int din = p.din, tid = threadIdx.x, nt = blockDim.x;
+  const float* q = params + p.param_off;
+  for (int i = tid; i < TImg::mean(din, JP); i += nt) sm[i] = 0.f;
+  __syncthreads();
+  int off = 0, hl = din;
+  if (p.n_hidden >= 1) {
+    for (int i = tid; i < p.h1 * din; i += nt) {
+      const int j = i / din, k = i - j * din;
+      sm[TImg::w1t(din, JP) + k * JP + j] = q[off + i];
     }
+    off += p.h1 * din;
+    for (int i = tid; i < p.h1; i += nt) sm[TImg::b1(din, JP) + i] = q[off + i];
+    off += p.h1;
+    hl = p.h1;
   }
-  for (int i = tid; i < L.P; i += NT) AW[i] = 0.f;
+  if (p.n_hidden >= 2) {
+    for (int i = tid; i < p.h2 * p.h1; i += nt) {
+      const int j = i / p.h1, ii = i - j * p.h1;
+      const float v = q[off + i];
+      sm[TImg::w2(din, JP) + j * JP + ii] = v;
+      sm[TImg::w2t(din, JP) + ii * JP + j] = v;
+    }
+    off += p.h2 * p.h1;
+    for (int i = tid; i < p.h2; i += nt) sm[TImg::b2(din, JP) + i] = q[off + i];
+    off += p.h2;
+    hl = p.h2;
+  }
+  for (int i = tid; i < hl; i += nt) sm[TImg::wf(din, JP) + i] = q[off + i];
+  off += hl;
+  if (tid == 0) sm[TImg::bf(din, JP)] = q[off];
+  for (int i = tid; i < din; i += nt) {
+    sm[TImg::mean(din, JP) + i] = norm ? norm[i] : 0.f;
+    sm[TImg::istd(din, JP) + i] = norm ? 1.0f / sqrtf(norm[din + i] + eps) : 1.f;
+  }
+}
+
+// Dynamic shared memory (floats):
+//   [image per pass][AW: 4 slices x P][stage: nstage x RS][XN: KP x RS][H1, H2, DZ1: JP x RS each]
+//   [lg, gv, gp, dv, lpv: R each]
+template <int R>
+__global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const float* __restrict__ params,
+                                                      const float* __restrict__ batch, int64_t ld, int64_t n,
+                                                      int64_t n_expert, float loss_scale,
+                                                      const float* __restrict__ grad_out,
+                                                      float* __restrict__ logits_out, float* __restrict__ partial,
+                                                      int JP, int KP, int img_sz, int aw_off, int st_off, int xn_off,
+                                                      int t_off, int v_off, int nsl) {
+  constexpr int NQ = R / 128;
+  constexpr int RS = R + TILE_PAD;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ float red[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* AW = smem + aw_off;
+  float* xs = smem + st_off;
+  float* XN = smem + xn_off;
+  float* H1 = smem + t_off;
+  float* H2 = H1 + JP * RS;
+  float* DZ1 = H2 + JP * RS;
+  float* lg = smem + v_off;
+  float* gv = lg + R;
+  float* gp = gv + R;
+  float* dv = gp + R;
+  float* lpv = dv + R;
+  const int P = L.P;
+
+  for (int p = 0; p < L.npass; ++p)
+    load_timg(smem + p * img_sz, L.pass[p], JP, params, L.pass[p].has_norm ? L.pass[p].norm : nullptr, L.pass[p].eps);
+  for (int i = tid; i < nsl * P; i += NT) AW[i] = 0.f;
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+    mbar_init(&bar, 1);
     mbar_fence_init();
   }
   __syncthreads();
 
   const int64_t ntiles = (n + R - 1) / R;
-  const uint32_t stage_bytes = (uint32_t)L.nstage * R * 4u;
-  auto issue = [&](int64_t tile, int stage) {
-    // one elected thread arms the barrier and issues one bulk copy per staged feature row
-    mbar_expect_tx(&bars[stage], stage_bytes);
-    float* dst = xs + (size_t)stage * L.nstage * XS_LD;
+  auto issue = [&](int64_t tile) {
+    int64_t cnt = ld - tile * R;  // floats available in each feature row from this tile's start
+    if (cnt > R) cnt = R;
+    mbar_expect_tx(&bar, (uint32_t)(L.nstage * cnt * 4));
     for (int s = 0; s < L.nstage; ++s)
-      bulk_g2s(dst + s * XS_LD, batch + (int64_t)L.stage_row[s] * ld + tile * R, R * 4u, &bars[stage]);
+      bulk_g2s(xs + s * RS, batch + (int64_t)L.stage_row[s] * ld + tile * R, (uint32_t)(cnt * 4), &bar);
   };
-  uint32_t phase[2] = {0u, 0u};
-  if (tid == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  uint32_t phase = 0;
+  if (tid == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x);
 
+  int rq[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) rq[q] = q * 128 + lane * 4;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float s_loss = 0.f, s_ent = 0.f;
   int c_exp = 0, c_gen = 0, c_pred_exp = 0;
 
-  int it = 0;
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const int stage = it & 1;
-    const int64_t next = tile + gridDim.x;
-    if (tid == 0 && next < ntiles) issue(next, stage ^ 1);  // prefetch while this tile computes
-    mbar_wait(&bars[stage], phase[stage]);
-    phase[stage] ^= 1u;
-    const float* x = xs + (size_t)stage * L.nstage * XS_LD;
-    const int64_t row = tile * R + tid;
-    const bool active = (tid < R) && (row < n);
-    const float done = (L.done_slot >= 0 && active) ? x[L.done_slot * XS_LD + tid] : 0.f;
-
-    // ---- logit: forward sweep over the passes (single pass: folded into phase A below) --------
-    float g = 0.f;  // dL/dlogit for this row
-    float h1[H], h2[H];
-    if (L.npass > 1) {
-      float logit = 0.f;
-      if (active) {
-        for (int p = 0; p < L.npass; ++p) {
-          const PassDesc& P = L.pass[p];
-          const float* mean = (p == 2) ? mean2 : img[p] + MlpSm<H>::mean_off(P.din);
-          const float* istd = (p == 2) ? istd2 : img[p] + MlpSm<H>::istd_off(P.din);
-          float* xn = XN + tid * xn_ld;
-          for (int k = 0; k < P.din; ++k) xn[k] = (x[P.in_slot[k] * XS_LD + tid] - mean[k]) * istd[k];
-          const float out = mlp_forward_row<H, false>(img[p], P, xn, h1, h2);
-          logit = fmaf(pass_coef(P.coef_kind, L.gamma, done), out, logit);
-        }
-        if (L.logp_slot >= 0) logit -= x[L.logp_slot * XS_LD + tid];
+  // one MLP forward over the tile for pass `p`: builds XN, H1, H2 and returns nothing; the per-row
+  // output is accumulated into lg[] (scaled by the pass coefficient) when `accumulate` is set.
+  auto forward_pass = [&](int p, int nv, bool accumulate, bool first) {
+    const PassDesc& Pd = L.pass[p];
+    const float* img = smem + p * img_sz;
+    const int din = Pd.din;
+    const float* mean = img + TImg::mean(din, JP);
+    const float* istd = img + TImg::istd(din, JP);
+    // normalised inputs, feature-major; rows >= nv and features >= din are zero
+    for (int i = tid; i < KP * (R / 4); i += NT) {
+      const int k = i / (R / 4), r4 = (i - k * (R / 4)) * 4;
+      float4 v = zero4;
+      if (k < din) {
+        const float4 x = ld4(xs + Pd.in_slot[k] * RS + r4);
+        const float m = mean[k], is = istd[k];
+        v.x = (r4 + 0 < nv) ? (x.x - m) * is : 0.f;
+        v.y = (r4 + 1 < nv) ? (x.y - m) * is : 0.f;
+        v.z = (r4 + 2 < nv) ? (x.z - m) * is : 0.f;
+        v.w = (r4 + 3 < nv) ? (x.w - m) * is : 0.f;
       }
-      if (active) {
+      st4(XN + k * RS + r4, v);
+    }
+    __syncthreads();
+    const float* HL = XN;
+    int hl = din;
+    float4 gq[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) gq[q] = zero4;
+    if (Pd.n_hidden >= 1) {
+      for (int jh = 0; jh < JP / 32; ++jh) {
+        const int j0 = jh * 32 + warp * 8;
+        float acc[NQ * 4][8];
+#pragma unroll
+        for (int a = 0; a < NQ * 4; ++a)
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[a][t] = 0.f;
+        gemm_acc<NQ, false>(acc, XN, RS, rq, img + TImg::w1t(din, JP), JP, j0, din, gq, nullptr);
+        const float* b1 = img + TImg::b1(din, JP);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float b = b1[j0 + t];
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            st4(H1 + (j0 + t) * RS + rq[q],
+                make_float4(fmaxf(acc[q * 4 + 0][t] + b, 0.f), fmaxf(acc[q * 4 + 1][t] + b, 0.f),
+                            fmaxf(acc[q * 4 + 2][t] + b, 0.f), fmaxf(acc[q * 4 + 3][t] + b, 0.f)));
+        }
+      }
+      __syncthreads();
+      HL = H1;
+      hl = Pd.h1;
+    }
+    if (Pd.n_hidden >= 2) {
+      for (int jh = 0; jh < JP / 32; ++jh) {
+        const int j0 = jh * 32 + warp * 8;
+        float acc[NQ * 4][8];
+#pragma unroll
+        for (int a = 0; a < NQ * 4; ++a)
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc[a][t] = 0.f;
+        gemm_acc<NQ, false>(acc, H1, RS, rq, img + TImg::w2t(din, JP), JP, j0, Pd.h1, gq, nullptr);
+        const float* b2 = img + TImg::b2(din, JP);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const float b = b2[j0 + t];
+#pragma unroll
+          for (int q = 0; q < NQ; ++q)
+            st4(H2 + (j0 + t) * RS + rq[q],
+                make_float4(fmaxf(acc[q * 4 + 0][t] + b, 0.f), fmaxf(acc[q * 4 + 1][t] + b, 0.f),
+                            fmaxf(acc[q * 4 + 2][t] + b, 0.f), fmaxf(acc[q * 4 + 3][t] + b, 0.f)));
+        }
+      }
+      __syncthreads();
+      HL = H2;
+      hl = Pd.h2;
+    }
+    if (accumulate) {
+      const float* wf = img + TImg::wf(din, JP);
+      const float bf = img[TImg::bf(din, JP)];
+      for (int r = tid; r < R; r += NT) {
+        float o = bf;
+        for (int j = 0; j < hl; ++j) o = fmaf(wf[j], HL[j * RS + r], o);
+        const float c = pass_coef(Pd.coef_kind, L.gamma, dv[r]);
+        lg[r] = first ? c * o : fmaf(c, o, lg[r]);
+      }
+      __syncthreads();
+    }
+  };
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(&bar, phase);
+    phase ^= 1u;
+    const int nv = (int)min((int64_t)R, n - tile * R);
+    for (int r = tid; r < R; r += NT) {
+      dv[r] = (L.done_slot >= 0 && r < nv) ? xs[L.done_slot * RS + r] : 0.f;
+      lpv[r] = (L.logp_slot >= 0 && r < nv) ? xs[L.logp_slot * RS + r] : 0.f;
+    }
+    __syncthreads();
+    // ---- logits: forward over all passes (the last pass's tiles stay valid for its backward) -------
+    for (int p = 0; p < L.npass; ++p) forward_pass(p, nv, true, p == 0);
+    // stage is free once the last forward that reads it is done -- unless passes are recomputed below
+    const bool recompute = L.npass > 1;
+    const int64_t next = tile + gridDim.x;
+    if (!recompute && tid == 0 && next < ntiles) issue(next);
+    // ---- dL/dlogit per row + statistics -------------------------------------------------------------
+    for (int r = tid; r < R; r += NT) {
+      float g = 0.f;
+      if (r < nv) {
+        const int64_t row = tile * R + r;
+        const float logit = lg[r] - lpv[r];
         if (logits_out) logits_out[row] = logit;
         if (grad_out) {
           g = grad_out[row];
@@ -272,199 +385,157 @@ __global__ void __launch_bounds__(NT) k_disc_fwdbwd(const DiscLaunch L, const fl
           g = (sg - y) * loss_scale;
         }
       }
+      gv[r] = g;
     }
+    __syncthreads();
 
-    for (int p = 0; p < L.npass; ++p) {
-      const PassDesc& P = L.pass[p];
-      const float* sm = img[p];
-      const float* mean = (p == 2) ? mean2 : sm + MlpSm<H>::mean_off(P.din);
-      const float* istd = (p == 2) ? istd2 : sm + MlpSm<H>::istd_off(P.din);
-      // ---------------- phase A: thread per row ------------------------------------------------
-      float gp = 0.f;
-      if (active) {
-        float* xn = XN + tid * xn_ld;
-        for (int k = 0; k < P.din; ++k) xn[k] = (x[P.in_slot[k] * XS_LD + tid] - mean[k]) * istd[k];
-        const float out = mlp_forward_row<H, true>(sm, P, xn, h1, h2);
-        if (L.npass == 1) {
-          float logit = out;
-          if (L.logp_slot >= 0) logit -= x[L.logp_slot * XS_LD + tid];
-          if (logits_out) logits_out[row] = logit;
-          if (grad_out) {
-            g = grad_out[row];
-          } else {
-            const float y = (row < n_expert) ? 1.f : 0.f;
-            const float sg = sigmoid_f(logit);
-            const float sp = fmaxf(logit, 0.f) + log1pf(expf(-fabsf(logit)));
-            s_loss += sp - logit * y;
-            s_ent += sp - logit * sg;
-            const bool pred_exp = !(logit < 0.f);
-            c_pred_exp += pred_exp;
-            if (y > 0.5f) c_exp += pred_exp; else c_gen += !pred_exp;
-            g = (sg - y) * loss_scale;
-          }
-        }
-        gp = g * pass_coef(P.coef_kind, L.gamma, done);
-        // backward to dL/dz1 (and keep h1, h2 for the weight gradients)
-        const float* wf = sm + MlpSm<H>::wf_off(P.din);
-        if (P.n_hidden == 2) {
-          const float* W2 = sm + MlpSm<H>::w2_off(P.din);
-          float dz1[H];
+    // ---- backward + weight gradients, pass by pass ---------------------------------------------------
+    for (int pi = 0; pi < L.npass; ++pi) {
+      const int p = L.npass - 1 - pi;  // last pass first: its forward tiles are still in shared memory
+      if (pi > 0) forward_pass(p, nv, false, false);
+      if (recompute && pi == L.npass - 1 && tid == 0 && next < ntiles) issue(next);
+      const PassDesc& Pd = L.pass[p];
+      const float* img = smem + p * img_sz;
+      const int din = Pd.din;
+      const float* wf = img + TImg::wf(din, JP);
+      for (int r = tid; r < R; r += NT) gp[r] = gv[r] * pass_coef(Pd.coef_kind, L.gamma, dv[r]);
+      __syncthreads();
+      float* A0 = AW;  // slice 0 accumulators
+      const int h1w = Pd.h1, h2w = Pd.h2;
+      const int off_w1 = Pd.param_off, off_b1 = off_w1 + h1w * din, off_w2 = off_b1 + h1w;
+      const int off_b2 = off_w2 + ((Pd.n_hidden == 2) ? h2w * h1w : 0);
+      const int off_wf = (Pd.n_hidden == 2) ? off_b2 + h2w : (Pd.n_hidden == 1 ? off_w2 : Pd.param_off);
+      const int hl = (Pd.n_hidden == 2) ? h2w : (Pd.n_hidden == 1 ? h1w : din);
+      const float* HL = (Pd.n_hidden == 2) ? H2 : (Pd.n_hidden == 1 ? H1 : XN);
+      // dL/dz1 tile
+      if (Pd.n_hidden == 2) {
+        float4 gq[NQ];
 #pragma unroll
-          for (int i = 0; i < H; ++i) dz1[i] = 0.f;
+        for (int q = 0; q < NQ; ++q) gq[q] = ld4(gp + rq[q]);
+        for (int jh = 0; jh < JP / 32; ++jh) {
+          const int i0 = jh * 32 + warp * 8;
+          float acc[NQ * 4][8];
 #pragma unroll
-          for (int j = 0; j < H; ++j) {
-            const float dz2 = (h2[j] > 0.f) ? gp * wf[j] : 0.f;
-            const float4* w = reinterpret_cast<const float4*>(W2 + j * H);
+          for (int a = 0; a < NQ * 4; ++a)
 #pragma unroll
-            for (int i4 = 0; i4 < H / 4; ++i4) {
-              const float4 ww = w[i4];
-              dz1[4 * i4 + 0] = fmaf(ww.x, dz2, dz1[4 * i4 + 0]);
-              dz1[4 * i4 + 1] = fmaf(ww.y, dz2, dz1[4 * i4 + 1]);
-              dz1[4 * i4 + 2] = fmaf(ww.z, dz2, dz1[4 * i4 + 2]);
-              dz1[4 * i4 + 3] = fmaf(ww.w, dz2, dz1[4 * i4 + 3]);
+            for (int t = 0; t < 8; ++t) acc[a][t] = 0.f;
+          gemm_acc<NQ, true>(acc, H2, RS, rq, img + TImg::w2(din, JP), JP, i0, h2w, gq, wf);
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+              const float4 h = ld4(H1 + (i0 + t) * RS + rq[q]);
+              st4(DZ1 + (i0 + t) * RS + rq[q],
+                  make_float4(h.x > 0.f ? acc[q * 4 + 0][t] : 0.f, h.y > 0.f ? acc[q * 4 + 1][t] : 0.f,
+                              h.z > 0.f ? acc[q * 4 + 2][t] : 0.f, h.w > 0.f ? acc[q * 4 + 3][t] : 0.f));
             }
-          }
-#pragma unroll
-          for (int i = 0; i < H; ++i) {
-            H1[tid * LD + i] = h1[i];
-            H2[tid * LD + i] = h2[i];
-            DZ1[tid * LD + i] = (h1[i] > 0.f) ? dz1[i] : 0.f;
-          }
-        } else if (P.n_hidden == 1) {
-#pragma unroll
-          for (int i = 0; i < H; ++i) {
-            H1[tid * LD + i] = h1[i];
-            DZ1[tid * LD + i] = (h1[i] > 0.f) ? gp * wf[i] : 0.f;
-          }
         }
-      } else if (tid < R) {
-        // inactive (padding) rows contribute zeros
-        float* xn = XN + tid * xn_ld;
-        for (int k = 0; k < P.din; ++k) xn[k] = 0.f;
-#pragma unroll
-        for (int i = 0; i < H; ++i) {
-          H1[tid * LD + i] = 0.f;
-          H2[tid * LD + i] = 0.f;
-          DZ1[tid * LD + i] = 0.f;
+      } else if (Pd.n_hidden == 1) {
+        for (int i = tid; i < JP * (R / 4); i += NT) {
+          const int j = i / (R / 4), r4 = (i - j * (R / 4)) * 4;
+          const float4 h = ld4(H1 + j * RS + r4), g = ld4(gp + r4);
+          const float w = wf[j];
+          st4(DZ1 + j * RS + r4, make_float4(h.x > 0.f ? g.x * w : 0.f, h.y > 0.f ? g.y * w : 0.f,
+                                             h.z > 0.f ? g.z * w : 0.f, h.w > 0.f ? g.w * w : 0.f));
         }
       }
-      if (tid < R) gv[tid] = gp;
       __syncthreads();
-
-      // ---------------- phase B: weight gradients, warps split the output columns ----------------
-      float* A = AW + P.param_off;
-      const int din = P.din;
-      constexpr int JW = H / 4;  // output units per warp
-      const int j0 = warp * JW;
-      if (P.n_hidden == 0) {
-        // dwf[k] = sum_r g_r xn[r][k]; dbf = sum_r g_r
-        for (int k = tid; k <= din; k += NT) {
-          float acc = 0.f;
-          if (k < din) {
-            for (int r = 0; r < R; ++r) acc = fmaf(gv[r], XN[r * xn_ld + k], acc);
-          } else {
-            for (int r = 0; r < R; ++r) acc += gv[r];
+      const int jl = lane & 7, il = lane >> 3;
+      // dW2 / db2
+      if (Pd.n_hidden == 2) {
+        const int nblk = (JP / 32) * (JP / 32), ntl = nblk * 32, slices = NT / ntl;
+        const int lt = tid % ntl, sl = tid / ntl, blk = lt >> 5;
+        const int jb = (blk % (JP / 32)) * 32, ib = (blk / (JP / 32)) * 32;
+        if (sl < slices) {
+          float acc[4][8], bacc[4], sj[4];
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            bacc[jj] = 0.f;
+            sj[jj] = wf[jb + jl + 8 * jj];
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = 0.f;
           }
-          A[k] += acc;
-        }
-      } else {
-        const int h1w = P.h1;
-        int off_w1 = 0, off_b1 = h1w * din, off_w2 = off_b1 + h1w;
-        int off_b2 = off_w2 + ((P.n_hidden == 2) ? P.h2 * h1w : 0);
-        int off_wf = (P.n_hidden == 2) ? off_b2 + P.h2 : off_w2;
-        const int hl = (P.n_hidden == 2) ? P.h2 : h1w;
-        // (1) dW1[j][k] = sum_r dz1[r][j] xn[r][k];  db1[j] = sum_r dz1[r][j]
-        {
-          float acc[JW][2];
-          float bs[JW];
+          const int rows = R / slices;
+          wgrad_acc<true>(acc, bacc, H2, H1, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, gp, sj);
+          float* A = A0 + sl * P;
 #pragma unroll
-          for (int jj = 0; jj < JW; ++jj) {
-            acc[jj][0] = acc[jj][1] = 0.f;
-            bs[jj] = 0.f;
-          }
-          const bool k0ok = lane < din, k1ok = (lane + 32) < din;
-          for (int r = 0; r < R; ++r) {
-            const float a0 = k0ok ? XN[r * xn_ld + lane] : 0.f;
-            const float a1 = k1ok ? XN[r * xn_ld + lane + 32] : 0.f;
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = jb + jl + 8 * jj;
+            if (j < h2w) {
 #pragma unroll
-            for (int jj = 0; jj < JW; ++jj) {
-              const float dz = DZ1[r * LD + j0 + jj];
-              acc[jj][0] = fmaf(dz, a0, acc[jj][0]);
-              acc[jj][1] = fmaf(dz, a1, acc[jj][1]);
-              bs[jj] += dz;
-            }
-          }
-#pragma unroll
-          for (int jj = 0; jj < JW; ++jj) {
-            const int j = j0 + jj;
-            if (j < h1w) {
-              if (k0ok) A[off_w1 + j * din + lane] += acc[jj][0];
-              if (k1ok) A[off_w1 + j * din + lane + 32] += acc[jj][1];
-              if (lane == 0) A[off_b1 + j] += bs[jj];
-            }
-          }
-        }
-        // (2) dW2[j][i] = sum_r dz2[r][j] h1[r][i];  db2[j] = sum_r dz2[r][j]
-        if (P.n_hidden == 2) {
-          const float* wf = sm + MlpSm<H>::wf_off(din);
-          float wfr[JW];
-#pragma unroll
-          for (int jj = 0; jj < JW; ++jj) wfr[jj] = wf[j0 + jj];
-          float acc[JW][H / 32];
-          float bs[JW];
-#pragma unroll
-          for (int jj = 0; jj < JW; ++jj) {
-#pragma unroll
-            for (int ii = 0; ii < H / 32; ++ii) acc[jj][ii] = 0.f;
-            bs[jj] = 0.f;
-          }
-          for (int r = 0; r < R; ++r) {
-            const float gr = gv[r];
-            float a[H / 32];
-#pragma unroll
-            for (int ii = 0; ii < H / 32; ++ii) a[ii] = H1[r * LD + lane + 32 * ii];
-#pragma unroll
-            for (int jj = 0; jj < JW; ++jj) {
-              const float dz2 = (H2[r * LD + j0 + jj] > 0.f) ? gr * wfr[jj] : 0.f;
-#pragma unroll
-              for (int ii = 0; ii < H / 32; ++ii) acc[jj][ii] = fmaf(dz2, a[ii], acc[jj][ii]);
-              bs[jj] += dz2;
-            }
-          }
-#pragma unroll
-          for (int jj = 0; jj < JW; ++jj) {
-            const int j = j0 + jj;
-            if (j < P.h2) {
-#pragma unroll
-              for (int ii = 0; ii < H / 32; ++ii) {
-                const int i = lane + 32 * ii;
+              for (int ii = 0; ii < 8; ++ii) {
+                const int i = ib + il + 4 * ii;
                 if (i < h1w) A[off_w2 + j * h1w + i] += acc[jj][ii];
               }
-              if (lane == 0) A[off_b2 + j] += bs[jj];
+              if (il == 0 && ib == 0) A[off_b2 + j] += bacc[jj];
             }
           }
         }
-        // (3) dwf[j] = sum_r g_r hlast[r][j];  dbf = sum_r g_r
-        {
-          const float* HL = (P.n_hidden == 2) ? H2 : H1;
-          for (int j = tid; j <= hl; j += NT) {
-            float acc = 0.f;
-            if (j < hl) {
-              for (int r = 0; r < R; ++r) acc = fmaf(gv[r], HL[r * LD + j], acc);
-            } else {
-              for (int r = 0; r < R; ++r) acc += gv[r];
-            }
-            A[off_wf + j] += acc;
+      }
+      // dW1 / db1
+      if (Pd.n_hidden >= 1) {
+        const int nblk = (JP / 32) * (KP / 32), ntl = nblk * 32, slices = NT / ntl;
+        const int lt = tid % ntl, sl = tid / ntl, blk = lt >> 5;
+        const int jb = (blk % (JP / 32)) * 32, ib = (blk / (JP / 32)) * 32;
+        if (sl < slices) {
+          float acc[4][8], bacc[4];
+          const float sj[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            bacc[jj] = 0.f;
+#pragma unroll
+            for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = 0.f;
           }
+          const int rows = R / slices;
+          wgrad_acc<false>(acc, bacc, DZ1, XN, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, nullptr, sj);
+          float* A = A0 + sl * P;
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = jb + jl + 8 * jj;
+            if (j < h1w) {
+#pragma unroll
+              for (int ii = 0; ii < 8; ++ii) {
+                const int k = ib + il + 4 * ii;
+                if (k < din) A[off_w1 + j * din + k] += acc[jj][ii];
+              }
+              if (il == 0 && ib == 0) A[off_b1 + j] += bacc[jj];
+            }
+          }
+        }
+      }
+      // dwf / dbf: thread j sums its feature row against gp (slice 1 accumulators keep owners unique)
+      {
+        float* A = A0 + 1 * P;
+        for (int j = tid; j <= hl; j += NT) {
+          float acc = 0.f;
+          if (j < hl) {
+            for (int r = 0; r < R; r += 4) {
+              const float4 h = ld4(HL + j * RS + r), g = ld4(gp + r);
+              acc = fmaf(h.x, g.x, acc);
+              acc = fmaf(h.y, g.y, acc);
+              acc = fmaf(h.z, g.z, acc);
+              acc = fmaf(h.w, g.w, acc);
+            }
+          } else {
+            for (int r = 0; r < R; r += 4) {
+              const float4 g = ld4(gp + r);
+              acc += (g.x + g.y) + (g.z + g.w);
+            }
+          }
+          A[off_wf + j] += acc;
         }
       }
       __syncthreads();
     }
   }
 
-  // ---- per-CTA partials: gradients + statistics -------------------------------------------------
-  float* my = partial + (int64_t)blockIdx.x * part_stride(L.P);
-  for (int i = tid; i < L.P; i += NT) my[i] = AW[i];
+  // ---- per-CTA partials: gradients (slices summed in fixed order) + statistics ----------------------
+  float* my = partial + (int64_t)blockIdx.x * part_stride(P);
+  for (int i = tid; i < P; i += NT) {
+    float v = AW[i];
+    for (int s2 = 1; s2 < nsl; ++s2) v += AW[s2 * P + i];
+    my[i] = v;
+  }
   s_loss = warp_sum(s_loss);
   s_ent = warp_sum(s_ent);
   c_exp = warp_sum_i(c_exp);
@@ -481,7 +552,7 @@ __global__ void __launch_bounds__(NT) k_disc_fwdbwd(const DiscLaunch L, const fl
   if (tid < 5) {
     float v = 0.f;
     for (int w = 0; w < NT / 32; ++w) v += red[w * 5 + tid];
-    my[L.P + tid] = v;
+    my[P + tid] = v;
   }
 }
 
@@ -670,13 +741,11 @@ __global__ void __launch_bounds__(1024) k_reward_norm_scan(float* __restrict__ r
 // ---- host-side launch helpers -----------------------------------------------------------------
 template <int H>
 struct SmemPlan {
-  int img1_off, aw_off, xs_off, xn_off, xn_ld, tiles_off, total_floats;
+  int img1_off, xn_off, xn_ld, total_floats;
 };
 template <int H>
-SmemPlan<H> plan_smem(const DiscLaunch& L, bool train) {
+SmemPlan<H> plan_smem(const DiscLaunch& L, bool) {
   SmemPlan<H> s;
-  constexpr int R = TileCfg<H>::R;
-  constexpr int LD = TileCfg<H>::LD;
   auto al = [](int x) { return (x + 31) / 32 * 32; };
   int o = al(MlpSm<H>::size(L.pass[0].din));
   s.img1_off = o;
@@ -684,20 +753,8 @@ SmemPlan<H> plan_smem(const DiscLaunch& L, bool train) {
   int maxdin = 0;
   for (int p = 0; p < L.npass; ++p) maxdin = L.pass[p].din > maxdin ? L.pass[p].din : maxdin;
   s.xn_ld = maxdin | 1;
-  if (train) {
-    s.aw_off = o;
-    o += al(L.P);
-    s.xs_off = o;
-    o += al(2 * L.nstage * XS_LD);
-    s.xn_off = o;
-    o += al(R * s.xn_ld);
-    s.tiles_off = o;
-    o += al(3 * R * LD + R + 32);
-  } else {
-    s.aw_off = s.xs_off = s.tiles_off = 0;
-    s.xn_off = o;
-    o += al(NT * s.xn_ld);
-  }
+  s.xn_off = o;
+  o += al(NT * s.xn_ld);
   s.total_floats = o;
   return s;
 }
@@ -752,31 +809,57 @@ extern "C" int imb_disc_norm_update(const imb_disc_desc* d, const float* batch, 
   return 0;
 }
 
-template <int H>
-static int launch_fwdbwd(const DiscLaunch& L, const float* params, const float* batch, int64_t ld, int64_t n,
-                         int64_t n_expert, float loss_scale, const float* grad_out, float* logits_out, float* ws,
-                         const WsLayout& w, cudaStream_t st) {
-  constexpr int R = TileCfg<H>::R;
-  const SmemPlan<H> s = plan_smem<H>(L, true);
-  const size_t bytes = (size_t)s.total_floats * 4;
-  IMB_REQUIRE(bytes <= IMB_SMEM_MAX, "discriminator too large for the fused kernel (%zu B smem)", bytes);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_disc_fwdbwd<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, IMB_SMEM_MAX);
-    if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+struct TPlan {
+  int JP, KP, img_sz, aw_off, st_off, xn_off, t_off, v_off, nsl, total;
+};
+static TPlan plan_tiled(const DiscLaunch& L, int R) {
+  TPlan t;
+  auto al = [](int x) { return (x + 31) / 32 * 32; };
+  const int RS = R + TILE_PAD;
+  int h = 1, dmax = 1;
+  for (int p = 0; p < L.npass; ++p) {
+    if (L.pass[p].n_hidden >= 1 && L.pass[p].h1 > h) h = L.pass[p].h1;
+    if (L.pass[p].n_hidden >= 2 && L.pass[p].h2 > h) h = L.pass[p].h2;
+    if (L.pass[p].din > dmax) dmax = L.pass[p].din;
+  }
+  t.JP = h <= 32 ? 32 : 64;
+  t.KP = dmax <= 32 ? 32 : 64;
+  t.img_sz = al(TImg::size(dmax, t.JP));
+  int o = L.npass * t.img_sz;
+  t.nsl = t.JP == 32 ? 4 : 2;  // row slices of the weight-gradient phase (>= 2: slice 1 holds dwf)
+  t.aw_off = o;
+  o += al(t.nsl * L.P);
+  t.st_off = o;
+  o += al(L.nstage * RS);
+  t.xn_off = o;
+  o += al(t.KP * RS);
+  t.t_off = o;
+  o += al(3 * t.JP * RS);
+  t.v_off = o;
+  o += al(5 * R);
+  t.total = o;
+  return t;
+}
+
+template <int R>
+static int launch_fwdbwd(const DiscLaunch& L, const TPlan& t, const float* params, const float* batch, int64_t ld,
+                         int64_t n, int64_t n_expert, float loss_scale, const float* grad_out, float* logits_out,
+                         float* ws, const WsLayout& w, cudaStream_t st) {
+  const size_t bytes = (size_t)t.total * 4;
+  static size_t attr_bytes = 0;
+  if (bytes > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k_disc_fwdbwd<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute(%zu): %s", bytes, cudaGetErrorString(e));
+    attr_bytes = bytes;
   }
   const int64_t ntiles = (n + R - 1) / R;
-  int per_sm = (int)((IMB_SMEM_MAX) / (bytes + 1024));
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;
-  int64_t G = (int64_t)imb_num_sms() * per_sm;
+  int64_t G = imb_num_sms();
   if (G > MAXG) G = MAXG;
   if (G > ntiles) G = ntiles;
   k_set_meta<<<1, 1, 0, st>>>(reinterpret_cast<int*>(ws + w.meta), (int)G, n, n_expert, loss_scale);
-  k_disc_fwdbwd<H><<<(int)G, NT, bytes, st>>>(L, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
-                                               ws + w.partial, L.npass, s.img1_off, s.aw_off, s.xs_off, s.xn_off,
-                                               s.xn_ld, s.tiles_off);
+  k_disc_fwdbwd<R><<<(int)G, NT, bytes, st>>>(L, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
+                                               ws + w.partial, t.JP, t.KP, t.img_sz, t.aw_off, t.st_off, t.xn_off,
+                                               t.t_off, t.v_off, t.nsl);
   IMB_CHECK_LAUNCH("k_disc_fwdbwd");
   return (int)G;
 }
@@ -800,10 +883,15 @@ extern "C" int imb_disc_fwd_bwd(const imb_disc_desc* d, const float* params, con
     cudaError_t e = cudaMemsetAsync(ws + w.gacc, 0, sizeof(float) * d->n_params, st);
     if (e != cudaSuccess) IMB_FAIL(-2, "memset: %s", cudaGetErrorString(e));
   }
-  int G = (pick_H(L) == 32) ? launch_fwdbwd<32>(L, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
-                                                ws, w, st)
-                            : launch_fwdbwd<64>(L, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
-                                                ws, w, st);
+  // 256-row tiles when they fit in shared memory (and the batch has that many rows), else 128
+  TPlan t256 = plan_tiled(L, 256), t128 = plan_tiled(L, 128);
+  int G;
+  if ((size_t)t256.total * 4 <= IMB_SMEM_MAX && n > 128)
+    G = launch_fwdbwd<256>(L, t256, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, ws, w, st);
+  else if ((size_t)t128.total * 4 <= IMB_SMEM_MAX)
+    G = launch_fwdbwd<128>(L, t128, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, ws, w, st);
+  else
+    IMB_FAIL(-1, "discriminator too large for the fused kernel (%zu B of shared memory)", (size_t)t128.total * 4);
   if (G < 0) return G;
   g_last_grid = G;
   return 0;

@@ -12,16 +12,13 @@
 // Also: imb_policy_logp = ActorCriticPolicy.evaluate_actions()[1] for the AIRL discriminator
 // batch (common.py:476-519).
 #include "imb_common.cuh"
+#include "imb_tile.cuh"
 
 namespace {
 
-constexpr int PT = 256;  // threads: warps 0-3 = policy tower, warps 4-7 = value tower
-
-template <int HP>
-struct PpoCfg {
-  static constexpr int MBR = (HP == 32) ? 128 : 64;  // max minibatch rows
-  static constexpr int LD = HP + 1;
-};
+constexpr int PT = 256;   // threads: 0..127 = policy tower, 128..255 = value tower
+constexpr int PR = 64;    // minibatch rows per step (SB3 batch_size <= 64)
+constexpr int PRS = PR + TILE_PAD;
 
 struct PpoArgs {
   imb_policy_desc pol;
@@ -30,7 +27,7 @@ struct PpoArgs {
   int rw;
   uint64_t seed;
   int moments_in_smem;
-  int mbr;  // minibatch rows the shared-memory tiles are sized for (batch_size rounded up to 32)
+  int HP, KP, slices;  // tower width / obs width padded to 32; row slices of the weight-gradient phase
 };
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -46,74 +43,76 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-// transposed working images rebuilt from the master parameters after every optimiser step
-template <int HP>
-__device__ void build_images(const imb_policy_desc& pd, const float* __restrict__ Pm, float* __restrict__ w1t_pi,
-                             float* __restrict__ w2t_pi, float* __restrict__ w1t_vf, float* __restrict__ w2t_vf) {
+// working images rebuilt from the master parameters after every optimiser step; per tower:
+//   W1t[KP][HP] (k-major for layer 1), W2t[HP][HP] (k = input unit), W2p[HP][HP] (torch layout, padded)
+__device__ void build_images(const imb_policy_desc& pd, const float* __restrict__ Pm, float* __restrict__ img,
+                             int HP, int KP) {
   const int Do = pd.d_obs, h = pd.hidden;
+  const int tsz = KP * HP + 2 * HP * HP;
   for (int i = threadIdx.x; i < h * Do; i += PT) {
     const int j = i / Do, k = i - j * Do;
-    w1t_pi[k * HP + j] = Pm[pd.off_pi_w1 + i];
-    w1t_vf[k * HP + j] = Pm[pd.off_vf_w1 + i];
+    img[k * HP + j] = Pm[pd.off_pi_w1 + i];
+    img[tsz + k * HP + j] = Pm[pd.off_vf_w1 + i];
   }
   for (int i = threadIdx.x; i < h * h; i += PT) {
     const int j = i / h, ii = i - j * h;
-    w2t_pi[ii * HP + j] = Pm[pd.off_pi_w2 + i];
-    w2t_vf[ii * HP + j] = Pm[pd.off_vf_w2 + i];
+    const float a = Pm[pd.off_pi_w2 + i], b = Pm[pd.off_vf_w2 + i];
+    img[KP * HP + ii * HP + j] = a;
+    img[KP * HP + HP * HP + j * HP + ii] = a;
+    img[tsz + KP * HP + ii * HP + j] = b;
+    img[tsz + KP * HP + HP * HP + j * HP + ii] = b;
   }
 }
 
-template <int HP>
 __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __restrict__ g_params,
                                                       float* __restrict__ g_norm, int32_t* __restrict__ g_norm_count,
                                                       float* __restrict__ g_m, float* __restrict__ g_v,
                                                       const float* __restrict__ rollout,
                                                       const int64_t* __restrict__ perm_in,
                                                       float* __restrict__ loss_log, int64_t* __restrict__ state) {
-  constexpr int LD = PpoCfg<HP>::LD;
-  const int MBR = A.mbr;
   extern __shared__ __align__(128) float smem[];
   __shared__ float red[32];
   __shared__ float bc[8];
   const imb_policy_desc& pd = A.pol;
-  const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params;
+  const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params, HP = A.HP, KP = A.KP;
   const int da_store = pd.discrete ? 1 : Da;
-  const int col_act = Do, col_logp = Do + da_store, col_adv = col_logp + 3, col_ret = col_logp + 4;
+  const int col_logp = Do + da_store, col_adv = col_logp + 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int net = tid >> 7, tt = tid & 127;  // tower, thread within tower
   auto al = [](int x) { return (x + 31) / 32 * 32; };
 
   // ---- shared-memory carve-up ---------------------------------------------------------------------------
   int o = 0;
   float* Pm = smem + o; o += al(NP);
   float* G = smem + o; o += al(NP);
+  float* GS = smem + o; o += A.slices * al(NP);  // per-slice weight gradients (deterministic sum)
   float* Mm = g_m;
   float* Vm = g_v;
   if (A.moments_in_smem) {
     Mm = smem + o; o += al(NP);
     Vm = smem + o; o += al(NP);
   }
-  float* w1t_pi = smem + o; o += al(Do * HP);
-  float* w2t_pi = smem + o; o += al(HP * HP);
-  float* w1t_vf = smem + o; o += al(Do * HP);
-  float* w2t_vf = smem + o; o += al(HP * HP);
-  const int xn_ld = Do | 1;
-  float* XN = smem + o; o += al(MBR * xn_ld);
-  const int mb_ld = (da_store + 3) | 1;  // act | logp_old | adv | ret
-  float* MB = smem + o; o += al(MBR * mb_ld);
-  float* T_H1[2], *T_LAT[2], *T_DZ2[2], *T_DZ1[2];
-  for (int n = 0; n < 2; ++n) {
-    T_H1[n] = smem + o; o += MBR * LD;
-    T_LAT[n] = smem + o; o += MBR * LD;
-    T_DZ2[n] = smem + o; o += MBR * LD;
-    T_DZ1[n] = smem + o; o += MBR * LD;
-  }
-  const int dm_ld = Da | 1;
-  float* DMEAN = smem + o; o += al(MBR * dm_ld);  // dL/d(action mean or logits) per row
-  float* DLS = smem + o; o += al(MBR * dm_ld);    // dL/d(log_std) per row (Box)
-  float* DVAL = smem + o; o += al(MBR);           // dL/d(value) per row
-  float* nmean = smem + o; o += al(Do);
-  float* nistd = smem + o; o += al(Do);
-  int* s_idx = reinterpret_cast<int*>(smem + o); o += al(MBR);
+  const int tsz = KP * HP + 2 * HP * HP;
+  float* img = smem + o; o += al(2 * tsz);
+  float* XN = smem + o; o += al(KP * PRS);
+  float* TH1 = smem + o; o += 2 * HP * PRS;   // [tower][HP][PRS]
+  float* TLAT = smem + o; o += 2 * HP * PRS;
+  float* TDZ2 = smem + o; o += 2 * HP * PRS;
+  float* TDZ1 = smem + o; o += 2 * HP * PRS;
+  const int DAP = (Da + 3) / 4 * 4;
+  float* DM = smem + o; o += al(DAP * PRS);    // dL/d(mean or logits), feature-major [a][row]
+  float* DLS = smem + o; o += al(DAP * PRS);   // dL/d(log_std) per row
+  float* MBv = smem + o; o += al((DAP + 3) * PRS);  // act[DAP rows] | logp_old | adv | ret, feature-major
+  float* DVAL = smem + o; o += al(PRS);
+  float* rstat = smem + o; o += al(2 * 64 + 4);  // running mean[64] | var[64] of the feature norm
+  int* s_idx = reinterpret_cast<int*>(smem + o); o += al(PR);
+  float* H1 = TH1 + net * HP * PRS;
+  float* LAT = TLAT + net * HP * PRS;
+  float* DZ2 = TDZ2 + net * HP * PRS;
+  float* DZ1 = TDZ1 + net * HP * PRS;
+  const float* W1t = img + net * tsz;
+  const float* W2t = W1t + KP * HP;
+  const float* W2p = W2t + HP * HP;
 
   for (int i = tid; i < NP; i += PT) {
     Pm[i] = g_params[i];
@@ -122,19 +121,18 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       Vm[i] = g_v[i];
     }
   }
-  for (int i = tid; i < al(Do * HP); i += PT) w1t_pi[i] = w1t_vf[i] = 0.f;
-  for (int i = tid; i < al(HP * HP); i += PT) w2t_pi[i] = w2t_vf[i] = 0.f;
-  float run_mean = 0.f, run_var = 1.f;  // feature norm state: thread k < Do owns feature k
-  int32_t run_count = 0;
-  if (pd.has_norm) {
-    if (tid < Do) {
-      run_mean = g_norm[tid];
-      run_var = g_norm[Do + tid];
-    }
-    run_count = *g_norm_count;
+  for (int i = tid; i < al(2 * tsz); i += PT) img[i] = 0.f;
+  for (int i = tid; i < KP * PRS; i += PT) XN[i] = 0.f;
+  for (int i = tid; i < 8 * HP * PRS; i += PT) TH1[i] = 0.f;  // TH1..TDZ1 are contiguous
+  for (int i = tid; i < (DAP + 3) * PRS; i += PT) MBv[i] = 0.f;
+  for (int i = tid; i < 2 * DAP * PRS; i += PT) DM[i] = 0.f;  // DM, DLS contiguous (both al() sized)
+  if (tid < 64) {
+    rstat[tid] = (pd.has_norm && tid < Do) ? g_norm[tid] : 0.f;
+    rstat[64 + tid] = (pd.has_norm && tid < Do) ? g_norm[Do + tid] : 1.f;
   }
+  int32_t run_count = pd.has_norm ? *g_norm_count : 0;
   __syncthreads();
-  build_images<HP>(pd, Pm, w1t_pi, w2t_pi, w1t_vf, w2t_vf);
+  build_images(pd, Pm, img, HP, KP);
   __syncthreads();
 
   const int64_t N = A.n_rows;
@@ -143,230 +141,198 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   int64_t adam_step = state[IMB_ST_PPO_STEP];
   const int64_t perm_draw0 = state[IMB_ST_PPO_EPOCH];
   int64_t log_i = 0;
+  const int rwg = Do + da_store + 3;      // gathered columns per row: obs | act | logp_old | adv | ret
+  const int r0 = (tt & 15) * 4;           // this thread's 4 tile rows
+  const int cgq = tt >> 4;                // column quad within a 32-wide block (0..7)
+  const int off_w1 = net ? pd.off_vf_w1 : pd.off_pi_w1, off_b1 = net ? pd.off_vf_b1 : pd.off_pi_b1;
+  const int off_w2 = net ? pd.off_vf_w2 : pd.off_pi_w2, off_b2 = net ? pd.off_vf_b2 : pd.off_pi_b2;
 
   for (int ep = 0; ep < A.hp.n_epochs; ++ep) {
     const FeistelKey fk = feistel_key(A.seed, IMB_STREAM_PPO_PERM, (uint64_t)(perm_draw0 + ep), (uint64_t)N);
     for (int64_t sidx = 0; sidx < steps_per_epoch; ++sidx) {
       const int64_t start = sidx * mb;
       const int nb = (int)min((int64_t)mb, N - start);
-      // ---- 1. gather the minibatch rows (warp per row, lanes walk the row) ---------------------------------
-      if (tid < nb) {
-        const int64_t q = start + tid;
-        s_idx[tid] = perm_in ? (int)perm_in[(int64_t)ep * N + q] : (int)feistel_perm(fk, (uint64_t)q, (uint64_t)N);
-      }
+      const float inv_nb = 1.0f / (float)nb;
+      // ---- 1. gather: every thread fetches independent elements (one L2 latency for the whole tile) ------
+      if (tid < PR)
+        s_idx[tid] = tid < nb ? (perm_in ? (int)perm_in[(int64_t)ep * N + start + tid]
+                                         : (int)feistel_perm(fk, (uint64_t)(start + tid), (uint64_t)N))
+                              : 0;
       __syncthreads();
-      for (int r = warp; r < nb; r += PT / 32) {
-        const float* src = rollout + (int64_t)s_idx[r] * A.rw;
-        for (int c = lane; c < Do; c += 32) XN[r * xn_ld + c] = src[c];
-        for (int c = lane; c < da_store; c += 32) MB[r * mb_ld + c] = src[col_act + c];
-        if (lane == 0) {
-          MB[r * mb_ld + da_store + 0] = src[col_logp];
-          MB[r * mb_ld + da_store + 1] = src[col_adv];
-          MB[r * mb_ld + da_store + 2] = src[col_ret];
+      for (int e = tid; e < PR * rwg; e += PT) {
+        const int r = e / rwg, c = e - r * rwg;
+        float v = 0.f;
+        if (r < nb) {
+          const int sc = c < col_logp ? c : (c == col_logp ? col_logp : col_adv + (c - col_logp - 1));
+          v = rollout[(int64_t)s_idx[r] * A.rw + sc];
         }
+        if (c < Do) XN[c * PRS + r] = v;
+        else MBv[(c - Do + (c >= col_logp ? DAP - da_store : 0)) * PRS + r] = v;
       }
       __syncthreads();
-      // ---- 2. feature RunningNorm (train mode: update with this minibatch, then normalise) -----------------
+      // ---- 2. feature RunningNorm: update with this minibatch, then normalise (train mode) ------------------
       if (pd.has_norm) {
-        if (tid < Do) {
-          float s = 0.f;
-          for (int r = 0; r < nb; ++r) s += XN[r * xn_ld + tid];
-          const float bmean = s / (float)nb;
-          float m2 = 0.f;
-          for (int r = 0; r < nb; ++r) {
-            const float d = XN[r * xn_ld + tid] - bmean;
-            m2 = fmaf(d, d, m2);
+        for (int k = warp; k < Do; k += PT / 32) {
+          const float x0 = lane < nb ? XN[k * PRS + lane] : 0.f, x1 = lane + 32 < nb ? XN[k * PRS + lane + 32] : 0.f;
+          const float bmean = warp_sum(x0 + x1) * inv_nb;
+          const float d0 = lane < nb ? x0 - bmean : 0.f, d1 = lane + 32 < nb ? x1 - bmean : 0.f;
+          const float bvar = warp_sum(d0 * d0 + d1 * d1) * inv_nb;
+          if (lane == 0) {
+            float mean = rstat[k], var = rstat[64 + k];
+            const float bn = (float)nb, c = (float)run_count, tot = c + bn, delta = bmean - mean;
+            mean += delta * bn / tot;
+            var *= c;
+            var += bvar * bn;
+            var += delta * delta * c * bn / tot;
+            var /= tot;
+            rstat[k] = mean;
+            rstat[64 + k] = var;
           }
-          const float bvar = m2 / (float)nb, bn = (float)nb, c = (float)run_count, tot = c + bn;
-          const float delta = bmean - run_mean;
-          run_mean += delta * bn / tot;
-          run_var *= c;
-          run_var += bvar * bn;
-          run_var += delta * delta * c * bn / tot;
-          run_var /= tot;
-          nmean[tid] = run_mean;
-          nistd[tid] = 1.0f / sqrtf(run_var + pd.norm_eps);
         }
         run_count += nb;
         __syncthreads();
-        for (int i = tid; i < nb * Do; i += PT) {
-          const int r = i / Do, k = i - r * Do;
-          XN[r * xn_ld + k] = (XN[r * xn_ld + k] - nmean[k]) * nistd[k];
+        for (int e = tid; e < Do * PR; e += PT) {
+          const int k = e / PR, r = e - k * PR;
+          XN[k * PRS + r] = r < nb ? (XN[k * PRS + r] - rstat[k]) / sqrtf(rstat[64 + k] + pd.norm_eps) : 0.f;
         }
       }
-      // ---- 3. advantage normalisation: (A - mean) / (std_unbiased + 1e-8) ---------------------------------
-      float adv_mean = 0.f, adv_istd = 1.f;
-      if (A.hp.normalize_advantage && nb > 1) {
-        const float a = (tid < nb) ? MB[tid * mb_ld + da_store + 1] : 0.f;
-        const float s = block_sum(a, red);
-        adv_mean = s / (float)nb;
-        const float d = (tid < nb) ? a - adv_mean : 0.f;
-        const float m2 = block_sum(d * d, red);
-        adv_istd = 1.0f / (sqrtf(m2 / (float)(nb - 1)) + 1e-8f);
+      // ---- 3. advantage normalisation (warp 0): (A - mean) / (std_unbiased + 1e-8) ----------------------------
+      if (warp == 0) {
+        float* adv = MBv + (DAP + 1) * PRS;
+        float am = 0.f, ais = 1.f;
+        if (A.hp.normalize_advantage && nb > 1) {
+          const float a0 = lane < nb ? adv[lane] : 0.f, a1 = lane + 32 < nb ? adv[lane + 32] : 0.f;
+          am = warp_sum(a0 + a1) * inv_nb;
+          const float d0 = lane < nb ? a0 - am : 0.f, d1 = lane + 32 < nb ? a1 - am : 0.f;
+          ais = 1.0f / (sqrtf(warp_sum(d0 * d0 + d1 * d1) / (float)(nb - 1)) + 1e-8f);
+        }
+        if (lane < nb) adv[lane] = (adv[lane] - am) * ais;
+        if (lane + 32 < nb) adv[lane + 32] = (adv[lane + 32] - am) * ais;
       }
       __syncthreads();
 
-      // ---- 4. phase A: thread per row per tower ---------------------------------------------------------------
-      float l_pg = 0.f, l_v = 0.f, l_ent = 0.f;
-      const int net = tid >> 7;          // 0 = policy tower (threads 0..127), 1 = value tower (128..255)
-      const int r = tid & 127;
-      const float inv_nb = 1.0f / (float)nb;
-      if (r < nb && r < MBR) {
-        const float* W1t = net ? w1t_vf : w1t_pi;
-        const float* W2t = net ? w2t_vf : w2t_pi;
-        const float* b1 = Pm + (net ? pd.off_vf_b1 : pd.off_pi_b1);
-        const float* b2 = Pm + (net ? pd.off_vf_b2 : pd.off_pi_b2);
-        const float* W2 = Pm + (net ? pd.off_vf_w2 : pd.off_pi_w2);  // torch layout [j][i]
-        const float* x = XN + r * xn_ld;
-        float h1[HP], lat[HP];
+      // ---- 4. forward: two tanh layers per tower as tiled GEMMs ---------------------------------------------
+      {
+        const float* b1 = Pm + off_b1;
+        for (int jh = 0; jh < HP / 32; ++jh) {
+          const int j0 = jh * 32 + cgq * 4;
+          float acc[4][4] = {};
+          gemm_acc44<false>(acc, XN, PRS, r0, W1t, HP, j0, Do);
 #pragma unroll
-        for (int j = 0; j < HP; ++j) h1[j] = (j < h) ? b1[j] : 0.f;
-        for (int k = 0; k < Do; ++k) {
-          const float xv = x[k];
-          const float4* w = reinterpret_cast<const float4*>(W1t + k * HP);
-#pragma unroll
-          for (int j4 = 0; j4 < HP / 4; ++j4) {
-            const float4 ww = w[j4];
-            h1[4 * j4 + 0] = fmaf(ww.x, xv, h1[4 * j4 + 0]);
-            h1[4 * j4 + 1] = fmaf(ww.y, xv, h1[4 * j4 + 1]);
-            h1[4 * j4 + 2] = fmaf(ww.z, xv, h1[4 * j4 + 2]);
-            h1[4 * j4 + 3] = fmaf(ww.w, xv, h1[4 * j4 + 3]);
+          for (int t = 0; t < 4; ++t) {
+            const float b = (j0 + t < h) ? b1[j0 + t] : 0.f;
+            st4(H1 + (j0 + t) * PRS + r0, make_float4(tanhf(acc[0][t] + b), tanhf(acc[1][t] + b),
+                                                      tanhf(acc[2][t] + b), tanhf(acc[3][t] + b)));
           }
         }
+      }
+      __syncthreads();
+      {
+        const float* b2 = Pm + off_b2;
+        for (int jh = 0; jh < HP / 32; ++jh) {
+          const int j0 = jh * 32 + cgq * 4;
+          float acc[4][4] = {};
+          gemm_acc44<false>(acc, H1, PRS, r0, W2t, HP, j0, h);
 #pragma unroll
-        for (int j = 0; j < HP; ++j) {
-          h1[j] = tanhf(h1[j]);
-          lat[j] = (j < h) ? b2[j] : 0.f;
-        }
-#pragma unroll
-        for (int i = 0; i < HP; ++i) {
-          const float hv = h1[i];
-          const float4* w = reinterpret_cast<const float4*>(W2t + i * HP);
-#pragma unroll
-          for (int j4 = 0; j4 < HP / 4; ++j4) {
-            const float4 ww = w[j4];
-            lat[4 * j4 + 0] = fmaf(ww.x, hv, lat[4 * j4 + 0]);
-            lat[4 * j4 + 1] = fmaf(ww.y, hv, lat[4 * j4 + 1]);
-            lat[4 * j4 + 2] = fmaf(ww.z, hv, lat[4 * j4 + 2]);
-            lat[4 * j4 + 3] = fmaf(ww.w, hv, lat[4 * j4 + 3]);
+          for (int t = 0; t < 4; ++t) {
+            const float b = (j0 + t < h) ? b2[j0 + t] : 0.f;
+            st4(LAT + (j0 + t) * PRS + r0, make_float4(tanhf(acc[0][t] + b), tanhf(acc[1][t] + b),
+                                                       tanhf(acc[2][t] + b), tanhf(acc[3][t] + b)));
           }
         }
-#pragma unroll
-        for (int j = 0; j < HP; ++j) lat[j] = tanhf(lat[j]);
+      }
+      __syncthreads();
 
-        float dlat[HP];
-#pragma unroll
-        for (int j = 0; j < HP; ++j) dlat[j] = 0.f;
-        const float* mbr = MB + r * mb_ld;
+      // ---- 5. heads + losses + dL/dlatent, thread per row (64 threads per tower) -----------------------------------
+      float l_pg = 0.f, l_v = 0.f, l_ent = 0.f;
+      if (tt < PR) {
+        const int r = tt;
+        const bool live = r < nb;
         if (net == 1) {
-          // value head + MSE
           const float* wv = Pm + pd.off_val_w;
           float v = Pm[pd.off_val_b];
-#pragma unroll
-          for (int j = 0; j < HP; ++j) v = (j < h) ? fmaf(wv[j], lat[j], v) : v;
-          const float ret = mbr[da_store + 2];
-          const float dv = v - ret;
-          l_v = dv * dv;
-          const float g = A.hp.vf_coef * 2.0f * dv * inv_nb;
+          for (int j = 0; j < h; ++j) v = fmaf(wv[j], LAT[j * PRS + r], v);
+          const float dv = v - MBv[(DAP + 2) * PRS + r];
+          float g = 0.f;
+          if (live) {
+            l_v = dv * dv;
+            g = A.hp.vf_coef * 2.0f * dv * inv_nb;
+          }
           DVAL[r] = g;
-#pragma unroll
-          for (int j = 0; j < HP; ++j) dlat[j] = (j < h) ? g * wv[j] : 0.f;
+          for (int j = 0; j < h; ++j) {
+            const float l = LAT[j * PRS + r];
+            DZ2[j * PRS + r] = g * wv[j] * (1.0f - l * l);
+          }
         } else {
           const float* Wa = Pm + pd.off_act_w;  // [Da][h]
           const float* ba = Pm + pd.off_act_b;
-          const float adv = (mbr[da_store + 1] - adv_mean) * adv_istd;
-          const float logp_old = mbr[da_store + 0];
+          const float adv = MBv[(DAP + 1) * PRS + r], logp_old = MBv[DAP * PRS + r];
           float logp = 0.f, ent = 0.f;
-          float* dmean = DMEAN + r * dm_ld;
-          float* dls = DLS + r * dm_ld;
           if (!pd.discrete) {
             const float* lstd = Pm + pd.off_log_std;
             for (int a = 0; a < Da; ++a) {
               float m = ba[a];
-#pragma unroll
-              for (int j = 0; j < HP; ++j) m = (j < h) ? fmaf(Wa[a * h + j], lat[j], m) : m;
+              for (int j = 0; j < h; ++j) m = fmaf(Wa[a * h + j], LAT[j * PRS + r], m);
               const float ls = lstd[a], sd = expf(ls), var = sd * sd;
-              const float diff = mbr[a] - m;
+              const float diff = MBv[a * PRS + r] - m;
               logp += -(diff * diff) / (2.0f * var) - ls - 0.9189385332046727f;
               ent += 1.4189385332046727f + ls;
-              dmean[a] = diff / var;               // d logp / d mean
-              dls[a] = diff * diff / var - 1.0f;   // d logp / d log_std
+              DM[a * PRS + r] = diff / var;              // d logp / d mean
+              DLS[a * PRS + r] = diff * diff / var - 1.0f;  // d logp / d log_std
             }
           } else {
             float mx = -INFINITY;
             for (int a = 0; a < Da; ++a) {
               float m = ba[a];
-#pragma unroll
-              for (int j = 0; j < HP; ++j) m = (j < h) ? fmaf(Wa[a * h + j], lat[j], m) : m;
-              dmean[a] = m;
+              for (int j = 0; j < h; ++j) m = fmaf(Wa[a * h + j], LAT[j * PRS + r], m);
+              DM[a * PRS + r] = m;
               mx = fmaxf(mx, m);
             }
             float se = 0.f;
-            for (int a = 0; a < Da; ++a) se += expf(dmean[a] - mx);
+            for (int a = 0; a < Da; ++a) se += expf(DM[a * PRS + r] - mx);
             const float lse = mx + logf(se);
-            const int act = (int)mbr[0];
-            logp = dmean[act] - lse;
+            const int act = (int)MBv[r];
             for (int a = 0; a < Da; ++a) {
-              const float lp = dmean[a] - lse, p = expf(lp);
-              ent -= p * lp;
-              dls[a] = lp;  // temporarily: log p_a
+              const float lp = DM[a * PRS + r] - lse;
+              if (a == act) logp = lp;
+              ent -= expf(lp) * lp;
+              DLS[a * PRS + r] = lp;  // temporarily: log p_a
             }
           }
           const float ratio = expf(logp - logp_old);
           const float lo = 1.0f - A.hp.clip_range, hi = 1.0f + A.hp.clip_range;
           const float pl1 = adv * ratio, pl2 = adv * fminf(fmaxf(ratio, lo), hi);
-          l_pg = -fminf(pl1, pl2);
-          l_ent = -ent;
           const bool inside = (ratio >= lo) && (ratio <= hi);
-          const float dl_dlogp = (inside || pl1 < pl2) ? -adv * ratio * inv_nb : 0.f;
-          const float dent = -A.hp.ent_coef * inv_nb;  // d(ent_coef * ent_loss)/d(entropy)
+          float dl_dlogp = (inside || pl1 < pl2) ? -adv * ratio * inv_nb : 0.f;
+          float dent = -A.hp.ent_coef * inv_nb;  // d(ent_coef * ent_loss) / d(entropy)
+          if (live) {
+            l_pg = -fminf(pl1, pl2);
+            l_ent = -ent;
+          } else {
+            dl_dlogp = 0.f;
+            dent = 0.f;
+          }
           if (!pd.discrete) {
             for (int a = 0; a < Da; ++a) {
-              dls[a] = dl_dlogp * dls[a] + dent;   // dH/dlog_std = 1
-              dmean[a] = dl_dlogp * dmean[a];
+              DLS[a * PRS + r] = dl_dlogp * DLS[a * PRS + r] + dent;  // dH/dlog_std = 1
+              DM[a * PRS + r] = dl_dlogp * DM[a * PRS + r];
             }
           } else {
-            const int act = (int)mbr[0];
+            const int act = (int)MBv[r];
             for (int a = 0; a < Da; ++a) {
-              const float lp = dls[a], p = expf(lp);
-              const float dlogp_dl = ((a == act) ? 1.f : 0.f) - p;
-              const float dent_dl = -p * (lp + ent);
-              dmean[a] = dl_dlogp * dlogp_dl + dent * dent_dl;
-              dls[a] = 0.f;
+              const float lp = DLS[a * PRS + r], p = expf(lp);
+              DM[a * PRS + r] = dl_dlogp * (((a == act) ? 1.f : 0.f) - p) + dent * (-p * (lp + ent));
+              DLS[a * PRS + r] = 0.f;
             }
           }
-          for (int a = 0; a < Da; ++a) {
-            const float g = dmean[a];
-#pragma unroll
-            for (int j = 0; j < HP; ++j) dlat[j] = (j < h) ? fmaf(g, Wa[a * h + j], dlat[j]) : 0.f;
+          for (int j = 0; j < h; ++j) {
+            float dl = 0.f;
+            for (int a = 0; a < Da; ++a) dl = fmaf(DM[a * PRS + r], Wa[a * h + j], dl);
+            const float l = LAT[j * PRS + r];
+            DZ2[j * PRS + r] = dl * (1.0f - l * l);
           }
-        }
-        // backward through the tower (tanh)
-        float* tH1 = T_H1[net] + r * LD;
-        float* tLAT = T_LAT[net] + r * LD;
-        float* tDZ2 = T_DZ2[net] + r * LD;
-        float* tDZ1 = T_DZ1[net] + r * LD;
-        float dh1[HP];
-#pragma unroll
-        for (int i = 0; i < HP; ++i) dh1[i] = 0.f;
-#pragma unroll
-        for (int j = 0; j < HP; ++j) {
-          const float dz2 = dlat[j] * (1.0f - lat[j] * lat[j]);
-          tDZ2[j] = dz2;
-          tLAT[j] = lat[j];
-          if (j < h) {
-            const float* w = W2 + j * h;
-#pragma unroll
-            for (int i = 0; i < HP; ++i) dh1[i] = (i < h) ? fmaf(w[i], dz2, dh1[i]) : 0.f;
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < HP; ++i) {
-          tH1[i] = h1[i];
-          tDZ1[i] = dh1[i] * (1.0f - h1[i] * h1[i]);
         }
       }
-      // loss terms for logging / parity
       {
         const float s_pg = block_sum(l_pg, red);
         const float s_v = block_sum(l_v, red);
@@ -382,106 +348,111 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       }
       __syncthreads();
 
-      // ---- 5. phase B: weight gradients (warps 0-3 policy tower, 4-7 value tower) ---------------------------------
+      // ---- 6. backward through layer 2: DZ1 = (DZ2 . W2) * (1 - H1^2) -----------------------------------------
+      for (int jh = 0; jh < HP / 32; ++jh) {
+        const int i0 = jh * 32 + cgq * 4;
+        float acc[4][4] = {};
+        gemm_acc44<false>(acc, DZ2, PRS, r0, W2p, HP, i0, h);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float4 hh = ld4(H1 + (i0 + t) * PRS + r0);
+          st4(DZ1 + (i0 + t) * PRS + r0, make_float4(acc[0][t] * (1.f - hh.x * hh.x), acc[1][t] * (1.f - hh.y * hh.y),
+                                                     acc[2][t] * (1.f - hh.z * hh.z), acc[3][t] * (1.f - hh.w * hh.w)));
+        }
+      }
+      __syncthreads();
+
+      // ---- 7. weight gradients per tower (128 threads): per-slice buffers, summed in fixed order ----------------
       {
-        const int bnet = warp >> 2, bw = warp & 3;
-        constexpr int JW = HP / 4;
-        const int j0 = bw * JW;
-        const float* tH1 = T_H1[bnet];
-        const float* tLAT = T_LAT[bnet];
-        const float* tDZ2 = T_DZ2[bnet];
-        const float* tDZ1 = T_DZ1[bnet];
-        const int off_w1 = bnet ? pd.off_vf_w1 : pd.off_pi_w1, off_b1 = bnet ? pd.off_vf_b1 : pd.off_pi_b1;
-        const int off_w2 = bnet ? pd.off_vf_w2 : pd.off_pi_w2, off_b2 = bnet ? pd.off_vf_b2 : pd.off_pi_b2;
-        // dW1 / db1
-        {
-          float acc[JW][2], bs[JW];
+        const int jl = lane & 7, il = lane >> 3;
+        const float sj0[4] = {0.f, 0.f, 0.f, 0.f};
+        {  // dW2 / db2
+          const int nblk = (HP / 32) * (HP / 32), ntl = nblk * 32;
+          const int lt = tt % ntl, sl = tt / ntl, blk = lt >> 5;
+          const int jb = (blk % (HP / 32)) * 32, ib = (blk / (HP / 32)) * 32;
+          const int rows = PR / A.slices;
+          float acc[4][8] = {}, bacc[4] = {};
+          wgrad_acc<false>(acc, bacc, DZ2, H1, PRS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, nullptr, sj0);
+          float* Gs = GS + sl * al(NP);
 #pragma unroll
-          for (int jj = 0; jj < JW; ++jj) acc[jj][0] = acc[jj][1] = bs[jj] = 0.f;
-          const bool k0 = lane < Do, k1 = lane + 32 < Do;
-          for (int rr = 0; rr < nb; ++rr) {
-            const float a0 = k0 ? XN[rr * xn_ld + lane] : 0.f;
-            const float a1 = k1 ? XN[rr * xn_ld + lane + 32] : 0.f;
-#pragma unroll
-            for (int jj = 0; jj < JW; ++jj) {
-              const float dz = tDZ1[rr * LD + j0 + jj];
-              acc[jj][0] = fmaf(dz, a0, acc[jj][0]);
-              acc[jj][1] = fmaf(dz, a1, acc[jj][1]);
-              bs[jj] += dz;
-            }
-          }
-#pragma unroll
-          for (int jj = 0; jj < JW; ++jj) {
-            const int j = j0 + jj;
-            if (j < h) {
-              if (k0) G[off_w1 + j * Do + lane] = acc[jj][0];
-              if (k1) G[off_w1 + j * Do + lane + 32] = acc[jj][1];
-              if (lane == 0) G[off_b1 + j] = bs[jj];
-            }
-          }
-        }
-        // dW2 / db2
-        {
-          float acc[JW][HP / 32], bs[JW];
-#pragma unroll
-          for (int jj = 0; jj < JW; ++jj) {
-#pragma unroll
-            for (int ii = 0; ii < HP / 32; ++ii) acc[jj][ii] = 0.f;
-            bs[jj] = 0.f;
-          }
-          for (int rr = 0; rr < nb; ++rr) {
-            float a[HP / 32];
-#pragma unroll
-            for (int ii = 0; ii < HP / 32; ++ii) a[ii] = tH1[rr * LD + lane + 32 * ii];
-#pragma unroll
-            for (int jj = 0; jj < JW; ++jj) {
-              const float dz = tDZ2[rr * LD + j0 + jj];
-#pragma unroll
-              for (int ii = 0; ii < HP / 32; ++ii) acc[jj][ii] = fmaf(dz, a[ii], acc[jj][ii]);
-              bs[jj] += dz;
-            }
-          }
-#pragma unroll
-          for (int jj = 0; jj < JW; ++jj) {
-            const int j = j0 + jj;
+          for (int jj = 0; jj < 4; ++jj) {
+            const int j = jb + jl + 8 * jj;
             if (j < h) {
 #pragma unroll
-              for (int ii = 0; ii < HP / 32; ++ii) {
-                const int i = lane + 32 * ii;
-                if (i < h) G[off_w2 + j * h + i] = acc[jj][ii];
+              for (int ii = 0; ii < 8; ++ii) {
+                const int i = ib + il + 4 * ii;
+                if (i < h) Gs[off_w2 + j * h + i] = acc[jj][ii];
               }
-              if (lane == 0) G[off_b2 + j] = bs[jj];
+              if (il == 0 && ib == 0) Gs[off_b2 + j] = bacc[jj];
             }
           }
         }
-        // heads
-        if (bnet == 0) {
-          // dWa[a][i], dba[a], dlog_std[a]: work items (a, i) over the 128 policy-side threads
-          const int t4 = tid;  // 0..127
-          for (int w = t4; w < Da * h; w += 128) {
-            const int a = w / h, i = w - a * h;
+        {  // dW1 / db1  (KP x HP blocks; with KP*HP/1024 blocks per tower the slice count may be smaller)
+          const int nblk = (HP / 32) * (KP / 32), ntl = nblk * 32;
+          const int sl_n = 128 / ntl < A.slices ? 128 / ntl : A.slices;
+          const int lt = tt % ntl, sl = tt / ntl, blk = lt >> 5;
+          const int jb = (blk % (HP / 32)) * 32, ib = (blk / (HP / 32)) * 32;
+          if (sl < sl_n) {
+            const int rows = PR / sl_n;
+            float acc[4][8] = {}, bacc[4] = {};
+            wgrad_acc<false>(acc, bacc, DZ1, XN, PRS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, nullptr, sj0);
+            float* Gs = GS + sl * al(NP);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = jb + jl + 8 * jj;
+              if (j < h) {
+#pragma unroll
+                for (int ii = 0; ii < 8; ++ii) {
+                  const int k = ib + il + 4 * ii;
+                  if (k < Do) Gs[off_w1 + j * Do + k] = acc[jj][ii];
+                }
+                if (il == 0 && ib == 0) Gs[off_b1 + j] = bacc[jj];
+              }
+            }
+          }
+          // slices that did not run this contraction must contribute zeros
+          for (int s2 = sl_n; s2 < A.slices; ++s2) {
+            float* Gz = GS + s2 * al(NP);
+            for (int i = tt; i < h * Do + h; i += 128) Gz[(i < h * Do ? off_w1 + i : off_b1 + (i - h * Do))] = 0.f;
+          }
+        }
+        // heads (written straight to G: one owner per element)
+        if (net == 0) {
+          for (int w = tt; w < Da * h; w += 128) {
+            const int a = w / h, j = w - a * h;
             float acc = 0.f;
-            for (int rr = 0; rr < nb; ++rr) acc = fmaf(DMEAN[rr * dm_ld + a], tLAT[rr * LD + i], acc);
+            for (int r = 0; r < PR; r += 4) {
+              const float4 d = ld4(DM + a * PRS + r), l = ld4(LAT + j * PRS + r);
+              acc = fmaf(d.x, l.x, acc);
+              acc = fmaf(d.y, l.y, acc);
+              acc = fmaf(d.z, l.z, acc);
+              acc = fmaf(d.w, l.w, acc);
+            }
             G[pd.off_act_w + w] = acc;
           }
-          for (int a = t4; a < Da; a += 128) {
+          for (int a = tt; a < Da; a += 128) {
             float acc = 0.f, accl = 0.f;
-            for (int rr = 0; rr < nb; ++rr) {
-              acc += DMEAN[rr * dm_ld + a];
-              accl += DLS[rr * dm_ld + a];
+            for (int r = 0; r < PR; ++r) {
+              acc += DM[a * PRS + r];
+              accl += DLS[a * PRS + r];
             }
             G[pd.off_act_b + a] = acc;
             if (!pd.discrete) G[pd.off_log_std + a] = accl;
           }
         } else {
-          const int t4 = tid - 128;
-          for (int i = t4; i <= h; i += 128) {
+          for (int j = tt; j <= h; j += 128) {
             float acc = 0.f;
-            if (i < h) {
-              for (int rr = 0; rr < nb; ++rr) acc = fmaf(DVAL[rr], tLAT[rr * LD + i], acc);
-              G[pd.off_val_w + i] = acc;
+            if (j < h) {
+              for (int r = 0; r < PR; r += 4) {
+                const float4 d = ld4(DVAL + r), l = ld4(LAT + j * PRS + r);
+                acc = fmaf(d.x, l.x, acc);
+                acc = fmaf(d.y, l.y, acc);
+                acc = fmaf(d.z, l.z, acc);
+                acc = fmaf(d.w, l.w, acc);
+              }
+              G[pd.off_val_w + j] = acc;
             } else {
-              for (int rr = 0; rr < nb; ++rr) acc += DVAL[rr];
+              for (int r = 0; r < PR; ++r) acc += DVAL[r];
               G[pd.off_val_b] = acc;
             }
           }
@@ -489,9 +460,20 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       }
       __syncthreads();
 
-      // ---- 6. clip_grad_norm_ + Adam (SB3: eps 1e-5) ---------------------------------------------------------------
+      // ---- 8. slice sum -> clip_grad_norm_ -> Adam (SB3: eps 1e-5) --------------------------------------------------
+      const int n_tower = 2 * (h * Do + h + h * h + h);  // towers' W1,b1,W2,b2 occupy the head of the vector
       float ss = 0.f;
-      for (int i = tid; i < NP; i += PT) ss = fmaf(G[i], G[i], ss);
+      for (int i = tid; i < NP; i += PT) {
+        float g;
+        if (i < n_tower) {
+          g = GS[i];
+          for (int s2 = 1; s2 < A.slices; ++s2) g += GS[s2 * al(NP) + i];
+          G[i] = g;
+        } else {
+          g = G[i];
+        }
+        ss = fmaf(g, g, ss);
+      }
       const float total = sqrtf(block_sum(ss, red));
       float clip = A.hp.max_grad_norm / (total + 1e-6f);
       clip = clip > 1.0f ? 1.0f : clip;
@@ -512,7 +494,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
         Pm[i] -= step_size * (mi / (sqrtf(vi) / bc2s + A.hp.adam_eps));
       }
       __syncthreads();
-      build_images<HP>(pd, Pm, w1t_pi, w2t_pi, w1t_vf, w2t_vf);
+      build_images(pd, Pm, img, HP, KP);
       __syncthreads();
     }
   }
@@ -527,8 +509,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   }
   if (pd.has_norm) {
     if (tid < Do) {
-      g_norm[tid] = run_mean;
-      g_norm[Do + tid] = run_var;
+      g_norm[tid] = rstat[tid];
+      g_norm[Do + tid] = rstat[64 + tid];
     }
     if (tid == 0) *g_norm_count = run_count;
   }
@@ -623,46 +605,45 @@ __global__ void __launch_bounds__(128) k_policy_logp(const imb_policy_desc pd, c
 
 }  // namespace
 
-template <int HP>
-static size_t ppo_smem_floats(const imb_policy_desc& pd, int moments_in_smem, int MBR) {
-  constexpr int LD = PpoCfg<HP>::LD;
+static size_t ppo_smem_floats(const PpoArgs& A) {
   auto al = [](int x) { return (x + 31) / 32 * 32; };
-  const int Do = pd.d_obs, Da = pd.d_act, NP = pd.n_params;
-  const int da_store = pd.discrete ? 1 : Da;
+  const int NP = A.pol.n_params, HP = A.HP, KP = A.KP, Da = A.pol.d_act;
+  const int DAP = (Da + 3) / 4 * 4;
   size_t o = 0;
-  o += al(NP) * (size_t)(moments_in_smem ? 4 : 2);
-  o += 2 * (size_t)(al(Do * HP) + al(HP * HP));
-  o += al(MBR * (Do | 1));
-  o += al(MBR * ((da_store + 3) | 1));
-  o += (size_t)8 * MBR * LD;
-  o += 2 * (size_t)al(MBR * (Da | 1));
-  o += al(MBR);
-  o += 2 * (size_t)al(Do);
-  o += al(MBR);
+  o += (size_t)al(NP) * (2 + A.slices + (A.moments_in_smem ? 2 : 0));
+  o += al(2 * (KP * HP + 2 * HP * HP));
+  o += al(KP * PRS);
+  o += (size_t)8 * HP * PRS;
+  o += 2 * (size_t)al(DAP * PRS);
+  o += al((DAP + 3) * PRS);
+  o += al(PRS);
+  o += al(2 * 64 + 4);
+  o += al(PR);
   return o;
 }
 
-template <int HP>
 static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* norm_count, float* m, float* v,
                       const float* rollout, const int64_t* perm, float* loss_log, int64_t* state, cudaStream_t st) {
   PpoArgs A = A0;
-  IMB_REQUIRE(A.hp.batch_size >= 1 && A.hp.batch_size <= PpoCfg<HP>::MBR,
-              "PPO minibatch size must be in [1, %d] for tower width %d", PpoCfg<HP>::MBR, HP);
-  A.mbr = (A.hp.batch_size + 31) / 32 * 32;
+  IMB_REQUIRE(A.hp.batch_size >= 1 && A.hp.batch_size <= PR, "PPO minibatch size must be in [1, %d]", PR);
+  A.HP = A.pol.hidden <= 32 ? 32 : 64;
+  A.KP = A.pol.d_obs <= 32 ? 32 : 64;
+  const int ntl = (A.HP / 32) * (A.HP / 32) * 32;
+  A.slices = 128 / ntl;  // 4 for 32-wide towers, 1 for 64-wide
   A.moments_in_smem = 1;
-  size_t fl = ppo_smem_floats<HP>(A.pol, 1, A.mbr);
+  size_t fl = ppo_smem_floats(A);
   if (fl * 4 > IMB_SMEM_MAX) {
     A.moments_in_smem = 0;
-    fl = ppo_smem_floats<HP>(A.pol, 0, A.mbr);
+    fl = ppo_smem_floats(A);
   }
   IMB_REQUIRE(fl * 4 <= IMB_SMEM_MAX, "PPO kernel needs %zu B of shared memory", fl * 4);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_ppo_update<HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, IMB_SMEM_MAX);
+  static size_t attr_bytes = 0;
+  if (fl * 4 > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k_ppo_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fl * 4));
     if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_bytes = fl * 4;
   }
-  k_ppo_update<HP><<<1, PT, fl * 4, st>>>(A, params, norm, norm_count, m, v, rollout, perm, loss_log, state);
+  k_ppo_update<<<1, PT, fl * 4, st>>>(A, params, norm, norm_count, m, v, rollout, perm, loss_log, state);
   IMB_CHECK_LAUNCH("k_ppo_update");
   return 0;
 }
@@ -683,12 +664,8 @@ extern "C" int imb_ppo_update(const imb_policy_desc* pol, float* pol_params, flo
   A.rw = imb_rollout_row_width(pol);
   A.seed = seed;
   A.moments_in_smem = 1;
-  cudaStream_t st = (cudaStream_t)stream;
-  if (pol->hidden <= 32)
-    return launch_ppo<32>(A, pol_params, pol_norm, pol_norm_count, exp_avg, exp_avg_sq, rollout, perm, loss_log,
-                          state, st);
-  return launch_ppo<64>(A, pol_params, pol_norm, pol_norm_count, exp_avg, exp_avg_sq, rollout, perm, loss_log, state,
-                        st);
+  return launch_ppo(A, pol_params, pol_norm, pol_norm_count, exp_avg, exp_avg_sq, rollout, perm, loss_log, state,
+                    (cudaStream_t)stream);
 }
 
 template <int HP>

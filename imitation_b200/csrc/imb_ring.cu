@@ -8,9 +8,7 @@
 // algorithms/adversarial/common.py:592-595.
 //
 // All of these are HBM-bound byte movers: tables are AoS rows so a random gather reads whole
-// contiguous rows (one warp per row, lanes = consecutive floats); batches are feature-major so
-// the consumer streams them.  The 32-row x tw tile is transposed through padded shared memory so
-// both the reads and the writes are coalesced.
+// contiguous rows; batches are feature-major so the consumer streams them.
 #include "imb_common.cuh"
 
 namespace {
@@ -97,39 +95,36 @@ __global__ void k_sample_advance(int kind, int64_t n, int64_t size, int64_t* sta
 }
 
 // ---- gather table rows into the feature-major batch --------------------------------------------------
-// Block = 8 warps, each warp owns 32 consecutive batch columns per iteration: it loads its 32 indices
-// with one coalesced read, walks them with __shfl_sync so that every row is read by consecutive
-// lanes (coalesced AoS read), parks the 32 x tw tile in padded shared memory and writes it back
-// transposed, 32 consecutive columns (128 B) per feature row.
-constexpr int G_WARPS = 8;
+// One lane per gathered row: a warp reads its 32 indices with one coalesced load, then walks the
+// tw columns; in each step the 32 lanes read the same column of 32 different table rows (each
+// row's 4*tw bytes are 5-6 sectors that stay in L1 across the column walk, so DRAM/L2 traffic is
+// the rows themselves) and write 32 consecutive batch columns = one coalesced 128-byte store per
+// feature row.  All tw loads of a lane are independent, so the whole tile costs ~one memory latency
+// (the former shuffle-and-transpose form serialised 32 dependent row reads per warp: 17.6 us for
+// 8192 rows; see profiles/).
+constexpr int G_WARPS = 4;
 __global__ void __launch_bounds__(G_WARPS * 32) k_gather_rows(const float* __restrict__ table, int64_t capacity,
                                                               int tw, const int64_t* __restrict__ idx, int64_t n,
                                                               float* __restrict__ batch, int64_t ld,
                                                               int64_t col0) {
-  extern __shared__ float tile_all[];  // [G_WARPS][tw][33]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* tile = tile_all + (size_t)warp * tw * 33;
   const int64_t ngroups = (n + 31) / 32;
   for (int64_t grp = (int64_t)blockIdx.x * G_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * G_WARPS) {
-    const int64_t b0 = grp * 32;
-    const int64_t mine = b0 + lane;
-    int64_t my_idx = 0;
-    if (mine < n) {
-      my_idx = idx ? idx[mine] : mine;
-      if (my_idx < 0) my_idx = 0;
-      if (my_idx >= capacity) my_idx = capacity - 1;
+    const int64_t mine = grp * 32 + lane;
+    if (mine >= n) continue;
+    int64_t r = idx ? idx[mine] : mine;
+    r = r < 0 ? 0 : (r >= capacity ? capacity - 1 : r);
+    const float* src = table + r * tw;
+    float* dst = batch + col0 + mine;
+    int c = 0;
+    for (; c + 8 <= tw; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[c + u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dst[(int64_t)(c + u) * ld] = v[u];
     }
-    const int cnt = (int)min((int64_t)32, n - b0);
-    for (int j = 0; j < cnt; ++j) {
-      const int64_t r = __shfl_sync(0xffffffffu, my_idx, j);
-      const float* src = table + r * tw;
-      for (int c = lane; c < tw; c += 32) tile[c * 33 + j] = src[c];
-    }
-    __syncwarp();
-    if (lane < cnt) {
-      for (int c = 0; c < tw; ++c) batch[(int64_t)c * ld + col0 + b0 + lane] = tile[c * 33 + lane];
-    }
-    __syncwarp();
+    for (; c < tw; ++c) dst[(int64_t)c * ld] = src[c];
   }
 }
 
@@ -173,18 +168,10 @@ extern "C" int imb_gather_rows(const float* table, int64_t capacity, int32_t tw,
                                float* batch, int64_t ld, int64_t col0, void* stream) {
   if (n <= 0) return 0;
   IMB_REQUIRE(capacity >= 1 && tw >= 1, "bad table shape");
-  const size_t smem = (size_t)G_WARPS * tw * 33 * sizeof(float);
-  IMB_REQUIRE(smem <= IMB_SMEM_MAX, "table row too wide for the gather tile");
-  static bool attr_set = false;
-  if (!attr_set && smem > 48 * 1024) {
-    cudaFuncSetAttribute(k_gather_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, IMB_SMEM_MAX);
-    attr_set = true;
-  }
   int64_t blocks = ((n + 31) / 32 + G_WARPS - 1) / G_WARPS;
-  const int64_t cap = (int64_t)imb_num_sms() * 4;
+  const int64_t cap = (int64_t)imb_num_sms() * 16;
   if (blocks > cap) blocks = cap;
-  k_gather_rows<<<(int)blocks, G_WARPS * 32, smem, (cudaStream_t)stream>>>(table, capacity, tw, idx, n, batch, ld,
-                                                                            col0);
+  k_gather_rows<<<(int)blocks, G_WARPS * 32, 0, (cudaStream_t)stream>>>(table, capacity, tw, idx, n, batch, ld, col0);
   IMB_CHECK_LAUNCH("k_gather_rows");
   return 0;
 }
