@@ -207,19 +207,22 @@ __device__ void load_timg(float* sm, const PassDesc& p, int JP, const float* __r
 //   [image per pass][AW: 4 slices x P][stage: nstage x RS][XN: KP x RS][H1, H2, DZ1: JP x RS each]
 //   [lg, gv, gp, dv, lpv: R each]
 template <int R>
-__global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const float* __restrict__ params,
+__global__ void __launch_bounds__(R, 1) k_disc_fwdbwd(const DiscLaunch L, const float* __restrict__ params,
                                                       const float* __restrict__ batch, int64_t ld, int64_t n,
                                                       int64_t n_expert, float loss_scale,
                                                       const float* __restrict__ grad_out,
                                                       float* __restrict__ logits_out, float* __restrict__ partial,
                                                       int JP, int KP, int img_sz, int aw_off, int st_off, int xn_off,
                                                       int t_off, int v_off, int nsl) {
-  constexpr int NQ = R / 128;
+  // one thread per tile row: R threads, warp w -> column group w % 4 (8 columns) and row half w / 4
+  constexpr int NQ = 1;
+  constexpr int NTK = R;
   constexpr int RS = R + TILE_PAD;
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bar;
-  __shared__ float red[32];
+  __shared__ float red[64];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cg = warp & 3, grp = warp >> 2, tg = tid & 127;
   float* AW = smem + aw_off;
   float* xs = smem + st_off;
   float* XN = smem + xn_off;
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
 
   for (int p = 0; p < L.npass; ++p)
     load_timg(smem + p * img_sz, L.pass[p], JP, params, L.pass[p].has_norm ? L.pass[p].norm : nullptr, L.pass[p].eps);
-  for (int i = tid; i < nsl * P; i += NT) AW[i] = 0.f;
+  for (int i = tid; i < nsl * P; i += NTK) AW[i] = 0.f;
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
@@ -254,8 +257,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
   if (tid == 0 && (int64_t)blockIdx.x < ntiles) issue(blockIdx.x);
 
   int rq[NQ];
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) rq[q] = q * 128 + lane * 4;
+  rq[0] = grp * 128 + lane * 4;
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float s_loss = 0.f, s_ent = 0.f;
   int c_exp = 0, c_gen = 0, c_pred_exp = 0;
@@ -269,7 +271,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
     const float* mean = img + TImg::mean(din, JP);
     const float* istd = img + TImg::istd(din, JP);
     // normalised inputs, feature-major; rows >= nv and features >= din are zero
-    for (int i = tid; i < KP * (R / 4); i += NT) {
+    for (int i = tid; i < KP * (R / 4); i += NTK) {
       const int k = i / (R / 4), r4 = (i - k * (R / 4)) * 4;
       float4 v = zero4;
       if (k < din) {
@@ -290,7 +292,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
     for (int q = 0; q < NQ; ++q) gq[q] = zero4;
     if (Pd.n_hidden >= 1) {
       for (int jh = 0; jh < JP / 32; ++jh) {
-        const int j0 = jh * 32 + warp * 8;
+        const int j0 = jh * 32 + cg * 8;
         float acc[NQ * 4][8];
 #pragma unroll
         for (int a = 0; a < NQ * 4; ++a)
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
     }
     if (Pd.n_hidden >= 2) {
       for (int jh = 0; jh < JP / 32; ++jh) {
-        const int j0 = jh * 32 + warp * 8;
+        const int j0 = jh * 32 + cg * 8;
         float acc[NQ * 4][8];
 #pragma unroll
         for (int a = 0; a < NQ * 4; ++a)
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
     if (accumulate) {
       const float* wf = img + TImg::wf(din, JP);
       const float bf = img[TImg::bf(din, JP)];
-      for (int r = tid; r < R; r += NT) {
+      for (int r = tid; r < R; r += NTK) {
         float o = bf;
         for (int j = 0; j < hl; ++j) o = fmaf(wf[j], HL[j * RS + r], o);
         const float c = pass_coef(Pd.coef_kind, L.gamma, dv[r]);
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
     mbar_wait(&bar, phase);
     phase ^= 1u;
     const int nv = (int)min((int64_t)R, n - tile * R);
-    for (int r = tid; r < R; r += NT) {
+    for (int r = tid; r < R; r += NTK) {
       dv[r] = (L.done_slot >= 0 && r < nv) ? xs[L.done_slot * RS + r] : 0.f;
       lpv[r] = (L.logp_slot >= 0 && r < nv) ? xs[L.logp_slot * RS + r] : 0.f;
     }
@@ -365,7 +367,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
     const int64_t next = tile + gridDim.x;
     if (!recompute && tid == 0 && next < ntiles) issue(next);
     // ---- dL/dlogit per row + statistics -------------------------------------------------------------
-    for (int r = tid; r < R; r += NT) {
+    for (int r = tid; r < R; r += NTK) {
       float g = 0.f;
       if (r < nv) {
         const int64_t row = tile * R + r;
@@ -398,7 +400,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
       const float* img = smem + p * img_sz;
       const int din = Pd.din;
       const float* wf = img + TImg::wf(din, JP);
-      for (int r = tid; r < R; r += NT) gp[r] = gv[r] * pass_coef(Pd.coef_kind, L.gamma, dv[r]);
+      for (int r = tid; r < R; r += NTK) gp[r] = gv[r] * pass_coef(Pd.coef_kind, L.gamma, dv[r]);
       __syncthreads();
       float* A0 = AW;  // slice 0 accumulators
       const int h1w = Pd.h1, h2w = Pd.h2;
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
 #pragma unroll
         for (int q = 0; q < NQ; ++q) gq[q] = ld4(gp + rq[q]);
         for (int jh = 0; jh < JP / 32; ++jh) {
-          const int i0 = jh * 32 + warp * 8;
+          const int i0 = jh * 32 + cg * 8;
           float acc[NQ * 4][8];
 #pragma unroll
           for (int a = 0; a < NQ * 4; ++a)
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
             }
         }
       } else if (Pd.n_hidden == 1) {
-        for (int i = tid; i < JP * (R / 4); i += NT) {
+        for (int i = tid; i < JP * (R / 4); i += NTK) {
           const int j = i / (R / 4), r4 = (i - j * (R / 4)) * 4;
           const float4 h = ld4(H1 + j * RS + r4), g = ld4(gp + r4);
           const float w = wf[j];
@@ -441,72 +443,71 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
       }
       __syncthreads();
       const int jl = lane & 7, il = lane >> 3;
-      // dW2 / db2
-      if (Pd.n_hidden == 2) {
-        const int nblk = (JP / 32) * (JP / 32), ntl = nblk * 32, slices = NT / ntl;
-        const int lt = tid % ntl, sl = tid / ntl, blk = lt >> 5;
+      // weight gradients: a group of 4 warps (128 threads) per contraction; with two groups (R = 256)
+      // dW2 and dW1 run concurrently, each split into row slices with private accumulators.
+      constexpr int NGRP = R / 128;
+      const bool do_w2 = Pd.n_hidden == 2 && (NGRP == 1 || grp == 0);
+      const bool do_w1 = Pd.n_hidden >= 1 && (NGRP == 1 || grp == (Pd.n_hidden == 2 ? 1 : 0));
+      if (do_w2) {
+        const int nblk = (JP / 32) * (JP / 32), ntl = nblk * 32, slices = 128 / ntl;
+        const int lt = tg % ntl, sl = tg / ntl, blk = lt >> 5;
         const int jb = (blk % (JP / 32)) * 32, ib = (blk / (JP / 32)) * 32;
-        if (sl < slices) {
-          float acc[4][8], bacc[4], sj[4];
+        float acc[4][8], bacc[4], sj[4];
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            bacc[jj] = 0.f;
-            sj[jj] = wf[jb + jl + 8 * jj];
+        for (int jj = 0; jj < 4; ++jj) {
+          bacc[jj] = 0.f;
+          sj[jj] = wf[jb + jl + 8 * jj];
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = 0.f;
-          }
-          const int rows = R / slices;
-          wgrad_acc<true>(acc, bacc, H2, H1, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, gp, sj);
-          float* A = A0 + sl * P;
+          for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = 0.f;
+        }
+        const int rows = R / slices;
+        wgrad_acc<true>(acc, bacc, H2, H1, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, gp, sj);
+        float* A = A0 + sl * P;
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = jb + jl + 8 * jj;
-            if (j < h2w) {
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = jb + jl + 8 * jj;
+          if (j < h2w) {
 #pragma unroll
-              for (int ii = 0; ii < 8; ++ii) {
-                const int i = ib + il + 4 * ii;
-                if (i < h1w) A[off_w2 + j * h1w + i] += acc[jj][ii];
-              }
-              if (il == 0 && ib == 0) A[off_b2 + j] += bacc[jj];
+            for (int ii = 0; ii < 8; ++ii) {
+              const int i = ib + il + 4 * ii;
+              if (i < h1w) A[off_w2 + j * h1w + i] += acc[jj][ii];
             }
+            if (il == 0 && ib == 0) A[off_b2 + j] += bacc[jj];
           }
         }
       }
-      // dW1 / db1
-      if (Pd.n_hidden >= 1) {
-        const int nblk = (JP / 32) * (KP / 32), ntl = nblk * 32, slices = NT / ntl;
-        const int lt = tid % ntl, sl = tid / ntl, blk = lt >> 5;
+      if (do_w1) {
+        const int nblk = (JP / 32) * (KP / 32), ntl = nblk * 32, slices = 128 / ntl;
+        const int lt = tg % ntl, sl = tg / ntl, blk = lt >> 5;
         const int jb = (blk % (JP / 32)) * 32, ib = (blk / (JP / 32)) * 32;
-        if (sl < slices) {
-          float acc[4][8], bacc[4];
-          const float sj[4] = {0.f, 0.f, 0.f, 0.f};
+        float acc[4][8], bacc[4];
+        const float sj[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            bacc[jj] = 0.f;
+        for (int jj = 0; jj < 4; ++jj) {
+          bacc[jj] = 0.f;
 #pragma unroll
-            for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = 0.f;
-          }
-          const int rows = R / slices;
-          wgrad_acc<false>(acc, bacc, DZ1, XN, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, nullptr, sj);
-          float* A = A0 + sl * P;
+          for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = 0.f;
+        }
+        const int rows = R / slices;
+        wgrad_acc<false>(acc, bacc, DZ1, XN, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, nullptr, sj);
+        float* A = A0 + sl * P;
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = jb + jl + 8 * jj;
-            if (j < h1w) {
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = jb + jl + 8 * jj;
+          if (j < h1w) {
 #pragma unroll
-              for (int ii = 0; ii < 8; ++ii) {
-                const int k = ib + il + 4 * ii;
-                if (k < din) A[off_w1 + j * din + k] += acc[jj][ii];
-              }
-              if (il == 0 && ib == 0) A[off_b1 + j] += bacc[jj];
+            for (int ii = 0; ii < 8; ++ii) {
+              const int kk = ib + il + 4 * ii;
+              if (kk < din) A[off_w1 + j * din + kk] += acc[jj][ii];
             }
+            if (il == 0 && ib == 0) A[off_b1 + j] += bacc[jj];
           }
         }
       }
       // dwf / dbf: thread j sums its feature row against gp (slice 1 accumulators keep owners unique)
       {
         float* A = A0 + 1 * P;
-        for (int j = tid; j <= hl; j += NT) {
+        for (int j = tid; j <= hl; j += NTK) {
           float acc = 0.f;
           if (j < hl) {
             for (int r = 0; r < R; r += 4) {
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
 
   // ---- per-CTA partials: gradients (slices summed in fixed order) + statistics ----------------------
   float* my = partial + (int64_t)blockIdx.x * part_stride(P);
-  for (int i = tid; i < P; i += NT) {
+  for (int i = tid; i < P; i += NTK) {
     float v = AW[i];
     for (int s2 = 1; s2 < nsl; ++s2) v += AW[s2 * P + i];
     my[i] = v;
@@ -551,7 +552,7 @@ __global__ void __launch_bounds__(NT, 1) k_disc_fwdbwd(const DiscLaunch L, const
   __syncthreads();
   if (tid < 5) {
     float v = 0.f;
-    for (int w = 0; w < NT / 32; ++w) v += red[w * 5 + tid];
+    for (int w = 0; w < NTK / 32; ++w) v += red[w * 5 + tid];
     my[P + tid] = v;
   }
 }
@@ -857,7 +858,7 @@ static int launch_fwdbwd(const DiscLaunch& L, const TPlan& t, const float* param
   if (G > MAXG) G = MAXG;
   if (G > ntiles) G = ntiles;
   k_set_meta<<<1, 1, 0, st>>>(reinterpret_cast<int*>(ws + w.meta), (int)G, n, n_expert, loss_scale);
-  k_disc_fwdbwd<R><<<(int)G, NT, bytes, st>>>(L, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
+  k_disc_fwdbwd<R><<<(int)G, R, bytes, st>>>(L, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
                                                ws + w.partial, t.JP, t.KP, t.img_sz, t.aw_off, t.st_off, t.xn_off,
                                                t.t_off, t.v_off, t.nsl);
   IMB_CHECK_LAUNCH("k_disc_fwdbwd");

@@ -1,4 +1,4 @@
-// imb_ppo.cu -- the generator update (PPO) as ONE persistent single-CTA launch per round.
+// imb_ppo.cu -- the generator update (PPO) as ONE persistent thread-block-cluster launch per round.
 //
 // The reference delegates this to stable-baselines3 (algorithms/adversarial/common.py:414,
 // gen_algo.learn -> PPO.train); its arithmetic is restated in oracle/ppo_port.py (parity
@@ -11,13 +11,17 @@
 //   phase B (warps split output units: weight gradients) -> clip_grad_norm_ -> Adam.
 // Also: imb_policy_logp = ActorCriticPolicy.evaluate_actions()[1] for the AIRL discriminator
 // batch (common.py:476-519).
+#include <cooperative_groups.h>
+
 #include "imb_common.cuh"
 #include "imb_tile.cuh"
 
 namespace {
 
-constexpr int PT = 256;   // threads: 0..127 = policy tower, 128..255 = value tower
-constexpr int PR = 64;    // minibatch rows per step (SB3 batch_size <= 64)
+constexpr int PT = 256;   // threads per CTA: 0..127 = policy tower, 128..255 = value tower
+constexpr int CL = 8;     // CTAs per cluster: each owns RL rows of every minibatch and 1/CL of the parameters
+constexpr int RL = 8;     // minibatch rows per CTA  (CL * RL = 64 >= SB3 batch_size)
+constexpr int PR = CL * RL;
 constexpr int PRS = PR + TILE_PAD;
 
 struct PpoArgs {
@@ -26,8 +30,7 @@ struct PpoArgs {
   int64_t n_rows;
   int rw;
   uint64_t seed;
-  int moments_in_smem;
-  int HP, KP, slices;  // tower width / obs width padded to 32; row slices of the weight-gradient phase
+  int HP, KP, S;  // tower width / obs width padded to 32; parameters per slice (multiple of 4)
 };
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
@@ -43,12 +46,13 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-// working images rebuilt from the master parameters after every optimiser step; per tower:
-//   W1t[KP][HP] (k-major for layer 1), W2t[HP][HP] (k = input unit), W2p[HP][HP] (torch layout, padded)
+// working images rebuilt from the parameters after every optimiser step; per tower:
+//   W1t[KP][HP] (k-major for layer 1), W2t[HP][HP] (k = input unit); the backward pass reads W2 in its
+//   torch layout straight from the parameter vector (row stride h, consecutive lanes = consecutive floats)
 __device__ void build_images(const imb_policy_desc& pd, const float* __restrict__ Pm, float* __restrict__ img,
                              int HP, int KP) {
   const int Do = pd.d_obs, h = pd.hidden;
-  const int tsz = KP * HP + 2 * HP * HP;
+  const int tsz = KP * HP + HP * HP;
   for (int i = threadIdx.x; i < h * Do; i += PT) {
     const int j = i / Do, k = i - j * Do;
     img[k * HP + j] = Pm[pd.off_pi_w1 + i];
@@ -56,96 +60,153 @@ __device__ void build_images(const imb_policy_desc& pd, const float* __restrict_
   }
   for (int i = threadIdx.x; i < h * h; i += PT) {
     const int j = i / h, ii = i - j * h;
-    const float a = Pm[pd.off_pi_w2 + i], b = Pm[pd.off_vf_w2 + i];
-    img[KP * HP + ii * HP + j] = a;
-    img[KP * HP + HP * HP + j * HP + ii] = a;
-    img[tsz + KP * HP + ii * HP + j] = b;
-    img[tsz + KP * HP + HP * HP + j * HP + ii] = b;
+    img[KP * HP + ii * HP + j] = Pm[pd.off_pi_w2 + i];
+    img[tsz + KP * HP + ii * HP + j] = Pm[pd.off_vf_w2 + i];
   }
 }
 
+__device__ __forceinline__ float dot8(const float* __restrict__ a, const float* __restrict__ b) {
+  const float4 a0 = ld4(a), a1 = ld4(a + 4), b0 = ld4(b), b1 = ld4(b + 4);
+  float s0 = a0.x * b0.x, s1 = a0.y * b0.y;
+  s0 = fmaf(a0.z, b0.z, s0);
+  s1 = fmaf(a0.w, b0.w, s1);
+  s0 = fmaf(a1.x, b1.x, s0);
+  s1 = fmaf(a1.y, b1.y, s1);
+  s0 = fmaf(a1.z, b1.z, s0);
+  s1 = fmaf(a1.w, b1.w, s1);
+  return s0 + s1;
+}
+
+// PPO.train for one rollout: n_epochs x ceil(N / batch) optimiser steps, ONE cluster of CL CTAs.
+// Every CTA gathers the whole minibatch (64 x ~26 floats) so that the feature RunningNorm and the
+// advantage normalisation are computed redundantly and identically everywhere; forward/backward
+// run on the CTA's own RL rows; the per-CTA partial gradients are exchanged through distributed
+// shared memory: slice owners sum the CL partials in fixed order, the squared norms of the slices
+// are exchanged for clip_grad_norm_, owners run Adam on their slice and push the new parameters to
+// all CTAs.  Three cluster barriers per optimiser step, no global-memory traffic inside a step
+// except the minibatch gather.
 __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __restrict__ g_params,
                                                       float* __restrict__ g_norm, int32_t* __restrict__ g_norm_count,
                                                       float* __restrict__ g_m, float* __restrict__ g_v,
                                                       const float* __restrict__ rollout,
                                                       const int64_t* __restrict__ perm_in,
                                                       float* __restrict__ loss_log, int64_t* __restrict__ state) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
   extern __shared__ __align__(128) float smem[];
   __shared__ float red[32];
   __shared__ float bc[8];
   const imb_policy_desc& pd = A.pol;
-  const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params, HP = A.HP, KP = A.KP;
+  const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params, HP = A.HP, KP = A.KP, S = A.S;
   const int da_store = pd.discrete ? 1 : Da;
   const int col_logp = Do + da_store, col_adv = col_logp + 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int net = tid >> 7, tt = tid & 127;  // tower, thread within tower
   auto al = [](int x) { return (x + 31) / 32 * 32; };
 
-  // ---- shared-memory carve-up ---------------------------------------------------------------------------
+  // ---- shared-memory carve-up (identical in every CTA: DSMEM addresses are rank + offset) ---------------
   int o = 0;
-  float* Pm = smem + o; o += al(NP);
-  float* G = smem + o; o += al(NP);
-  float* GS = smem + o; o += A.slices * al(NP);  // per-slice weight gradients (deterministic sum)
-  float* Mm = g_m;
-  float* Vm = g_v;
-  if (A.moments_in_smem) {
-    Mm = smem + o; o += al(NP);
-    Vm = smem + o; o += al(NP);
-  }
-  const int tsz = KP * HP + 2 * HP * HP;
+  float* Pm = smem + o; o += al(CL * S);        // full parameter vector (padded to CL slices)
+  float* G = smem + o; o += al(CL * S);         // this CTA's partial gradient
+  float* Ms = smem + o; o += al(S);             // Adam moments of the owned slice
+  float* Vs = smem + o; o += al(S);
+  float* GSL = smem + o; o += al(S);            // summed gradient of the owned slice
+  float* SSQ = smem + o; o += 32;               // [CL] squared gradient norms of the slices
+  float* LOSS = smem + o; o += 32;              // [CL][3] partial loss sums (read by CTA 0)
+  const int tsz = KP * HP + HP * HP;
   float* img = smem + o; o += al(2 * tsz);
-  float* XN = smem + o; o += al(KP * PRS);
-  float* TH1 = smem + o; o += 2 * HP * PRS;   // [tower][HP][PRS]
-  float* TLAT = smem + o; o += 2 * HP * PRS;
-  float* TDZ2 = smem + o; o += 2 * HP * PRS;
-  float* TDZ1 = smem + o; o += 2 * HP * PRS;
+  float* XNf = smem + o; o += al(KP * PRS);     // full minibatch, feature-major
   const int DAP = (Da + 3) / 4 * 4;
-  float* DM = smem + o; o += al(DAP * PRS);    // dL/d(mean or logits), feature-major [a][row]
-  float* DLS = smem + o; o += al(DAP * PRS);   // dL/d(log_std) per row
-  float* MBv = smem + o; o += al((DAP + 3) * PRS);  // act[DAP rows] | logp_old | adv | ret, feature-major
-  float* DVAL = smem + o; o += al(PRS);
-  float* rstat = smem + o; o += al(2 * 64 + 4);  // running mean[64] | var[64] of the feature norm
+  float* MBf = smem + o; o += al((DAP + 3) * PRS);  // act[DAP] | logp_old | adv | ret, full minibatch
+  // own-row tiles, feature-major [feature][RL]
+  float* XNo = smem + o; o += al(KP * RL);
+  float* TH1 = smem + o; o += 2 * HP * RL;
+  float* TLAT = smem + o; o += 2 * HP * RL;
+  float* TDZ2 = smem + o; o += 2 * HP * RL;
+  float* TDZ1 = smem + o; o += 2 * HP * RL;
+  float* DM = smem + o; o += DAP * RL;          // dL/d(mean|logits) [a][RL]
+  float* DLS = smem + o; o += DAP * RL;         // dL/d(log_std) per row [a][RL]
+  float* MEAN = smem + o; o += DAP * RL;        // action means / logits [a][RL]
+  float* DVAL = smem + o; o += 32;              // [RL] dL/dvalue ; VALS at +8 ; ONES at +16
+  float* VALS = DVAL + 8;
+  float* ONES = DVAL + 16;
+  float* rstat = smem + o; o += al(2 * 64 + 4);
   int* s_idx = reinterpret_cast<int*>(smem + o); o += al(PR);
-  float* H1 = TH1 + net * HP * PRS;
-  float* LAT = TLAT + net * HP * PRS;
-  float* DZ2 = TDZ2 + net * HP * PRS;
-  float* DZ1 = TDZ1 + net * HP * PRS;
+  unsigned short* offA = reinterpret_cast<unsigned short*>(smem + o); o += al((CL * S + 1) / 2);
+  unsigned short* offB = reinterpret_cast<unsigned short*>(smem + o); o += al((CL * S + 1) / 2);
+  float* H1 = TH1 + net * HP * RL;
+  float* LAT = TLAT + net * HP * RL;
+  float* DZ2 = TDZ2 + net * HP * RL;
+  float* DZ1 = TDZ1 + net * HP * RL;
   const float* W1t = img + net * tsz;
   const float* W2t = W1t + KP * HP;
-  const float* W2p = W2t + HP * HP;
 
-  for (int i = tid; i < NP; i += PT) {
-    Pm[i] = g_params[i];
-    if (A.moments_in_smem) {
-      Mm[i] = g_m[i];
-      Vm[i] = g_v[i];
-    }
+  for (int i = tid; i < CL * S; i += PT) {
+    Pm[i] = i < NP ? g_params[i] : 0.f;
+    G[i] = 0.f;
+  }
+  for (int i = tid; i < S; i += PT) {
+    const int p = crank * S + i;
+    Ms[i] = p < NP ? g_m[p] : 0.f;
+    Vs[i] = p < NP ? g_v[p] : 0.f;
   }
   for (int i = tid; i < al(2 * tsz); i += PT) img[i] = 0.f;
-  for (int i = tid; i < KP * PRS; i += PT) XN[i] = 0.f;
-  for (int i = tid; i < 8 * HP * PRS; i += PT) TH1[i] = 0.f;  // TH1..TDZ1 are contiguous
-  for (int i = tid; i < (DAP + 3) * PRS; i += PT) MBv[i] = 0.f;
-  for (int i = tid; i < 2 * DAP * PRS; i += PT) DM[i] = 0.f;  // DM, DLS contiguous (both al() sized)
+  for (int i = tid; i < KP * PRS; i += PT) XNf[i] = 0.f;
+  for (int i = tid; i < (DAP + 3) * PRS; i += PT) MBf[i] = 0.f;
+  for (int i = tid; i < KP * RL; i += PT) XNo[i] = 0.f;
+  for (int i = tid; i < 8 * HP * RL; i += PT) TH1[i] = 0.f;   // TH1..TDZ1 contiguous
+  for (int i = tid; i < 3 * DAP * RL + 32; i += PT) DM[i] = 0.f;  // DM, DLS, MEAN, DVAL.. contiguous
   if (tid < 64) {
     rstat[tid] = (pd.has_norm && tid < Do) ? g_norm[tid] : 0.f;
     rstat[64 + tid] = (pd.has_norm && tid < Do) ? g_norm[Do + tid] : 1.f;
+    SSQ[tid & 31] = 0.f;
+    LOSS[tid & 31] = 0.f;
+  }
+  __syncthreads();
+  if (tid < RL) ONES[tid] = 1.f;
+  // gradient of parameter p = dot over the CTA's RL rows of two feature rows: offA[p], offB[p]
+  // (float offsets into this CTA's shared memory); biases / log_std pair with ONES.
+  for (int p = tid; p < CL * S; p += PT) {
+    int a = (int)(ONES - smem), b2 = a;  // default: harmless
+    if (p < NP) {
+      auto tower = [&](int q, int tw) -> bool {  // q relative to the tower's first parameter
+        const int w1 = h * Do, b1 = w1 + h, w2 = b1 + h * h, bb2 = w2 + h;
+        const float* tDZ1 = TDZ1 + tw * HP * RL, *tDZ2 = TDZ2 + tw * HP * RL, *tH1 = TH1 + tw * HP * RL;
+        if (q < w1) { a = (int)(tDZ1 - smem) + (q / Do) * RL; b2 = (int)(XNo - smem) + (q % Do) * RL; return true; }
+        if (q < b1) { a = (int)(tDZ1 - smem) + (q - w1) * RL; b2 = (int)(ONES - smem); return true; }
+        if (q < w2) { const int r = q - b1; a = (int)(tDZ2 - smem) + (r / h) * RL; b2 = (int)(tH1 - smem) + (r % h) * RL; return true; }
+        if (q < bb2) { a = (int)(tDZ2 - smem) + (q - w2) * RL; b2 = (int)(ONES - smem); return true; }
+        return false;
+      };
+      const int tp = h * Do + h + h * h + h;
+      if (p < tp) tower(p, 0);
+      else if (p < 2 * tp) tower(p - tp, 1);
+      else if (p < pd.off_act_b) { const int r = p - pd.off_act_w; a = (int)(DM - smem) + (r / h) * RL; b2 = (int)(TLAT - smem) + (r % h) * RL; }
+      else if (p < pd.off_val_w) { a = (int)(DM - smem) + (p - pd.off_act_b) * RL; b2 = (int)(ONES - smem); }
+      else if (p < pd.off_val_b) { a = (int)(DVAL - smem); b2 = (int)(TLAT + HP * RL - smem) + (p - pd.off_val_w) * RL; }
+      else if (p == pd.off_val_b) { a = (int)(DVAL - smem); b2 = (int)(ONES - smem); }
+      else { a = (int)(DLS - smem) + (p - pd.off_log_std) * RL; b2 = (int)(ONES - smem); }
+    }
+    offA[p] = (unsigned short)(a / 4);   // all rows are 16-byte aligned: store offset / 4
+    offB[p] = (unsigned short)(b2 / 4);
   }
   int32_t run_count = pd.has_norm ? *g_norm_count : 0;
   __syncthreads();
   build_images(pd, Pm, img, HP, KP);
-  __syncthreads();
+  cluster.sync();
 
   const int64_t N = A.n_rows;
   const int mb = A.hp.batch_size;
   const int64_t steps_per_epoch = (N + mb - 1) / mb;
   int64_t adam_step = state[IMB_ST_PPO_STEP];
   const int64_t perm_draw0 = state[IMB_ST_PPO_EPOCH];
+  double b1pow = pow(0.9, (double)adam_step), b2pow = pow(0.999, (double)adam_step);  // beta^t, kept incrementally
   int64_t log_i = 0;
-  const int rwg = Do + da_store + 3;      // gathered columns per row: obs | act | logp_old | adv | ret
-  const int r0 = (tt & 15) * 4;           // this thread's 4 tile rows
-  const int cgq = tt >> 4;                // column quad within a 32-wide block (0..7)
-  const int off_w1 = net ? pd.off_vf_w1 : pd.off_pi_w1, off_b1 = net ? pd.off_vf_b1 : pd.off_pi_b1;
-  const int off_w2 = net ? pd.off_vf_w2 : pd.off_pi_w2, off_b2 = net ? pd.off_vf_b2 : pd.off_pi_b2;
+  const int rwg = Do + da_store + 3;  // gathered columns per row: obs | act | logp_old | adv | ret
+  const int row0 = crank * RL;        // first minibatch row owned by this CTA
+  // own-row GEMM mapping: thread -> column j = tt % HP and RPT = HP / 16 consecutive rows
+  const int gj = tt % HP, RPT = HP / 16, gr0 = (tt / HP) * RPT;
 
   for (int ep = 0; ep < A.hp.n_epochs; ++ep) {
     const FeistelKey fk = feistel_key(A.seed, IMB_STREAM_PPO_PERM, (uint64_t)(perm_draw0 + ep), (uint64_t)N);
@@ -153,27 +214,39 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       const int64_t start = sidx * mb;
       const int nb = (int)min((int64_t)mb, N - start);
       const float inv_nb = 1.0f / (float)nb;
-      // ---- 1. gather: every thread fetches independent elements (one L2 latency for the whole tile) ------
+      // ---- 1. gather the whole minibatch (independent loads, 4 in flight per thread) ------------------------
       if (tid < PR)
         s_idx[tid] = tid < nb ? (perm_in ? (int)perm_in[(int64_t)ep * N + start + tid]
                                          : (int)feistel_perm(fk, (uint64_t)(start + tid), (uint64_t)N))
                               : 0;
       __syncthreads();
-      for (int e = tid; e < PR * rwg; e += PT) {
-        const int r = e / rwg, c = e - r * rwg;
-        float v = 0.f;
-        if (r < nb) {
-          const int sc = c < col_logp ? c : (c == col_logp ? col_logp : col_adv + (c - col_logp - 1));
-          v = rollout[(int64_t)s_idx[r] * A.rw + sc];
+      for (int e0 = tid; e0 < PR * rwg; e0 += 4 * PT) {
+        float v[4];
+        int dst[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = e0 + u * PT;
+          v[u] = 0.f;
+          dst[u] = -1;
+          if (e < PR * rwg) {
+            const int r = e / rwg, c = e - r * rwg;
+            if (r < nb) {
+              const int sc = c < col_logp ? c : (c == col_logp ? col_logp : col_adv + (c - col_logp - 1));
+              v[u] = rollout[(int64_t)s_idx[r] * A.rw + sc];
+            }
+            dst[u] = c < Do ? (int)(XNf - smem) + c * PRS + r
+                            : (int)(MBf - smem) + (c - Do + (c >= col_logp ? DAP - da_store : 0)) * PRS + r;
+          }
         }
-        if (c < Do) XN[c * PRS + r] = v;
-        else MBv[(c - Do + (c >= col_logp ? DAP - da_store : 0)) * PRS + r] = v;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dst[u] >= 0) smem[dst[u]] = v[u];
       }
       __syncthreads();
-      // ---- 2. feature RunningNorm: update with this minibatch, then normalise (train mode) ------------------
+      // ---- 2. feature RunningNorm over the whole minibatch (identical in every CTA) -----------------------------
       if (pd.has_norm) {
         for (int k = warp; k < Do; k += PT / 32) {
-          const float x0 = lane < nb ? XN[k * PRS + lane] : 0.f, x1 = lane + 32 < nb ? XN[k * PRS + lane + 32] : 0.f;
+          const float x0 = lane < nb ? XNf[k * PRS + lane] : 0.f, x1 = lane + 32 < nb ? XNf[k * PRS + lane + 32] : 0.f;
           const float bmean = warp_sum(x0 + x1) * inv_nb;
           const float d0 = lane < nb ? x0 - bmean : 0.f, d1 = lane + 32 < nb ? x1 - bmean : 0.f;
           const float bvar = warp_sum(d0 * d0 + d1 * d1) * inv_nb;
@@ -191,14 +264,16 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
         }
         run_count += nb;
         __syncthreads();
-        for (int e = tid; e < Do * PR; e += PT) {
-          const int k = e / PR, r = e - k * PR;
-          XN[k * PRS + r] = r < nb ? (XN[k * PRS + r] - rstat[k]) / sqrtf(rstat[64 + k] + pd.norm_eps) : 0.f;
-        }
       }
-      // ---- 3. advantage normalisation (warp 0): (A - mean) / (std_unbiased + 1e-8) ----------------------------
+      // own rows, normalised, feature-major [k][RL]
+      for (int e = tid; e < Do * RL; e += PT) {
+        const int k = e / RL, r = e - k * RL;
+        const float x = XNf[k * PRS + row0 + r];
+        XNo[e] = (row0 + r < nb) ? (pd.has_norm ? (x - rstat[k]) / sqrtf(rstat[64 + k] + pd.norm_eps) : x) : 0.f;
+      }
+      // ---- 3. advantage normalisation over the whole minibatch (warp 0, identical in every CTA) ----------------
       if (warp == 0) {
-        float* adv = MBv + (DAP + 1) * PRS;
+        float* adv = MBf + (DAP + 1) * PRS;
         float am = 0.f, ais = 1.f;
         if (A.hp.normalize_advantage && nb > 1) {
           const float a0 = lane < nb ? adv[lane] : 0.f, a1 = lane + 32 < nb ? adv[lane + 32] : 0.f;
@@ -211,92 +286,107 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       }
       __syncthreads();
 
-      // ---- 4. forward: two tanh layers per tower as tiled GEMMs ---------------------------------------------
-      {
-        const float* b1 = Pm + off_b1;
-        for (int jh = 0; jh < HP / 32; ++jh) {
-          const int j0 = jh * 32 + cgq * 4;
-          float acc[4][4] = {};
-          gemm_acc44<false>(acc, XN, PRS, r0, W1t, HP, j0, Do);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float b = (j0 + t < h) ? b1[j0 + t] : 0.f;
-            st4(H1 + (j0 + t) * PRS + r0, make_float4(tanhf(acc[0][t] + b), tanhf(acc[1][t] + b),
-                                                      tanhf(acc[2][t] + b), tanhf(acc[3][t] + b)));
+      // ---- 4. forward on the own rows: thread = (tower, column gj, RPT rows) -----------------------------------------
+      auto own_gemm = [&](const float* __restrict__ Ain, const float* __restrict__ Wk, int wld, int K,
+                          float (&acc)[4]) {
+        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) {
+          const float w = Wk[k * wld + gj];
+          const float* ar = Ain + k * RL + gr0;
+          if (RPT == 2) {
+            const float2 a = *reinterpret_cast<const float2*>(ar);
+            acc[0] = fmaf(a.x, w, acc[0]);
+            acc[1] = fmaf(a.y, w, acc[1]);
+          } else {
+            const float4 a = ld4(ar);
+            acc[0] = fmaf(a.x, w, acc[0]);
+            acc[1] = fmaf(a.y, w, acc[1]);
+            acc[2] = fmaf(a.z, w, acc[2]);
+            acc[3] = fmaf(a.w, w, acc[3]);
           }
         }
+      };
+      {
+        float acc[4];
+        own_gemm(XNo, W1t, HP, Do, acc);
+        const float b = gj < h ? Pm[(net ? pd.off_vf_b1 : pd.off_pi_b1) + gj] : 0.f;
+        for (int x = 0; x < RPT; ++x) H1[gj * RL + gr0 + x] = tanhf(acc[x] + b);
       }
       __syncthreads();
       {
-        const float* b2 = Pm + off_b2;
-        for (int jh = 0; jh < HP / 32; ++jh) {
-          const int j0 = jh * 32 + cgq * 4;
-          float acc[4][4] = {};
-          gemm_acc44<false>(acc, H1, PRS, r0, W2t, HP, j0, h);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const float b = (j0 + t < h) ? b2[j0 + t] : 0.f;
-            st4(LAT + (j0 + t) * PRS + r0, make_float4(tanhf(acc[0][t] + b), tanhf(acc[1][t] + b),
-                                                       tanhf(acc[2][t] + b), tanhf(acc[3][t] + b)));
-          }
-        }
+        float acc[4];
+        own_gemm(H1, W2t, HP, h, acc);
+        const float b = gj < h ? Pm[(net ? pd.off_vf_b2 : pd.off_pi_b2) + gj] : 0.f;
+        for (int x = 0; x < RPT; ++x) LAT[gj * RL + gr0 + x] = tanhf(acc[x] + b);
       }
       __syncthreads();
 
-      // ---- 5. heads + losses + dL/dlatent, thread per row (64 threads per tower) -----------------------------------
+      // ---- 5. heads -----------------------------------------------------------------------------------------------------
+      // (i) action means / logits: thread (a, r) ; value: 32 threads = (r, quarter of the latent)
+      if (net == 0) {
+        const float* Wa = Pm + pd.off_act_w;
+        for (int w = tt; w < Da * RL; w += 128) {
+          const int a = w / RL, r = w - a * RL;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int j = 0;
+          for (; j + 4 <= h; j += 4) {
+            s0 = fmaf(Wa[a * h + j + 0], LAT[(j + 0) * RL + r], s0);
+            s1 = fmaf(Wa[a * h + j + 1], LAT[(j + 1) * RL + r], s1);
+            s2 = fmaf(Wa[a * h + j + 2], LAT[(j + 2) * RL + r], s2);
+            s3 = fmaf(Wa[a * h + j + 3], LAT[(j + 3) * RL + r], s3);
+          }
+          for (; j < h; ++j) s0 = fmaf(Wa[a * h + j], LAT[j * RL + r], s0);
+          MEAN[a * RL + r] = Pm[pd.off_act_b + a] + ((s0 + s1) + (s2 + s3));
+        }
+      } else if (tt < 4 * RL) {
+        const float* wv = Pm + pd.off_val_w;
+        const int r = tt >> 2, q = tt & 3;
+        float s = 0.f;
+        for (int j = q; j < h; j += 4) s = fmaf(wv[j], LAT[j * RL + r], s);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        if (q == 0) VALS[r] = s + Pm[pd.off_val_b];
+      }
+      __syncthreads();
+      // (ii) per-row loss terms and dL/d(head outputs): RL threads per tower
       float l_pg = 0.f, l_v = 0.f, l_ent = 0.f;
-      if (tt < PR) {
-        const int r = tt;
-        const bool live = r < nb;
+      if (tt < RL) {
+        const int r = tt, gr = row0 + r;
+        const bool live = gr < nb;
         if (net == 1) {
-          const float* wv = Pm + pd.off_val_w;
-          float v = Pm[pd.off_val_b];
-          for (int j = 0; j < h; ++j) v = fmaf(wv[j], LAT[j * PRS + r], v);
-          const float dv = v - MBv[(DAP + 2) * PRS + r];
+          const float dv = VALS[r] - MBf[(DAP + 2) * PRS + gr];
           float g = 0.f;
           if (live) {
             l_v = dv * dv;
             g = A.hp.vf_coef * 2.0f * dv * inv_nb;
           }
           DVAL[r] = g;
-          for (int j = 0; j < h; ++j) {
-            const float l = LAT[j * PRS + r];
-            DZ2[j * PRS + r] = g * wv[j] * (1.0f - l * l);
-          }
         } else {
-          const float* Wa = Pm + pd.off_act_w;  // [Da][h]
-          const float* ba = Pm + pd.off_act_b;
-          const float adv = MBv[(DAP + 1) * PRS + r], logp_old = MBv[DAP * PRS + r];
+          const float adv = MBf[(DAP + 1) * PRS + gr], logp_old = MBf[DAP * PRS + gr];
           float logp = 0.f, ent = 0.f;
           if (!pd.discrete) {
             const float* lstd = Pm + pd.off_log_std;
             for (int a = 0; a < Da; ++a) {
-              float m = ba[a];
-              for (int j = 0; j < h; ++j) m = fmaf(Wa[a * h + j], LAT[j * PRS + r], m);
               const float ls = lstd[a], sd = expf(ls), var = sd * sd;
-              const float diff = MBv[a * PRS + r] - m;
+              const float diff = MBf[a * PRS + gr] - MEAN[a * RL + r];
               logp += -(diff * diff) / (2.0f * var) - ls - 0.9189385332046727f;
               ent += 1.4189385332046727f + ls;
-              DM[a * PRS + r] = diff / var;              // d logp / d mean
-              DLS[a * PRS + r] = diff * diff / var - 1.0f;  // d logp / d log_std
+              DM[a * RL + r] = diff / var;                 // d logp / d mean
+              DLS[a * RL + r] = diff * diff / var - 1.0f;  // d logp / d log_std
             }
           } else {
             float mx = -INFINITY;
-            for (int a = 0; a < Da; ++a) {
-              float m = ba[a];
-              for (int j = 0; j < h; ++j) m = fmaf(Wa[a * h + j], LAT[j * PRS + r], m);
-              DM[a * PRS + r] = m;
-              mx = fmaxf(mx, m);
-            }
+            for (int a = 0; a < Da; ++a) mx = fmaxf(mx, MEAN[a * RL + r]);
             float se = 0.f;
-            for (int a = 0; a < Da; ++a) se += expf(DM[a * PRS + r] - mx);
+            for (int a = 0; a < Da; ++a) se += expf(MEAN[a * RL + r] - mx);
             const float lse = mx + logf(se);
-            const int act = (int)MBv[r];
+            const int act = (int)MBf[gr];
             for (int a = 0; a < Da; ++a) {
-              const float lp = DM[a * PRS + r] - lse;
+              const float lp = MEAN[a * RL + r] - lse;
               if (a == act) logp = lp;
               ent -= expf(lp) * lp;
-              DLS[a * PRS + r] = lp;  // temporarily: log p_a
+              DLS[a * RL + r] = lp;  // temporarily: log p_a
             }
           }
           const float ratio = expf(logp - logp_old);
@@ -314,210 +404,149 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
           }
           if (!pd.discrete) {
             for (int a = 0; a < Da; ++a) {
-              DLS[a * PRS + r] = dl_dlogp * DLS[a * PRS + r] + dent;  // dH/dlog_std = 1
-              DM[a * PRS + r] = dl_dlogp * DM[a * PRS + r];
+              DLS[a * RL + r] = dl_dlogp * DLS[a * RL + r] + dent;  // dH/dlog_std = 1
+              DM[a * RL + r] = dl_dlogp * DM[a * RL + r];
             }
           } else {
-            const int act = (int)MBv[r];
+            const int act = (int)MBf[gr];
             for (int a = 0; a < Da; ++a) {
-              const float lp = DLS[a * PRS + r], p = expf(lp);
-              DM[a * PRS + r] = dl_dlogp * (((a == act) ? 1.f : 0.f) - p) + dent * (-p * (lp + ent));
-              DLS[a * PRS + r] = 0.f;
+              const float lp = DLS[a * RL + r], pp = expf(lp);
+              DM[a * RL + r] = dl_dlogp * (((a == act) ? 1.f : 0.f) - pp) + dent * (-pp * (lp + ent));
+              DLS[a * RL + r] = 0.f;
             }
-          }
-          for (int j = 0; j < h; ++j) {
-            float dl = 0.f;
-            for (int a = 0; a < Da; ++a) dl = fmaf(DM[a * PRS + r], Wa[a * h + j], dl);
-            const float l = LAT[j * PRS + r];
-            DZ2[j * PRS + r] = dl * (1.0f - l * l);
           }
         }
       }
+      // partial loss sums of this CTA -> CTA 0 (distributed shared memory)
       {
         const float s_pg = block_sum(l_pg, red);
         const float s_v = block_sum(l_v, red);
         const float s_ent = block_sum(l_ent, red);
         if (tid == 0 && loss_log) {
-          const float pg = s_pg * inv_nb, vl = s_v * inv_nb, el = s_ent * inv_nb;
-          loss_log[log_i * 4 + 0] = pg;
-          loss_log[log_i * 4 + 1] = vl;
-          loss_log[log_i * 4 + 2] = el;
-          loss_log[log_i * 4 + 3] = pg + A.hp.ent_coef * el + A.hp.vf_coef * vl;
-        }
-        ++log_i;
-      }
-      __syncthreads();
-
-      // ---- 6. backward through layer 2: DZ1 = (DZ2 . W2) * (1 - H1^2) -----------------------------------------
-      for (int jh = 0; jh < HP / 32; ++jh) {
-        const int i0 = jh * 32 + cgq * 4;
-        float acc[4][4] = {};
-        gemm_acc44<false>(acc, DZ2, PRS, r0, W2p, HP, i0, h);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const float4 hh = ld4(H1 + (i0 + t) * PRS + r0);
-          st4(DZ1 + (i0 + t) * PRS + r0, make_float4(acc[0][t] * (1.f - hh.x * hh.x), acc[1][t] * (1.f - hh.y * hh.y),
-                                                     acc[2][t] * (1.f - hh.z * hh.z), acc[3][t] * (1.f - hh.w * hh.w)));
+          float* L0 = cluster.map_shared_rank(LOSS, 0);
+          L0[crank * 3 + 0] = s_pg;
+          L0[crank * 3 + 1] = s_v;
+          L0[crank * 3 + 2] = s_ent;
         }
       }
       __syncthreads();
-
-      // ---- 7. weight gradients per tower (128 threads): per-slice buffers, summed in fixed order ----------------
+      // (iii) dL/dz2 = (dL/dlatent) * (1 - lat^2): thread = (tower, column gj, RPT rows)
+      for (int x = 0; x < RPT; ++x) {
+        const int r = gr0 + x;
+        float dl = 0.f;
+        if (gj < h) {
+          if (net == 1) {
+            dl = DVAL[r] * Pm[pd.off_val_w + gj];
+          } else {
+            const float* Wa = Pm + pd.off_act_w;
+            for (int a = 0; a < Da; ++a) dl = fmaf(DM[a * RL + r], Wa[a * h + gj], dl);
+          }
+        }
+        const float l = LAT[gj * RL + r];
+        DZ2[gj * RL + r] = dl * (1.0f - l * l);
+      }
+      __syncthreads();
+      // ---- 6. backward through layer 2 --------------------------------------------------------------------------------------
       {
-        const int jl = lane & 7, il = lane >> 3;
-        const float sj0[4] = {0.f, 0.f, 0.f, 0.f};
-        {  // dW2 / db2
-          const int nblk = (HP / 32) * (HP / 32), ntl = nblk * 32;
-          const int lt = tt % ntl, sl = tt / ntl, blk = lt >> 5;
-          const int jb = (blk % (HP / 32)) * 32, ib = (blk / (HP / 32)) * 32;
-          const int rows = PR / A.slices;
-          float acc[4][8] = {}, bacc[4] = {};
-          wgrad_acc<false>(acc, bacc, DZ2, H1, PRS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, nullptr, sj0);
-          float* Gs = GS + sl * al(NP);
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int j = jb + jl + 8 * jj;
-            if (j < h) {
-#pragma unroll
-              for (int ii = 0; ii < 8; ++ii) {
-                const int i = ib + il + 4 * ii;
-                if (i < h) Gs[off_w2 + j * h + i] = acc[jj][ii];
-              }
-              if (il == 0 && ib == 0) Gs[off_b2 + j] = bacc[jj];
-            }
-          }
-        }
-        {  // dW1 / db1  (KP x HP blocks; with KP*HP/1024 blocks per tower the slice count may be smaller)
-          const int nblk = (HP / 32) * (KP / 32), ntl = nblk * 32;
-          const int sl_n = 128 / ntl < A.slices ? 128 / ntl : A.slices;
-          const int lt = tt % ntl, sl = tt / ntl, blk = lt >> 5;
-          const int jb = (blk % (HP / 32)) * 32, ib = (blk / (HP / 32)) * 32;
-          if (sl < sl_n) {
-            const int rows = PR / sl_n;
-            float acc[4][8] = {}, bacc[4] = {};
-            wgrad_acc<false>(acc, bacc, DZ1, XN, PRS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, nullptr, sj0);
-            float* Gs = GS + sl * al(NP);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = jb + jl + 8 * jj;
-              if (j < h) {
-#pragma unroll
-                for (int ii = 0; ii < 8; ++ii) {
-                  const int k = ib + il + 4 * ii;
-                  if (k < Do) Gs[off_w1 + j * Do + k] = acc[jj][ii];
-                }
-                if (il == 0 && ib == 0) Gs[off_b1 + j] = bacc[jj];
-              }
-            }
-          }
-          // slices that did not run this contraction must contribute zeros
-          for (int s2 = sl_n; s2 < A.slices; ++s2) {
-            float* Gz = GS + s2 * al(NP);
-            for (int i = tt; i < h * Do + h; i += 128) Gz[(i < h * Do ? off_w1 + i : off_b1 + (i - h * Do))] = 0.f;
-          }
-        }
-        // heads (written straight to G: one owner per element)
-        if (net == 0) {
-          for (int w = tt; w < Da * h; w += 128) {
-            const int a = w / h, j = w - a * h;
-            float acc = 0.f;
-            for (int r = 0; r < PR; r += 4) {
-              const float4 d = ld4(DM + a * PRS + r), l = ld4(LAT + j * PRS + r);
-              acc = fmaf(d.x, l.x, acc);
-              acc = fmaf(d.y, l.y, acc);
-              acc = fmaf(d.z, l.z, acc);
-              acc = fmaf(d.w, l.w, acc);
-            }
-            G[pd.off_act_w + w] = acc;
-          }
-          for (int a = tt; a < Da; a += 128) {
-            float acc = 0.f, accl = 0.f;
-            for (int r = 0; r < PR; ++r) {
-              acc += DM[a * PRS + r];
-              accl += DLS[a * PRS + r];
-            }
-            G[pd.off_act_b + a] = acc;
-            if (!pd.discrete) G[pd.off_log_std + a] = accl;
-          }
-        } else {
-          for (int j = tt; j <= h; j += 128) {
-            float acc = 0.f;
-            if (j < h) {
-              for (int r = 0; r < PR; r += 4) {
-                const float4 d = ld4(DVAL + r), l = ld4(LAT + j * PRS + r);
-                acc = fmaf(d.x, l.x, acc);
-                acc = fmaf(d.y, l.y, acc);
-                acc = fmaf(d.z, l.z, acc);
-                acc = fmaf(d.w, l.w, acc);
-              }
-              G[pd.off_val_w + j] = acc;
-            } else {
-              for (int r = 0; r < PR; ++r) acc += DVAL[r];
-              G[pd.off_val_b] = acc;
-            }
-          }
+        float acc[4];
+        own_gemm(DZ2, Pm + (net ? pd.off_vf_w2 : pd.off_pi_w2), h, h, acc);  // W2[j][i]: k = j, column = i
+        for (int x = 0; x < RPT; ++x) {
+          const float hh = H1[gj * RL + gr0 + x];
+          DZ1[gj * RL + gr0 + x] = gj < h ? acc[x] * (1.f - hh * hh) : 0.f;
         }
       }
       __syncthreads();
+      // ---- 7. partial gradient of every parameter: one dot product over the RL own rows ----------------------------
+      for (int p = tid; p < NP; p += PT) G[p] = dot8(smem + 4 * (int)offA[p], smem + 4 * (int)offB[p]);
+      cluster.sync();  // (a) all partial gradients (and partial losses) are visible cluster-wide
 
-      // ---- 8. slice sum -> clip_grad_norm_ -> Adam (SB3: eps 1e-5) --------------------------------------------------
-      const int n_tower = 2 * (h * Do + h + h * h + h);  // towers' W1,b1,W2,b2 occupy the head of the vector
+      // ---- 8. slice owners: sum the CL partials in fixed order, exchange squared norms ----------------------------------
       float ss = 0.f;
-      for (int i = tid; i < NP; i += PT) {
-        float g;
-        if (i < n_tower) {
-          g = GS[i];
-          for (int s2 = 1; s2 < A.slices; ++s2) g += GS[s2 * al(NP) + i];
-          G[i] = g;
-        } else {
-          g = G[i];
+      {
+        for (int i = tid; i < S; i += PT) {
+          const int p = crank * S + i;
+          float g = 0.f;
+          if (p < NP) {
+#pragma unroll
+            for (int c = 0; c < CL; ++c) g += cluster.map_shared_rank(G, c)[p];
+          }
+          GSL[i] = g;
+          ss = fmaf(g, g, ss);
         }
-        ss = fmaf(g, g, ss);
       }
-      const float total = sqrtf(block_sum(ss, red));
+      const float my_ssq = block_sum(ss, red);
+      if (tid < CL) cluster.map_shared_rank(SSQ, tid)[crank] = my_ssq;
+      if (crank == 0 && tid == 0 && loss_log) {
+        float pg = 0.f, vl = 0.f, el = 0.f;
+        for (int c = 0; c < CL; ++c) {
+          pg += LOSS[c * 3 + 0];
+          vl += LOSS[c * 3 + 1];
+          el += LOSS[c * 3 + 2];
+        }
+        pg *= inv_nb, vl *= inv_nb, el *= inv_nb;
+        loss_log[log_i * 4 + 0] = pg;
+        loss_log[log_i * 4 + 1] = vl;
+        loss_log[log_i * 4 + 2] = el;
+        loss_log[log_i * 4 + 3] = pg + A.hp.ent_coef * el + A.hp.vf_coef * vl;
+      }
+      ++log_i;
+      cluster.sync();  // (b) all slice norms are in every CTA's SSQ
+
+      // ---- 9. clip_grad_norm_ + Adam on the owned slice; push the new parameters to every CTA ----------------------------
+      float total = 0.f;
+#pragma unroll
+      for (int c = 0; c < CL; ++c) total += SSQ[c];
+      total = sqrtf(total);
       float clip = A.hp.max_grad_norm / (total + 1e-6f);
       clip = clip > 1.0f ? 1.0f : clip;
       ++adam_step;
-      if (tid == 0) {
-        const double b1c = 1.0 - pow(0.9, (double)adam_step), b2c = 1.0 - pow(0.999, (double)adam_step);
-        bc[0] = (float)((double)A.hp.lr / b1c);
-        bc[1] = (float)sqrt(b2c);
+      b1pow *= 0.9;
+      b2pow *= 0.999;
+      const float step_size = (float)((double)A.hp.lr / (1.0 - b1pow)), bc2s = (float)sqrt(1.0 - b2pow);
+      {
+        for (int i = tid; i < S; i += PT) {
+          const int p = crank * S + i;
+          if (p < NP) {
+            const float g = GSL[i] * clip;
+            const float mi = Ms[i] + (g - Ms[i]) * (1.0f - 0.9f);
+            const float vi = Vs[i] * 0.999f + (1.0f - 0.999f) * g * g;
+            Ms[i] = mi;
+            Vs[i] = vi;
+            const float np_ = Pm[p] - step_size * (mi / (sqrtf(vi) / bc2s + A.hp.adam_eps));
+#pragma unroll
+            for (int c = 0; c < CL; ++c) cluster.map_shared_rank(Pm, c)[p] = np_;
+          }
+        }
       }
-      __syncthreads();
-      const float step_size = bc[0], bc2s = bc[1];
-      for (int i = tid; i < NP; i += PT) {
-        const float g = G[i] * clip;
-        const float mi = Mm[i] + (g - Mm[i]) * (1.0f - 0.9f);
-        const float vi = Vm[i] * 0.999f + (1.0f - 0.999f) * g * g;
-        Mm[i] = mi;
-        Vm[i] = vi;
-        Pm[i] -= step_size * (mi / (sqrtf(vi) / bc2s + A.hp.adam_eps));
-      }
-      __syncthreads();
+      cluster.sync();  // (c) every CTA has the new parameters
       build_images(pd, Pm, img, HP, KP);
       __syncthreads();
     }
   }
 
-  // ---- write back ------------------------------------------------------------------------------------------------
-  for (int i = tid; i < NP; i += PT) {
-    g_params[i] = Pm[i];
-    if (A.moments_in_smem) {
-      g_m[i] = Mm[i];
-      g_v[i] = Vm[i];
+  // ---- write back: slice owners store parameters and moments; CTA 0 stores norm state and counters -------------------
+  for (int i = tid; i < S; i += PT) {
+    const int p = crank * S + i;
+    if (p < NP) {
+      g_params[p] = Pm[p];
+      g_m[p] = Ms[i];
+      g_v[p] = Vs[i];
     }
   }
-  if (pd.has_norm) {
-    if (tid < Do) {
-      g_norm[tid] = rstat[tid];
-      g_norm[Do + tid] = rstat[64 + tid];
+  if (crank == 0) {
+    if (pd.has_norm) {
+      if (tid < Do) {
+        g_norm[tid] = rstat[tid];
+        g_norm[Do + tid] = rstat[64 + tid];
+      }
+      if (tid == 0) *g_norm_count = run_count;
     }
-    if (tid == 0) *g_norm_count = run_count;
+    if (tid == 0) {
+      state[IMB_ST_PPO_STEP] = adam_step;
+      state[IMB_ST_PPO_EPOCH] = perm_draw0 + A.hp.n_epochs;
+    }
   }
-  if (tid == 0) {
-    state[IMB_ST_PPO_STEP] = adam_step;
-    state[IMB_ST_PPO_EPOCH] = perm_draw0 + A.hp.n_epochs;
-  }
+  cluster.sync();  // no CTA may exit while peers can still address its shared memory
 }
 
 // ---- log pi(a|s) for the AIRL discriminator batch --------------------------------------------------------------
@@ -607,18 +636,15 @@ __global__ void __launch_bounds__(128) k_policy_logp(const imb_policy_desc pd, c
 
 static size_t ppo_smem_floats(const PpoArgs& A) {
   auto al = [](int x) { return (x + 31) / 32 * 32; };
-  const int NP = A.pol.n_params, HP = A.HP, KP = A.KP, Da = A.pol.d_act;
+  const int HP = A.HP, KP = A.KP, Da = A.pol.d_act, S = A.S;
   const int DAP = (Da + 3) / 4 * 4;
   size_t o = 0;
-  o += (size_t)al(NP) * (2 + A.slices + (A.moments_in_smem ? 2 : 0));
-  o += al(2 * (KP * HP + 2 * HP * HP));
-  o += al(KP * PRS);
-  o += (size_t)8 * HP * PRS;
-  o += 2 * (size_t)al(DAP * PRS);
-  o += al((DAP + 3) * PRS);
-  o += al(PRS);
-  o += al(2 * 64 + 4);
-  o += al(PR);
+  o += 2 * (size_t)al(CL * S) + 3 * (size_t)al(S) + 64;
+  o += al(2 * (KP * HP + HP * HP));
+  o += al(KP * PRS) + al((DAP + 3) * PRS);
+  o += al(KP * RL) + (size_t)8 * HP * RL + (size_t)3 * DAP * RL + 32;
+  o += al(2 * 64 + 4) + al(PR);
+  o += 2 * (size_t)al((CL * S + 1) / 2);
   return o;
 }
 
@@ -628,23 +654,31 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
   IMB_REQUIRE(A.hp.batch_size >= 1 && A.hp.batch_size <= PR, "PPO minibatch size must be in [1, %d]", PR);
   A.HP = A.pol.hidden <= 32 ? 32 : 64;
   A.KP = A.pol.d_obs <= 32 ? 32 : 64;
-  const int ntl = (A.HP / 32) * (A.HP / 32) * 32;
-  A.slices = 128 / ntl;  // 4 for 32-wide towers, 1 for 64-wide
-  A.moments_in_smem = 1;
-  size_t fl = ppo_smem_floats(A);
-  if (fl * 4 > IMB_SMEM_MAX) {
-    A.moments_in_smem = 0;
-    fl = ppo_smem_floats(A);
-  }
-  IMB_REQUIRE(fl * 4 <= IMB_SMEM_MAX, "PPO kernel needs %zu B of shared memory", fl * 4);
+  A.S = ((A.pol.n_params + CL - 1) / CL + 3) / 4 * 4;
+  const size_t fl = ppo_smem_floats(A);
+  IMB_REQUIRE(fl * 4 <= IMB_SMEM_MAX, "PPO kernel needs %zu B of shared memory per CTA", fl * 4);
+  IMB_REQUIRE(fl < 65536 * 4, "PPO kernel: shared-memory offsets must fit 18 bits");
   static size_t attr_bytes = 0;
   if (fl * 4 > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(k_ppo_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fl * 4));
     if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_bytes = fl * 4;
   }
-  k_ppo_update<<<1, PT, fl * 4, st>>>(A, params, norm, norm_count, m, v, rollout, perm, loss_log, state);
-  IMB_CHECK_LAUNCH("k_ppo_update");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(CL);
+  cfg.blockDim = dim3(PT);
+  cfg.dynamicSmemBytes = fl * 4;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_ppo_update, A, params, norm, norm_count, m, v, rollout, perm, loss_log,
+                                     state);
+  if (e != cudaSuccess) IMB_FAIL(-2, "k_ppo_update (cluster launch): %s", cudaGetErrorString(e));
   return 0;
 }
 
@@ -663,7 +697,6 @@ extern "C" int imb_ppo_update(const imb_policy_desc* pol, float* pol_params, flo
   A.n_rows = n_rows;
   A.rw = imb_rollout_row_width(pol);
   A.seed = seed;
-  A.moments_in_smem = 1;
   return launch_ppo(A, pol_params, pol_norm, pol_norm_count, exp_avg, exp_avg_sq, rollout, perm, loss_log, state,
                     (cudaStream_t)stream);
 }
