@@ -92,8 +92,8 @@ def lib() -> C.CDLL:
 # kernel launches issued through this binding (bench.py reports them as `gpu_launches`)
 LAUNCHES = {"count": 0}
 _KERNELS_PER_CALL = {
-    "imb_state_init": 0, "imb_disc_norm_update": None, "imb_disc_fwd_bwd": 2, "imb_disc_reduce": 1,
-    "imb_disc_adam": 2, "imb_reward_forward": 1, "imb_reward_norm_scan": 1, "imb_table_store": 1,
+    "imb_state_init": 0, "imb_disc_norm_update": None, "imb_disc_fwd_bwd": 1, "imb_disc_reduce": 1,
+    "imb_disc_adam": 1, "imb_reward_forward": 1, "imb_reward_norm_scan": 1, "imb_table_store": 1,
     "imb_ring_advance": 1, "imb_sample_indices": 2, "imb_gather_rows": 1, "imb_rollout": 1, "imb_gae": 1,
     "imb_rollout_advance": 1, "imb_env_reset": 1, "imb_ppo_update": 1, "imb_policy_logp": 1,
 }

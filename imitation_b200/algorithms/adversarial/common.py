@@ -186,6 +186,9 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         self.disc_train_mode = False  # set by `train()`'s `networks.training(self.reward_train)`
         self._capturing = False
         self._graph = None
+        self.use_cuda_graph = True   # replay warm kernel sequences from CUDA graphs (device sampling only)
+        self._disc_graphs = {}
+        self._stage = {}
 
     # -- helpers --------------------------------------------------------------------------------------------------
     @staticmethod
@@ -265,27 +268,97 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         else:
             _lib.sample_indices(0, self._idx_g, self.demo_batch_size, 0, self.seed, self.venv.state)
 
+    # -- host-provided samples: async copies into persistent staging buffers ------------------------------------
+    def _stage_host(self, samples: Mapping, which: str) -> None:
+        """H2D (non-blocking when the source is pinned) of obs/acts/next_obs/dones into static device
+        buffers; the AoS packing (imb_table_store) is part of the update's kernel sequence."""
+        v, dev, B = self.venv, self._device, self.demo_batch_size
+        st = self._stage.get(which)
+        if st is None:
+            st = dict(obs=th.empty(B, v.d_obs, device=dev), next_obs=th.empty(B, v.d_obs, device=dev),
+                      acts=(th.empty(B, dtype=th.int64, device=dev) if v.discrete else th.empty(B, v.d_act, device=dev)),
+                      dones=th.empty(B, dtype=th.uint8, device=dev),
+                      table=th.zeros(B, _desc.table_width(v.d_obs, v.d_act), device=dev),
+                      state=th.zeros(_lib.ST_WORDS, dtype=th.int64, device=dev))
+            self._stage[which] = st
+        for k in ("obs", "next_obs", "acts", "dones"):
+            src = samples[k]
+            if isinstance(src, np.ndarray):
+                src = th.from_numpy(np.ascontiguousarray(src) if src.flags.writeable else src.copy())
+            dst = st[k]
+            src = src.detach().reshape(dst.shape)
+            if src.dtype != dst.dtype and not src.is_cuda:
+                src = src.to(dst.dtype)  # host-side cast (bool -> uint8, float64 -> float32, ...)
+            dst.copy_(src, non_blocking=True)
+
+    def _pack_staged(self, which: str) -> th.Tensor:
+        v, st, B = self.venv, self._stage[which], self.demo_batch_size
+        _lib.table_store(st["table"], B, v.d_obs, v.d_act, st["obs"], None if v.discrete else st["acts"],
+                         st["acts"] if v.discrete else None, st["next_obs"], st["dones"], B, False, st["state"])
+        return st["table"]
+
     def train_disc_async(self, *, expert_samples: Optional[Mapping] = None, gen_samples: Optional[Mapping] = None,
                          stats_out: Optional[th.Tensor] = None, check_ring: bool = True) -> th.Tensor:
         """One discriminator update entirely on the stream; returns the device stats vector
-        (index order = STAT_KEYS) without synchronising."""
+        (index order = STAT_KEYS) without synchronising.  The kernel sequence after the H2D copies is
+        replayed from a CUDA graph once warm (device sampling only)."""
         if not self._fused:
             raise NotImplementedError("train_disc_async needs the fused Adam path")
+        if gen_samples is None and check_ring and self._gen_replay_buffer.size() == 0:
+            raise RuntimeError("No generator samples for training. Call `train_gen()` first.")
+        e_host, g_host = expert_samples is not None, gen_samples is not None
+        if e_host:
+            self._stage_host(self._check_samples(expert_samples, "expert"), "expert")
+        if g_host:
+            self._stage_host(self._check_samples(gen_samples, "gen"), "gen")
+        train_mode = bool(self.reward_train.training or self.disc_train_mode)
+        out = self._stats if stats_out is None else stats_out
+        graphable = (self.use_cuda_graph and not self._capturing and self.sampling == "device"
+                     and (e_host or self._expert_compat is None))
+        if not graphable:
+            self._disc_update_body(e_host, g_host, train_mode, out)
+        else:
+            eng = self._fused_net.engine()
+            key = (e_host, g_host, train_mode, out.data_ptr(), eng.params.data_ptr(), eng.norm_state.data_ptr(),
+                   self._gen_replay_buffer.table.data_ptr(),
+                   self.policy.flat_vectors()[0].data_ptr() if self._needs_logp else 0)
+            ent = self._disc_graphs.get(key)
+            if ent is None:
+                # first call with this signature runs eagerly (allocations, function attributes) ...
+                self._disc_update_body(e_host, g_host, train_mode, out)
+                self._disc_graphs[key] = "warm"
+            else:
+                if ent == "warm":  # ... the second one is captured, later ones are replayed
+                    before = _lib.LAUNCHES["count"]
+                    self._capturing = True
+                    try:
+                        g = th.cuda.CUDAGraph()
+                        with th.cuda.graph(g):
+                            self._disc_update_body(e_host, g_host, train_mode, out)
+                    finally:
+                        self._capturing = False
+                    ent = (g, _lib.LAUNCHES["count"] - before)
+                    _lib.LAUNCHES["count"] = before
+                    self._disc_graphs[key] = ent
+                ent[0].replay()
+                _lib.LAUNCHES["count"] += ent[1]
+        if not self._capturing:
+            self._disc_step += 1
+        return out
+
+    def _disc_update_body(self, e_host: bool, g_host: bool, train_mode: bool, out: th.Tensor) -> None:
         B, mb = self.demo_batch_size, self.demo_minibatch_size
         eng = self._fused_net.engine()
-        if expert_samples is None:
+        if not e_host:
             self._sample_expert_indices()
             e_table, e_idx, e_cap = self._expert_table, self._idx_e, self._expert_n
         else:
-            e_table, e_idx, e_cap = self._rows_to_table(self._check_samples(expert_samples, "expert")), None, B
-        if gen_samples is None:
-            if check_ring and self._gen_replay_buffer.size() == 0:
-                raise RuntimeError("No generator samples for training. Call `train_gen()` first.")
+            e_table, e_idx, e_cap = self._pack_staged("expert"), None, B
+        if not g_host:
             self._sample_gen_indices()
             g_table, g_idx, g_cap = self._gen_replay_buffer.table, self._idx_g, self._gen_replay_buffer.capacity
         else:
-            g_table, g_idx, g_cap = self._rows_to_table(self._check_samples(gen_samples, "gen")), None, B
-        train_mode = bool(self.reward_train.training or self.disc_train_mode)
+            g_table, g_idx, g_cap = self._pack_staged("gen"), None, B
         n = 2 * mb
         for i, start in enumerate(range(0, B, mb)):
             ei = e_idx[start:start + mb] if e_idx is not None else None
@@ -302,13 +375,9 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
                 eng.norm_update(self._batch, self._ld, n)
             eng.fwd_bwd(self._batch, self._ld, n, mb, 1.0 / (2 * B), None, self._logits, i == 0, tn)
             eng.reduce(None)
-        out = self._stats if stats_out is None else stats_out
         opt: FusedAdamState = self._disc_opt
         _lib.disc_adam(eng.desc, opt.hp, eng.params, opt.exp_avg, opt.exp_avg_sq, None, 1.0, eng.ws, self.venv.state,
                        out)
-        if not self._capturing:
-            self._disc_step += 1
-        return out
 
     # -- whole round as one CUDA graph (no host work between kernels) ---------------------------------------------
     def _enqueue_round(self) -> None:

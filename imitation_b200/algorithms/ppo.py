@@ -58,6 +58,11 @@ class DevicePPO:
         self.noise = None         # optional pinned sampling noise for the next rollout (parity tests)
         self.perm = None          # optional host permutations [n_epochs][N] (parity tests)
         self._capturing = False   # True while a CUDA graph of the round is being captured
+        self.use_cuda_graph = True  # learn(): replay [rollout -> GAE -> advance -> PPO update] as one CUDA graph
+        self._graph = None
+        self._graph_key = None
+        self._graph_launches = 0
+        self._eager_iters = 0
 
     # -- SB3 surface ---------------------------------------------------------------------------------------------
     def set_env(self, env, force_reset: bool = True) -> None:
@@ -134,6 +139,52 @@ class DevicePPO:
         _lib.ppo_update(pol.desc, pp, pn, pc, self.exp_avg, self.exp_avg_sq, self._tbl, N, self.hp, self.perm,
                         self.seed, self.loss_log, self._base_env.state)
 
+    def _pointer_key(self):
+        """Everything a captured graph bakes in: device pointers of the vectors the kernels touch."""
+        pp, pn, pc = self.policy.flat_vectors()
+        key = [pp.data_ptr(), pn.data_ptr(), pc.data_ptr(), self._tbl.data_ptr() if self._tbl is not None else 0,
+               self.n_steps, id(self._rw_wrapper), id(self._buffering)]
+        if self._rw_wrapper is not None:
+            net, mode, out_norm = self._rw_wrapper.resolve()
+            eng = net.engine()
+            key += [eng.params.data_ptr(), eng.norm_state.data_ptr(), mode, id(out_norm)]
+        if self._buffering is not None and self._buffering._ring is not None:
+            key.append(self._buffering._ring.table.data_ptr())
+        return tuple(key)
+
+    def _iteration(self) -> None:
+        """One collect_rollouts + train, replayed from a CUDA graph once it is warm (the kernels read every
+        per-call scalar from the device counter block, so the captured launch sequence is exact)."""
+        plain = self.noise is None and self.perm is None and self.loss_log is None
+        if not (self.use_cuda_graph and plain):
+            self.collect_rollouts()
+            self.train()
+            self._eager_iters += 1
+            return
+        if self._eager_iters < 1 or self._tbl is None:
+            self.collect_rollouts()
+            self.train()
+            self._eager_iters += 1
+            return
+        key = self._pointer_key()
+        if self._graph is None or key != self._graph_key:
+            before = _lib.LAUNCHES["count"]
+            self._capturing = True
+            try:
+                g = th.cuda.CUDAGraph()
+                with th.cuda.graph(g):
+                    self.collect_rollouts()
+                    self.train()
+            finally:
+                self._capturing = False
+            self._graph, self._graph_key = g, key
+            self._graph_launches = _lib.LAUNCHES["count"] - before
+            _lib.LAUNCHES["count"] = before
+        t0 = self._base_env.host_ep_step
+        self._graph.replay()
+        _lib.LAUNCHES["count"] += self._graph_launches
+        self.after_rollout_host(t0)
+
     def learn(self, total_timesteps: int, callback=None, reset_num_timesteps: bool = True, **kwargs):
         per = self._base_env.num_envs * self.n_steps
         done = 0
@@ -142,8 +193,7 @@ class DevicePPO:
         while done < total_timesteps:
             if callback is not None and hasattr(callback, "on_rollout_start"):
                 callback.on_rollout_start()
-            self.collect_rollouts()
-            self.train()
+            self._iteration()
             done += per
         return self
 

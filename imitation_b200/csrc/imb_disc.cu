@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(R, 1) k_disc_fwdbwd(const DiscLaunch L, const 
                                                       int64_t n_expert, float loss_scale,
                                                       const float* __restrict__ grad_out,
                                                       float* __restrict__ logits_out, float* __restrict__ partial,
-                                                      int JP, int KP, int img_sz, int aw_off, int st_off, int xn_off,
+                                                      int* __restrict__ meta, int JP, int KP, int img_sz, int aw_off, int st_off, int xn_off,
                                                       int t_off, int v_off, int nsl) {
   // one thread per tile row: R threads, warp w -> column group w % 4 (8 columns) and row half w / 4
   constexpr int NQ = 1;
@@ -242,6 +242,12 @@ __global__ void __launch_bounds__(R, 1) k_disc_fwdbwd(const DiscLaunch L, const 
   if (tid == 0) {
     mbar_init(&bar, 1);
     mbar_fence_init();
+    if (blockIdx.x == 0) {  // launch record for k_disc_reduce / k_disc_adam (stats of the LAST minibatch)
+      meta[0] = (int)gridDim.x;
+      meta[1] = (int)n;
+      meta[2] = (int)n_expert;
+      reinterpret_cast<float*>(meta)[3] = loss_scale;
+    }
   }
   __syncthreads();
 
@@ -562,6 +568,8 @@ __global__ void __launch_bounds__(R, 1) k_disc_fwdbwd(const DiscLaunch L, const 
 __global__ void __launch_bounds__(256) k_disc_reduce(int P, int G, const float* __restrict__ partial,
                                                     float* __restrict__ gacc, float* __restrict__ stats,
                                                     float* __restrict__ grad_out_flat) {
+  // (the Adam step number is read by k_disc_adam from the device counter block; the increment is
+  //  committed by a single thread there AFTER every block has read it -- see k_disc_adam)
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -582,20 +590,27 @@ __global__ void __launch_bounds__(256) k_disc_reduce(int P, int G, const float* 
   }
 }
 
-__global__ void __launch_bounds__(256) k_disc_adam(int P, imb_adam opt, float* __restrict__ params,
+// single block: every thread reads the step counter before thread 0 commits the increment (no race,
+// no extra launch); P <= ~8.5k parameters = a handful of iterations per thread.
+__global__ void __launch_bounds__(1024) k_disc_adam(int P, imb_adam opt, float* __restrict__ params,
                                                   float* __restrict__ m, float* __restrict__ v,
                                                   const float* __restrict__ grad, float grad_div,
                                                   const float* __restrict__ stats, const int* __restrict__ meta,
-                                                  const int64_t* __restrict__ state,
+                                                  int64_t* __restrict__ step_io,
                                                   float* __restrict__ stats_out) {
   // bias corrections in double like torch's Python-scalar arithmetic (torch/optim/adam.py)
-  const int64_t step = state[IMB_ST_DISC_STEP] + 1;
-  const double bc1d = 1.0 - pow((double)opt.beta1, (double)step);
-  const double bc2d = 1.0 - pow((double)opt.beta2, (double)step);
-  const float step_size = (float)((double)opt.lr / bc1d);
-  const float bc2_sqrt = (float)sqrt(bc2d);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P) {
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const int64_t step = *step_io + 1;
+    const double bc1d = 1.0 - pow((double)opt.beta1, (double)step);
+    const double bc2d = 1.0 - pow((double)opt.beta2, (double)step);
+    s_bc[0] = (float)((double)opt.lr / bc1d);
+    s_bc[1] = (float)sqrt(bc2d);
+    *step_io = step;
+  }
+  __syncthreads();
+  const float step_size = s_bc[0], bc2_sqrt = s_bc[1];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
     const float g = grad[i] / grad_div;
     const float mi = m[i] + (g - m[i]) * (1.0f - opt.beta1);        // torch: exp_avg.lerp_(grad, 1-beta1)
     const float vi = v[i] * opt.beta2 + (1.0f - opt.beta2) * g * g;  // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
@@ -857,9 +872,8 @@ static int launch_fwdbwd(const DiscLaunch& L, const TPlan& t, const float* param
   int64_t G = imb_num_sms();
   if (G > MAXG) G = MAXG;
   if (G > ntiles) G = ntiles;
-  k_set_meta<<<1, 1, 0, st>>>(reinterpret_cast<int*>(ws + w.meta), (int)G, n, n_expert, loss_scale);
   k_disc_fwdbwd<R><<<(int)G, R, bytes, st>>>(L, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
-                                               ws + w.partial, t.JP, t.KP, t.img_sz, t.aw_off, t.st_off, t.xn_off,
+                                               ws + w.partial, reinterpret_cast<int*>(ws + w.meta), t.JP, t.KP, t.img_sz, t.aw_off, t.st_off, t.xn_off,
                                                t.t_off, t.v_off, t.nsl);
   IMB_CHECK_LAUNCH("k_disc_fwdbwd");
   return (int)G;
@@ -919,11 +933,9 @@ extern "C" int imb_disc_adam(const imb_disc_desc* d, const imb_adam* opt, float*
   const int P = d->n_params;
   const float* grad = grad_flat_or_null ? grad_flat_or_null : ws + w.gacc;
   // loss statistic: sum * loss_scale recorded by the last fwd/bwd launch (meta[3])
-  k_disc_adam<<<(P + 255) / 256, 256, 0, st>>>(P, *opt, params, exp_avg, exp_avg_sq, grad, grad_div, ws + w.stats,
-                                               reinterpret_cast<const int*>(ws + w.meta), state, stats_out);
+  k_disc_adam<<<1, 1024, 0, st>>>(P, *opt, params, exp_avg, exp_avg_sq, grad, grad_div, ws + w.stats,
+                                  reinterpret_cast<const int*>(ws + w.meta), state + IMB_ST_DISC_STEP, stats_out);
   IMB_CHECK_LAUNCH("k_disc_adam");
-  k_state_add<<<1, 1, 0, st>>>(state, IMB_ST_DISC_STEP, 1);
-  IMB_CHECK_LAUNCH("k_state_add");
   return 0;
 }
 
