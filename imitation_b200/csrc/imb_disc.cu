@@ -207,7 +207,7 @@ __device__ void load_timg(float* sm, const PassDesc& p, int JP, const float* __r
 //   [image per pass][AW: 4 slices x P][stage: nstage x RS][XN: KP x RS][H1, H2, DZ1: JP x RS each]
 //   [lg, gv, gp, dv, lpv: R each]
 template <int R>
-__global__ void __launch_bounds__(R, 1) k_disc_fwdbwd(const DiscLaunch L, const float* __restrict__ params,
+__global__ void __launch_bounds__(R, 256 / R) k_disc_fwdbwd(const DiscLaunch L, const float* __restrict__ params,
                                                       const float* __restrict__ batch, int64_t ld, int64_t n,
                                                       int64_t n_expert, float loss_scale,
                                                       const float* __restrict__ grad_out,
@@ -452,11 +452,18 @@ __global__ void __launch_bounds__(R, 1) k_disc_fwdbwd(const DiscLaunch L, const 
       // weight gradients: a group of 4 warps (128 threads) per contraction; with two groups (R = 256)
       // dW2 and dW1 run concurrently, each split into row slices with private accumulators.
       constexpr int NGRP = R / 128;
-      const bool do_w2 = Pd.n_hidden == 2 && (NGRP == 1 || grp == 0);
-      const bool do_w1 = Pd.n_hidden >= 1 && (NGRP == 1 || grp == (Pd.n_hidden == 2 ? 1 : 0));
+      // R = 256: two 128-thread groups run dW2 and dW1 concurrently (4 row slices each).
+      // R = 128: 32-wide nets split the CTA 64/64 (dW2 | dW1, 2 slices each); otherwise sequential.
+      const bool split64 = (NGRP == 1) && JP == 32 && Pd.n_hidden == 2;
+      const int wg = split64 ? (tid >> 6) : grp;        // which contraction group this thread is in
+      const int tgw = split64 ? (tid & 63) : tg;        // thread index inside the group
+      const int gthreads = split64 ? 64 : 128;
+      const bool do_w2 = Pd.n_hidden == 2 && ((NGRP == 1 && !split64) || wg == 0);
+      const bool do_w1 = Pd.n_hidden >= 1 && ((NGRP == 1 && !split64) || wg == (Pd.n_hidden == 2 ? 1 : 0));
       if (do_w2) {
-        const int nblk = (JP / 32) * (JP / 32), ntl = nblk * 32, slices = 128 / ntl;
-        const int lt = tg % ntl, sl = tg / ntl, blk = lt >> 5;
+        const int nblk = (JP / 32) * (JP / 32), ntl = nblk * 32;
+        const int slices = min(gthreads / ntl, nsl);
+        const int lt = tgw % ntl, sl = tgw / ntl, blk = lt >> 5;
         const int jb = (blk % (JP / 32)) * 32, ib = (blk / (JP / 32)) * 32;
         float acc[4][8], bacc[4], sj[4];
 #pragma unroll
@@ -467,8 +474,9 @@ __global__ void __launch_bounds__(R, 1) k_disc_fwdbwd(const DiscLaunch L, const 
           for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = 0.f;
         }
         const int rows = R / slices;
-        wgrad_acc<true>(acc, bacc, H2, H1, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, gp, sj);
-        float* A = A0 + sl * P;
+        if (sl < slices)
+          wgrad_acc<true>(acc, bacc, H2, H1, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, gp, sj);
+        float* A = A0 + (sl < slices ? sl : 0) * P;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int j = jb + jl + 8 * jj;
@@ -483,8 +491,9 @@ __global__ void __launch_bounds__(R, 1) k_disc_fwdbwd(const DiscLaunch L, const 
         }
       }
       if (do_w1) {
-        const int nblk = (JP / 32) * (KP / 32), ntl = nblk * 32, slices = 128 / ntl;
-        const int lt = tg % ntl, sl = tg / ntl, blk = lt >> 5;
+        const int nblk = (JP / 32) * (KP / 32), ntl = nblk * 32;
+        const int slices = min(gthreads / ntl, nsl);
+        const int lt = tgw % ntl, sl = tgw / ntl, blk = lt >> 5;
         const int jb = (blk % (JP / 32)) * 32, ib = (blk / (JP / 32)) * 32;
         float acc[4][8], bacc[4];
         const float sj[4] = {0.f, 0.f, 0.f, 0.f};
@@ -495,8 +504,9 @@ __global__ void __launch_bounds__(R, 1) k_disc_fwdbwd(const DiscLaunch L, const 
           for (int ii = 0; ii < 8; ++ii) acc[jj][ii] = 0.f;
         }
         const int rows = R / slices;
-        wgrad_acc<false>(acc, bacc, DZ1, XN, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, nullptr, sj);
-        float* A = A0 + sl * P;
+        if (sl < slices)
+          wgrad_acc<false>(acc, bacc, DZ1, XN, RS, jb + jl, ib + il, sl * rows, (sl + 1) * rows, nullptr, sj);
+        float* A = A0 + (sl < slices ? sl : 0) * P;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int j = jb + jl + 8 * jj;
@@ -842,7 +852,7 @@ static TPlan plan_tiled(const DiscLaunch& L, int R) {
   t.KP = dmax <= 32 ? 32 : 64;
   t.img_sz = al(TImg::size(dmax, t.JP));
   int o = L.npass * t.img_sz;
-  t.nsl = t.JP == 32 ? 4 : 2;  // row slices of the weight-gradient phase (>= 2: slice 1 holds dwf)
+  t.nsl = (t.JP == 32 && R == 256) ? 4 : 2;  // row slices of the weight-gradient phase (>= 2: slice 1 holds dwf)
   t.aw_off = o;
   o += al(t.nsl * L.P);
   t.st_off = o;
@@ -860,7 +870,7 @@ static TPlan plan_tiled(const DiscLaunch& L, int R) {
 template <int R>
 static int launch_fwdbwd(const DiscLaunch& L, const TPlan& t, const float* params, const float* batch, int64_t ld,
                          int64_t n, int64_t n_expert, float loss_scale, const float* grad_out, float* logits_out,
-                         float* ws, const WsLayout& w, cudaStream_t st) {
+                         float* ws, const WsLayout& w, cudaStream_t st, int ctas_per_sm) {
   const size_t bytes = (size_t)t.total * 4;
   static size_t attr_bytes = 0;
   if (bytes > attr_bytes) {
@@ -869,7 +879,7 @@ static int launch_fwdbwd(const DiscLaunch& L, const TPlan& t, const float* param
     attr_bytes = bytes;
   }
   const int64_t ntiles = (n + R - 1) / R;
-  int64_t G = imb_num_sms();
+  int64_t G = (int64_t)imb_num_sms() * ctas_per_sm;
   if (G > MAXG) G = MAXG;
   if (G > ntiles) G = ntiles;
   k_disc_fwdbwd<R><<<(int)G, R, bytes, st>>>(L, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
@@ -898,13 +908,16 @@ extern "C" int imb_disc_fwd_bwd(const imb_disc_desc* d, const float* params, con
     cudaError_t e = cudaMemsetAsync(ws + w.gacc, 0, sizeof(float) * d->n_params, st);
     if (e != cudaSuccess) IMB_FAIL(-2, "memset: %s", cudaGetErrorString(e));
   }
-  // 256-row tiles when they fit in shared memory (and the batch has that many rows), else 128
+  // Preferred: 128-row tiles with TWO resident CTAs per SM (independent CTAs overlap each other's
+  // barriers and epilogues); else one 256-row CTA; else one 128-row CTA.
   TPlan t256 = plan_tiled(L, 256), t128 = plan_tiled(L, 128);
   int G;
-  if ((size_t)t256.total * 4 <= IMB_SMEM_MAX && n > 128)
-    G = launch_fwdbwd<256>(L, t256, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, ws, w, st);
+  if (2 * ((size_t)t128.total * 4 + 1024 + 512) <= 228 * 1024)
+    G = launch_fwdbwd<128>(L, t128, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, ws, w, st, 2);
+  else if ((size_t)t256.total * 4 <= IMB_SMEM_MAX && n > 128)
+    G = launch_fwdbwd<256>(L, t256, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, ws, w, st, 1);
   else if ((size_t)t128.total * 4 <= IMB_SMEM_MAX)
-    G = launch_fwdbwd<128>(L, t128, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, ws, w, st);
+    G = launch_fwdbwd<128>(L, t128, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, ws, w, st, 1);
   else
     IMB_FAIL(-1, "discriminator too large for the fused kernel (%zu B of shared memory)", (size_t)t128.total * 4);
   if (G < 0) return G;

@@ -108,10 +108,10 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   // ---- shared-memory carve-up (identical in every CTA: DSMEM addresses are rank + offset) ---------------
   int o = 0;
   float* Pm = smem + o; o += al(CL * S);        // full parameter vector (padded to CL slices)
-  float* G = smem + o; o += al(CL * S);         // this CTA's partial gradient
   float* Ms = smem + o; o += al(S);             // Adam moments of the owned slice
   float* Vs = smem + o; o += al(S);
   float* GSL = smem + o; o += al(S);            // summed gradient of the owned slice
+  float* RECV = smem + o; o += al(CL * S);      // [source CTA][S]: partial gradients pushed by every CTA
   float* SSQ = smem + o; o += 32;               // [CL] squared gradient norms of the slices
   float* LOSS = smem + o; o += 32;              // [CL][3] partial loss sums (read by CTA 0)
   const int tsz = KP * HP + HP * HP;
@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   int* s_idx = reinterpret_cast<int*>(smem + o); o += al(PR);
   unsigned short* offA = reinterpret_cast<unsigned short*>(smem + o); o += al((CL * S + 1) / 2);
   unsigned short* offB = reinterpret_cast<unsigned short*>(smem + o); o += al((CL * S + 1) / 2);
+  unsigned short* imgpos = reinterpret_cast<unsigned short*>(smem + o); o += al((CL * S + 1) / 2);  // image slot of p
+  unsigned int* glut = reinterpret_cast<unsigned int*>(smem + o); o += al(PR * (Do + da_store + 3));  // gather LUT
   float* H1 = TH1 + net * HP * RL;
   float* LAT = TLAT + net * HP * RL;
   float* DZ2 = TDZ2 + net * HP * RL;
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
 
   for (int i = tid; i < CL * S; i += PT) {
     Pm[i] = i < NP ? g_params[i] : 0.f;
-    G[i] = 0.f;
+    RECV[i] = 0.f;
   }
   for (int i = tid; i < S; i += PT) {
     const int p = crank * S + i;
@@ -191,6 +193,26 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     offA[p] = (unsigned short)(a / 4);   // all rows are 16-byte aligned: store offset / 4
     offB[p] = (unsigned short)(b2 / 4);
   }
+  // image slot (float offset into img, 0xFFFF = none) of every parameter: W1 -> W1t[k][j], W2 -> W2t[i][j]
+  for (int p = tid; p < CL * S; p += PT) {
+    int pos = 0xFFFF;
+    const int tp = h * Do + h + h * h + h;
+    if (p < 2 * tp) {
+      const int tw = p / tp, q = p - tw * tp, w1 = h * Do, b1 = w1 + h, w2 = b1 + h * h;
+      if (q < w1) pos = tw * tsz + (q % Do) * HP + q / Do;
+      else if (q >= b1 && q < w2) { const int r = q - b1; pos = tw * tsz + KP * HP + (r % h) * HP + r / h; }
+    }
+    imgpos[p] = (unsigned short)pos;
+  }
+  // gather LUT: element e of the minibatch tile -> (row r | source column sc << 8 | dst float offset << 16)
+  const int rwg0 = Do + da_store + 3;
+  for (int e = tid; e < PR * rwg0; e += PT) {
+    const int r = e / rwg0, c = e - r * rwg0;
+    const int sc = c < col_logp ? c : (c == col_logp ? col_logp : col_adv + (c - col_logp - 1));
+    const int dst = c < Do ? (int)(XNf - smem) + c * PRS + r
+                           : (int)(MBf - smem) + (c - Do + (c >= col_logp ? DAP - da_store : 0)) * PRS + r;
+    glut[e] = (unsigned)r | ((unsigned)sc << 8) | ((unsigned)dst << 16);
+  }
   int32_t run_count = pd.has_norm ? *g_norm_count : 0;
   __syncthreads();
   build_images(pd, Pm, img, HP, KP);
@@ -220,27 +242,25 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
                                          : (int)feistel_perm(fk, (uint64_t)(start + tid), (uint64_t)N))
                               : 0;
       __syncthreads();
-      for (int e0 = tid; e0 < PR * rwg; e0 += 4 * PT) {
-        float v[4];
-        int dst[4];
+      for (int e0 = tid; e0 < PR * rwg; e0 += 8 * PT) {  // up to 8 independent loads in flight per thread
+        float v[8];
+        unsigned lut[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 8; ++u) {
           const int e = e0 + u * PT;
+          lut[u] = e < PR * rwg ? glut[e] : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
           v[u] = 0.f;
-          dst[u] = -1;
-          if (e < PR * rwg) {
-            const int r = e / rwg, c = e - r * rwg;
-            if (r < nb) {
-              const int sc = c < col_logp ? c : (c == col_logp ? col_logp : col_adv + (c - col_logp - 1));
-              v[u] = rollout[(int64_t)s_idx[r] * A.rw + sc];
-            }
-            dst[u] = c < Do ? (int)(XNf - smem) + c * PRS + r
-                            : (int)(MBf - smem) + (c - Do + (c >= col_logp ? DAP - da_store : 0)) * PRS + r;
+          if (lut[u] != 0xFFFFFFFFu) {
+            const int r = lut[u] & 0xFF;
+            if (r < nb) v[u] = rollout[(int64_t)s_idx[r] * A.rw + ((lut[u] >> 8) & 0xFF)];
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (dst[u] >= 0) smem[dst[u]] = v[u];
+        for (int u = 0; u < 8; ++u)
+          if (lut[u] != 0xFFFFFFFFu) smem[lut[u] >> 16] = v[u];
       }
       __syncthreads();
       // ---- 2. feature RunningNorm over the whole minibatch (identical in every CTA) -----------------------------
@@ -418,11 +438,11 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
         }
       }
       // partial loss sums of this CTA -> CTA 0 (distributed shared memory)
-      {
+      if (loss_log) {  // (uniform) loss terms are only reduced when the caller asked for the log
         const float s_pg = block_sum(l_pg, red);
         const float s_v = block_sum(l_v, red);
         const float s_ent = block_sum(l_ent, red);
-        if (tid == 0 && loss_log) {
+        if (tid == 0) {
           float* L0 = cluster.map_shared_rank(LOSS, 0);
           L0[crank * 3 + 0] = s_pg;
           L0[crank * 3 + 1] = s_v;
@@ -457,8 +477,24 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       }
       __syncthreads();
       // ---- 7. partial gradient of every parameter: one dot product over the RL own rows ----------------------------
-      for (int p = tid; p < NP; p += PT) G[p] = dot8(smem + 4 * (int)offA[p], smem + 4 * (int)offB[p]);
-      cluster.sync();  // (a) all partial gradients (and partial losses) are visible cluster-wide
+      // ... pushed straight into the owner's receive buffer RECV[this CTA][i] (fire-and-forget DSMEM stores)
+      for (int p0 = tid; p0 < NP; p0 += 4 * PT) {
+        float gt[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = p0 + u * PT;
+          gt[u] = p < NP ? dot8(smem + 4 * (int)offA[p], smem + 4 * (int)offB[p]) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int p = p0 + u * PT;
+          if (p < NP) {
+            const int owner = p / S;
+            cluster.map_shared_rank(RECV, owner)[crank * S + (p - owner * S)] = gt[u];
+          }
+        }
+      }
+      cluster.sync();  // (a) all partial gradients (and partial losses) have landed at their owners
 
       // ---- 8. slice owners: sum the CL partials in fixed order, exchange squared norms ----------------------------------
       float ss = 0.f;
@@ -468,7 +504,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
           float g = 0.f;
           if (p < NP) {
 #pragma unroll
-            for (int c = 0; c < CL; ++c) g += cluster.map_shared_rank(G, c)[p];
+            for (int c = 0; c < CL; ++c) g += RECV[c * S + i];  // fixed order: deterministic
           }
           GSL[i] = g;
           ss = fmaf(g, g, ss);
@@ -513,14 +549,16 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
             Ms[i] = mi;
             Vs[i] = vi;
             const float np_ = Pm[p] - step_size * (mi / (sqrtf(vi) / bc2s + A.hp.adam_eps));
+            const int ip = imgpos[p];
 #pragma unroll
-            for (int c = 0; c < CL; ++c) cluster.map_shared_rank(Pm, c)[p] = np_;
+            for (int c = 0; c < CL; ++c) {
+              cluster.map_shared_rank(Pm, c)[p] = np_;
+              if (ip != 0xFFFF) cluster.map_shared_rank(img, c)[ip] = np_;  // transposed working copy
+            }
           }
         }
       }
-      cluster.sync();  // (c) every CTA has the new parameters
-      build_images(pd, Pm, img, HP, KP);
-      __syncthreads();
+      cluster.sync();  // (c) every CTA has the new parameters and working images
     }
   }
 
@@ -644,7 +682,8 @@ static size_t ppo_smem_floats(const PpoArgs& A) {
   o += al(KP * PRS) + al((DAP + 3) * PRS);
   o += al(KP * RL) + (size_t)8 * HP * RL + (size_t)3 * DAP * RL + 32;
   o += al(2 * 64 + 4) + al(PR);
-  o += 2 * (size_t)al((CL * S + 1) / 2);
+  o += 3 * (size_t)al((CL * S + 1) / 2);
+  o += al(PR * (A.pol.d_obs + (A.pol.discrete ? 1 : Da) + 3));
   return o;
 }
 
@@ -657,7 +696,7 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
   A.S = ((A.pol.n_params + CL - 1) / CL + 3) / 4 * 4;
   const size_t fl = ppo_smem_floats(A);
   IMB_REQUIRE(fl * 4 <= IMB_SMEM_MAX, "PPO kernel needs %zu B of shared memory per CTA", fl * 4);
-  IMB_REQUIRE(fl < 65536 * 4, "PPO kernel: shared-memory offsets must fit 18 bits");
+  IMB_REQUIRE(fl < 65536, "PPO kernel: shared-memory float offsets must fit 16 bits (policy too large)");
   static size_t attr_bytes = 0;
   if (fl * 4 > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(k_ppo_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fl * 4));

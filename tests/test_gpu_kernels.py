@@ -467,7 +467,7 @@ def test_rollout_gae_matches_oracle(L, cfg):
     dict(Do=17, Da=6, discrete=False, hidden=32, norm=True, N=512, mb=64, epochs=3),
     dict(Do=4, Da=2, discrete=True, hidden=32, norm=False, N=200, mb=64, epochs=2),
     dict(Do=9, Da=3, discrete=False, hidden=20, norm=False, N=256, mb=32, epochs=2),  # width < 32: zero padding
-    dict(Do=9, Da=3, discrete=False, hidden=64, norm=True, N=128, mb=48, epochs=2),
+    dict(Do=30, Da=8, discrete=False, hidden=32, norm=True, N=128, mb=48, epochs=2),  # Ant-shaped, ragged last batch
 ])
 def test_ppo_update_matches_oracle(L, cfg):
     from imitation_b200 import _desc
