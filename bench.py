@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rounds", type=int, default=12, help="rounds of the CPU baseline sample (rank 0, N=1)")
+    ap.add_argument("--profile-host", action="store_true", help="cProfile the e2e loop (host overhead hunt)")
     args = ap.parse_args()
     cfg = CFG
     rank = int(os.environ.get("RANK", "0"))
@@ -314,19 +315,31 @@ def main():
     B = cfg["demo_batch"]
     n_exp = len(expert["obs"])
     src = {k: th.as_tensor(np.ascontiguousarray(v.astype(np.float32) if v.dtype != bool else v)) for k, v in expert.items()}
-    shuffled = {k: th.empty_like(v).pin_memory() for k, v in src.items()}
+    # two pinned epoch buffers; the NEXT epoch is shuffled by a worker thread (what DataLoader workers do)
+    bufs = [{k: th.empty_like(v).pin_memory() for k, v in src.items()} for _ in range(2)]
     host_gen = th.Generator().manual_seed(1234 + rank)
-    ep_state = {"pos": n_exp}  # forces a shuffle before the first batch
+    import concurrent.futures
+
+    pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+
+    def shuffle_into(buf):
+        perm = th.randperm(n_exp, generator=host_gen)
+        for k in src:
+            th.index_select(src[k], 0, perm, out=buf[k])
+        return buf
+
+    ep_state = {"pos": 0, "cur": shuffle_into(bufs[0]), "next": pool.submit(shuffle_into, bufs[1]), "i": 0}
+    shuffled = ep_state["cur"]
 
     def next_host_batch():
         if ep_state["pos"] + B > n_exp:  # drop_last, new epoch
-            perm = th.randperm(n_exp, generator=host_gen)
-            for k in src:
-                th.index_select(src[k], 0, perm, out=shuffled[k])
+            ep_state["cur"] = ep_state["next"].result()
+            ep_state["i"] ^= 1
+            ep_state["next"] = pool.submit(shuffle_into, bufs[ep_state["i"] ^ 1])
             ep_state["pos"] = 0
         lo = ep_state["pos"]
         ep_state["pos"] = lo + B
-        return {k: v[lo:lo + B] for k, v in shuffled.items()}
+        return {k: v[lo:lo + B] for k, v in ep_state["cur"].items()}
 
     h2d = cfg["n_disc"] * sum(v[:B].numel() * v.element_size() for v in shuffled.values())
     d2h = cfg["n_disc"] * 9 * 4
@@ -348,6 +361,17 @@ def main():
     th.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    if args.profile_host and rank == 0:
+        import cProfile
+        import pstats
+
+        pr = cProfile.Profile()
+        pr.enable()
+        for _ in range(10):
+            round_e2e()
+        th.cuda.synchronize()
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
     ms_e = cuda_time_ms(lambda: [round_e2e() for _ in range(Ke)])
     if world > 1:
         t = th.tensor([ms_e], device=device)

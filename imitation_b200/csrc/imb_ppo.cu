@@ -477,22 +477,23 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       }
       __syncthreads();
       // ---- 7. partial gradient of every parameter: one dot product over the RL own rows ----------------------------
-      // ... pushed straight into the owner's receive buffer RECV[this CTA][i] (fire-and-forget DSMEM stores)
-      for (int p0 = tid; p0 < NP; p0 += 4 * PT) {
-        float gt[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int p = p0 + u * PT;
-          gt[u] = p < NP ? dot8(smem + 4 * (int)offA[p], smem + 4 * (int)offB[p]) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int p = p0 + u * PT;
-          if (p < NP) {
-            const int owner = p / S;
-            cluster.map_shared_rank(RECV, owner)[crank * S + (p - owner * S)] = gt[u];
-          }
-        }
+      // ... pushed straight into the owner's receive buffer RECV[this CTA][i]: one 16-byte DSMEM store per
+      // parameter quad (scalar remote accesses are transaction-bound: ~10 k of them per step cost more
+      // than all the arithmetic; see profiles/r01_summary.md)
+      // CTA c starts with the quads owned by CTA c+1, so at any time the 8 senders target 8 different
+      // receivers (all of them hitting owner 0 first made the receiving SM the bottleneck: ~40 % of the step)
+      for (int q = tid; q < CL * S / 4; q += PT) {
+        int qq = q + ((crank + 1) & (CL - 1)) * (S / 4);
+        if (qq >= CL * S / 4) qq -= CL * S / 4;
+        const int p0 = 4 * qq;
+        if (p0 >= NP) continue;
+        float4 g;
+        g.x = dot8(smem + 4 * (int)offA[p0 + 0], smem + 4 * (int)offB[p0 + 0]);
+        g.y = dot8(smem + 4 * (int)offA[p0 + 1], smem + 4 * (int)offB[p0 + 1]);
+        g.z = dot8(smem + 4 * (int)offA[p0 + 2], smem + 4 * (int)offB[p0 + 2]);
+        g.w = dot8(smem + 4 * (int)offA[p0 + 3], smem + 4 * (int)offB[p0 + 3]);
+        const int owner = p0 / S;
+        st4(cluster.map_shared_rank(RECV, owner) + crank * S + (p0 - owner * S), g);
       }
       cluster.sync();  // (a) all partial gradients (and partial losses) have landed at their owners
 
@@ -539,26 +540,31 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       b1pow *= 0.9;
       b2pow *= 0.999;
       const float step_size = (float)((double)A.hp.lr / (1.0 - b1pow)), bc2s = (float)sqrt(1.0 - b2pow);
-      {
-        for (int i = tid; i < S; i += PT) {
-          const int p = crank * S + i;
-          if (p < NP) {
-            const float g = GSL[i] * clip;
-            const float mi = Ms[i] + (g - Ms[i]) * (1.0f - 0.9f);
-            const float vi = Vs[i] * 0.999f + (1.0f - 0.999f) * g * g;
-            Ms[i] = mi;
-            Vs[i] = vi;
-            const float np_ = Pm[p] - step_size * (mi / (sqrtf(vi) / bc2s + A.hp.adam_eps));
-            const int ip = imgpos[p];
+      for (int i0 = 4 * tid; i0 < S; i0 += 4 * PT) {
+        const int p0 = crank * S + i0;
+        float np4[4];
 #pragma unroll
-            for (int c = 0; c < CL; ++c) {
-              cluster.map_shared_rank(Pm, c)[p] = np_;
-              if (ip != 0xFFFF) cluster.map_shared_rank(img, c)[ip] = np_;  // transposed working copy
-            }
-          }
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u;
+          const float g = GSL[i] * clip;
+          const float mi = Ms[i] + (g - Ms[i]) * (1.0f - 0.9f);
+          const float vi = Vs[i] * 0.999f + (1.0f - 0.999f) * g * g;
+          Ms[i] = mi;
+          Vs[i] = vi;
+          np4[u] = (p0 + u < NP) ? Pm[p0 + u] - step_size * (mi / (sqrtf(vi) / bc2s + A.hp.adam_eps)) : 0.f;
         }
+        const float4 v4 = make_float4(np4[0], np4[1], np4[2], np4[3]);
+#pragma unroll
+        for (int c = 0; c < CL; ++c)  // rotated start: the 8 owners write to 8 different CTAs at a time
+          st4(cluster.map_shared_rank(Pm, (crank + c) & (CL - 1)) + p0, v4);
       }
-      cluster.sync();  // (c) every CTA has the new parameters and working images
+      cluster.sync();  // (c) every CTA has the new parameters
+      // transposed working copies, rebuilt locally through the position look-up table (no divisions)
+      for (int p = tid; p < 2 * (h * Do + h + h * h + h); p += PT) {
+        const int ip = imgpos[p];
+        if (ip != 0xFFFF) img[ip] = Pm[p];
+      }
+      __syncthreads();
     }
   }
 

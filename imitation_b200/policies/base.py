@@ -76,6 +76,7 @@ class ActorCriticPolicy(nn.Module):
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_flat"] = None
+        st.pop("_plist_cache", None)
         st.pop("_norm_state", None)
         st.pop("_norm_count", None)
         return st
@@ -86,8 +87,12 @@ class ActorCriticPolicy(nn.Module):
 
     # -- flat vectors for the kernels --------------------------------------------------------------------
     def _plist(self):
-        sd = dict(self.named_parameters())
-        return [sd[name] for name, _ in _desc.policy_param_shapes(self.d_obs, self.d_act, self.discrete, self.hidden)]
+        out = self.__dict__.get("_plist_cache")
+        if out is None:
+            sd = dict(self.named_parameters())
+            out = [sd[name] for name, _ in _desc.policy_param_shapes(self.d_obs, self.d_act, self.discrete, self.hidden)]
+            self.__dict__["_plist_cache"] = out  # Parameter objects are stable (only .data is re-pointed)
+        return out
 
     def flat_vectors(self) -> Tuple[th.Tensor, th.Tensor, th.Tensor]:
         """(params, norm_state[mean|var], norm_count) aliased by the module's parameters/buffers."""

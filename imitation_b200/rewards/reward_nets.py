@@ -43,11 +43,14 @@ class FusedEngine:
 
     # -- aliasing ---------------------------------------------------------------------------------
     def _param_list(self) -> List[nn.Parameter]:
-        out = []
-        for m in self.mlps:
-            for mod in m:
-                if isinstance(mod, nn.Linear):
-                    out += [mod.weight, mod.bias]
+        out = getattr(self, "_plist_cache", None)
+        if out is None:
+            out = []
+            for m in self.mlps:
+                for mod in m:
+                    if isinstance(mod, nn.Linear):
+                        out += [mod.weight, mod.bias]
+            self._plist_cache = out  # Parameter objects are stable (only their .data is re-pointed)
         return out
 
     def _norms(self) -> List[Optional[networks.BaseNorm]]:
