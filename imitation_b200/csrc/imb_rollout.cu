@@ -1,15 +1,5 @@
-// imb_rollout.cu -- C-ABI entry points of stage 1 (kernels: imb_rollout_impl.cuh; the four
-// (policy width, reward-net width) instantiations are compiled in parallel translation units).
+// imb_rollout.cu -- C-ABI entry points of stage 1 (kernels: imb_rollout_impl.cuh).
 #include "imb_rollout_impl.cuh"
-
-#define IMB_RL_ARGS                                                                                              \
-  const void *A, const void *L, const float *env_params, float *env_obs, const float *pol_params,               \
-      const float *pol_norm, const float *disc_params, float *rollout, float *ring, float *flat_out, float *aux, \
-      const float *noise, const int64_t *state, cudaStream_t st
-int imb_rl_32_32(IMB_RL_ARGS);
-int imb_rl_32_64(IMB_RL_ARGS);
-int imb_rl_64_32(IMB_RL_ARGS);
-int imb_rl_64_64(IMB_RL_ARGS);
 
 extern "C" int imb_rollout_row_width(const imb_policy_desc* pol) {
   return pol->d_obs + (pol->discrete ? 1 : pol->d_act) + 5;
@@ -38,7 +28,6 @@ extern "C" int imb_rollout(const imb_env_desc* env, const float* env_params, flo
   A.ring_capacity = ring ? ring_capacity : 0;
   DiscLaunch L;
   memset(&L, 0, sizeof(L));
-  int HD = 32;
   if (reward_mode != 0) {
     IMB_REQUIRE(disc && disc_params, "reward_mode != 0 needs a reward net");
     const int onehot = env->discrete ? env->d_act : env->d_act;
@@ -46,20 +35,10 @@ extern "C" int imb_rollout(const imb_env_desc* env, const float* env_params, flo
     imb_disc_desc dd = *disc;
     dd.subtract_logp = 0;  // reward_train.predict_processed never subtracts log pi (airl.py:121-124)
     if (int rc = build_launch(&dd, disc_norm, nullptr, L)) return rc;
-    for (int p = 0; p < L.npass; ++p) {
-      if (L.pass[p].n_hidden >= 1 && L.pass[p].h1 > HD) HD = 64;
-      if (L.pass[p].n_hidden >= 2 && L.pass[p].h2 > HD) HD = 64;
-    }
   }
   cudaStream_t st = (cudaStream_t)stream;
-#define IMB_RL(fn)                                                                                             \
-  return fn(&A, &L, env_params, env_obs, pol_params, pol_norm, disc_params, rollout, ring, flat_out, aux, noise, \
-            state, st)
-  if (pol->hidden <= 32 && HD == 32) IMB_RL(imb_rl_32_32);
-  if (pol->hidden <= 32 && HD == 64) IMB_RL(imb_rl_32_64);
-  if (pol->hidden > 32 && HD == 32) IMB_RL(imb_rl_64_32);
-  IMB_RL(imb_rl_64_64);
-#undef IMB_RL
+  return launch_rollout(A, L, env_params, env_obs, pol_params, pol_norm, disc_params, rollout, ring, flat_out, aux,
+                        noise, state, st);
 }
 
 extern "C" int imb_rollout_advance(int64_t* state, int64_t n_envs, int64_t n_steps, int32_t horizon,

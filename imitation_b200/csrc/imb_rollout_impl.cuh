@@ -1,7 +1,9 @@
-// imb_rollout.cu -- stage 1 of the GAIL/AIRL round: generator rollouts, GPU resident.
+// imb_rollout_impl.cuh -- stage 1 of the GAIL/AIRL round: generator rollouts, GPU resident.
 //
-// One launch runs T environment steps for E environments (thread per env; environments never
-// interact inside a rollout because the reward net and the policy run in eval mode):
+// One launch runs T environment steps for E environments; a CTA owns 128 environments (= tile rows)
+// and every per-step network evaluation is a shared-memory tiled GEMM over that tile
+// (imb_tile.cuh), with the environment state, the policy, the reward network and the synthetic
+// dynamics all resident in shared memory for the whole rollout:
 //   policy forward + sampling      SB3 OnPolicyAlgorithm.collect_rollouts (restated; see
 //                                  oracle/ppo_port.py -- parity unpinned by the reference)
 //   env step + auto-reset          synthetic MuJoCo-shaped env; VecEnv
@@ -14,62 +16,80 @@
 //                                  envs are fixed-horizon and run in lock-step; rows go straight
 //                                  into the generator ring with Buffer.store truncation/wrap
 //                                  (data/buffer.py:174-192).
-// Env state is SoA [d_obs][E] in HBM; all weights (<50 KB) live in shared memory.
+// Env state is SoA [d_obs][E] in HBM (coalesced tile load/store); environments never interact inside
+// a rollout because the reward net and the policy run in eval mode.
+// (First version: one thread per env with register-resident MLPs -- 218 us for 1024 envs x 4 steps,
+//  250 KB of unrolled SASS per variant; see profiles/r01_summary.md.)
 #pragma once
 #include "imb_common.cuh"
 #include "imb_mlp.cuh"
+#include "imb_tile.cuh"
 
 namespace {
 
-constexpr int RT = 32;  // threads (= envs) per CTA: small CTAs spread the envs over many SMs
+constexpr int RR = 128;              // envs (tile rows) per CTA = threads per CTA
+constexpr int RRS = RR + TILE_PAD;   // tile row stride
 
-// shared-memory image of the actor-critic policy, tower width HP (two tanh layers)
-template <int HP>
-struct PolSm {
-  int w1t_pi, b1_pi, w2t_pi, b2_pi, w1t_vf, b1_vf, w2t_vf, b2_vf, wa, ba, wv, bv, lstd, mean, istd, total;
-  __host__ __device__ PolSm(int d_obs, int d_act) {
+struct RolloutArgs {
+  imb_env_desc env;
+  imb_policy_desc pol;
+  imb_ppo_hparams hp;
+  int reward_mode;
+  int deterministic;  // 1: act = mean (Box) / argmax (Discrete), like policy.predict(deterministic=True)
+  int64_t E, T;
+  int rw;             // rollout row width
+  int64_t ring_capacity;
+  // shared-memory plan (floats)
+  int HP, JP, IP, KU;          // policy width, reward-net width, obs width (padded to 32), d_obs + d_act
+  int pol_off, env_off, img_off, img_sz, obsu_off, xn_off, h1_off, h2_off, nobs_off, vec_off, total;
+};
+
+// policy image (runtime tower width HP, zero padded):
+//   piW1t[Do][HP] pib1[HP] piW2t[HP][HP] pib2[HP] vfW1t vfb1 vfW2t vfb2 Wa[Da][HP] ba[64] wv[HP] bv[4] lstd[64] mean[64] istd[64]
+struct PolImg {
+  int w1p, b1p, w2p, b2p, w1v, b1v, w2v, b2v, wa, ba, wv, bv, lstd, mean, istd, total;
+  __host__ __device__ PolImg(int Do, int Da, int HP) {
     int o = 0;
-    w1t_pi = o; o += d_obs * HP;
-    b1_pi = o; o += HP;
-    w2t_pi = o; o += HP * HP;
-    b2_pi = o; o += HP;
-    w1t_vf = o; o += d_obs * HP;
-    b1_vf = o; o += HP;
-    w2t_vf = o; o += HP * HP;
-    b2_vf = o; o += HP;
-    wa = o; o += d_act * HP;
-    ba = o; o += (d_act + 3) / 4 * 4;
+    w1p = o; o += Do * HP;
+    b1p = o; o += HP;
+    w2p = o; o += HP * HP;
+    b2p = o; o += HP;
+    w1v = o; o += Do * HP;
+    b1v = o; o += HP;
+    w2v = o; o += HP * HP;
+    b2v = o; o += HP;
+    wa = o; o += Da * HP;
+    ba = o; o += 64;
     wv = o; o += HP;
     bv = o; o += 4;
-    lstd = o; o += (d_act + 3) / 4 * 4;
-    mean = o; o += (d_obs + 3) / 4 * 4;
-    istd = o; o += (d_obs + 3) / 4 * 4;
+    lstd = o; o += 64;
+    mean = o; o += 64;
+    istd = o; o += 64;
     total = o;
   }
 };
 
-template <int HP>
-__device__ void load_policy(float* sm, const PolSm<HP>& S, const imb_policy_desc& pd, const float* __restrict__ q,
-                            const float* __restrict__ norm) {
+__device__ void load_policy_img(float* sm, const PolImg& S, const imb_policy_desc& pd, int HP,
+                                const float* __restrict__ q, const float* __restrict__ norm) {
   const int tid = threadIdx.x, nt = blockDim.x;
   const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden;
   for (int i = tid; i < S.total; i += nt) sm[i] = 0.f;
   __syncthreads();
   for (int i = tid; i < h * Do; i += nt) {
     const int j = i / Do, k = i - j * Do;
-    sm[S.w1t_pi + k * HP + j] = q[pd.off_pi_w1 + i];
-    sm[S.w1t_vf + k * HP + j] = q[pd.off_vf_w1 + i];
+    sm[S.w1p + k * HP + j] = q[pd.off_pi_w1 + i];
+    sm[S.w1v + k * HP + j] = q[pd.off_vf_w1 + i];
   }
   for (int i = tid; i < h * h; i += nt) {
     const int j = i / h, ii = i - j * h;
-    sm[S.w2t_pi + ii * HP + j] = q[pd.off_pi_w2 + i];
-    sm[S.w2t_vf + ii * HP + j] = q[pd.off_vf_w2 + i];
+    sm[S.w2p + ii * HP + j] = q[pd.off_pi_w2 + i];
+    sm[S.w2v + ii * HP + j] = q[pd.off_vf_w2 + i];
   }
   for (int i = tid; i < h; i += nt) {
-    sm[S.b1_pi + i] = q[pd.off_pi_b1 + i];
-    sm[S.b2_pi + i] = q[pd.off_pi_b2 + i];
-    sm[S.b1_vf + i] = q[pd.off_vf_b1 + i];
-    sm[S.b2_vf + i] = q[pd.off_vf_b2 + i];
+    sm[S.b1p + i] = q[pd.off_pi_b1 + i];
+    sm[S.b2p + i] = q[pd.off_pi_b2 + i];
+    sm[S.b1v + i] = q[pd.off_vf_b1 + i];
+    sm[S.b2v + i] = q[pd.off_vf_b2 + i];
     sm[S.wv + i] = q[pd.off_val_w + i];
   }
   for (int i = tid; i < Da * h; i += nt) {
@@ -82,78 +102,10 @@ __device__ void load_policy(float* sm, const PolSm<HP>& S, const imb_policy_desc
   }
   if (tid == 0) sm[S.bv] = q[pd.off_val_b];
   for (int i = tid; i < Do; i += nt) {
-    if (pd.has_norm) {
-      sm[S.mean + i] = norm[i];
-      sm[S.istd + i] = 1.0f / sqrtf(norm[Do + i] + pd.norm_eps);
-    } else {
-      sm[S.mean + i] = 0.f;
-      sm[S.istd + i] = 1.f;
-    }
+    sm[S.mean + i] = pd.has_norm ? norm[i] : 0.f;
+    sm[S.istd + i] = pd.has_norm ? 1.0f / sqrtf(norm[Do + i] + pd.norm_eps) : 1.f;
   }
 }
-
-// two-layer tanh tower: lat = tanh(W2 tanh(W1 x + b1) + b2); x in shared memory (stride 1)
-template <int HP>
-__device__ __forceinline__ void tower_fwd(const float* __restrict__ W1t, const float* __restrict__ b1,
-                                          const float* __restrict__ W2t, const float* __restrict__ b2,
-                                          const float* __restrict__ x, int din, float (&lat)[HP]) {
-  float h1[HP];
-#pragma unroll
-  for (int j = 0; j < HP; ++j) h1[j] = b1[j];
-  for (int k = 0; k < din; ++k) {
-    const float xv = x[k];
-    const float4* w = reinterpret_cast<const float4*>(W1t + k * HP);
-#pragma unroll
-    for (int j4 = 0; j4 < HP / 4; ++j4) {
-      const float4 ww = w[j4];
-      h1[4 * j4 + 0] = fmaf(ww.x, xv, h1[4 * j4 + 0]);
-      h1[4 * j4 + 1] = fmaf(ww.y, xv, h1[4 * j4 + 1]);
-      h1[4 * j4 + 2] = fmaf(ww.z, xv, h1[4 * j4 + 2]);
-      h1[4 * j4 + 3] = fmaf(ww.w, xv, h1[4 * j4 + 3]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < HP; ++j) {
-    h1[j] = tanhf(h1[j]);
-    lat[j] = b2[j];
-  }
-#pragma unroll
-  for (int i = 0; i < HP; ++i) {
-    const float hv = h1[i];
-    const float4* w = reinterpret_cast<const float4*>(W2t + i * HP);
-#pragma unroll
-    for (int j4 = 0; j4 < HP / 4; ++j4) {
-      const float4 ww = w[j4];
-      lat[4 * j4 + 0] = fmaf(ww.x, hv, lat[4 * j4 + 0]);
-      lat[4 * j4 + 1] = fmaf(ww.y, hv, lat[4 * j4 + 1]);
-      lat[4 * j4 + 2] = fmaf(ww.z, hv, lat[4 * j4 + 2]);
-      lat[4 * j4 + 3] = fmaf(ww.w, hv, lat[4 * j4 + 3]);
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < HP; ++j) lat[j] = tanhf(lat[j]);
-}
-
-template <int HP>
-__device__ __forceinline__ float value_of(const float* psm, const PolSm<HP>& S, const float* feat, int d_obs) {
-  float lat[HP];
-  tower_fwd<HP>(psm + S.w1t_vf, psm + S.b1_vf, psm + S.w2t_vf, psm + S.b2_vf, feat, d_obs, lat);
-  float v = psm[S.bv];
-#pragma unroll
-  for (int j = 0; j < HP; ++j) v = fmaf(psm[S.wv + j], lat[j], v);
-  return v;
-}
-
-struct RolloutArgs {
-  imb_env_desc env;
-  imb_policy_desc pol;
-  imb_ppo_hparams hp;
-  int reward_mode;
-  int deterministic;  // 1: act = mean (Box) / argmax (Discrete), like policy.predict(deterministic=True)
-  int64_t E, T;
-  int rw;             // rollout row width
-  int64_t ring_capacity;
-};
 
 // flattened (reference-order) index of local step t of env e; see file header
 __device__ __forceinline__ int64_t flat_index(int64_t e, int64_t t, int64_t E, int64_t T, int64_t t0, int64_t H) {
@@ -164,62 +116,98 @@ __device__ __forceinline__ int64_t flat_index(int64_t e, int64_t t, int64_t E, i
   return E * start + e * (end - start) + (t - start);
 }
 
-template <int HP, int HD>
-__global__ void __launch_bounds__(RT) k_rollout(const RolloutArgs A, const DiscLaunch L,
-                                                const float* __restrict__ env_params, float* __restrict__ env_obs,
-                                                const float* __restrict__ pol_params,
-                                                const float* __restrict__ pol_norm,
-                                                const float* __restrict__ disc_params, float* __restrict__ rollout,
-                                                float* __restrict__ ring, float* __restrict__ flat_out,
-                                                float* __restrict__ aux, const float* __restrict__ noise,
-                                                const int64_t* __restrict__ state, int img1_off, int env_off,
-                                                int pol_off, int scr_off, int scr_ld) {
-  extern __shared__ __align__(128) float smem[];
-  const int tid = threadIdx.x;
-  const int Do = A.env.d_obs, Da = A.env.d_act;
-  const PolSm<HP> S(Do, Da);
-  float* img[MAX_PASS] = {smem, smem + img1_off, smem + img1_off};
-  float* esm = smem + env_off;  // A[Do][Do] | Bm[Do][Da] | c[Do] | w[Do]
-  float* psm = smem + pol_off;
-  float* scr = smem + scr_off + tid * scr_ld;  // per-thread scratch: obs | u | nobs | xn
-  float* s_obs = scr;
-  float* s_u = scr + Do;
-  float* s_no = s_u + Da;
-  float* s_xn = s_no + Do;
+enum { ACT_TANH = 0, ACT_RELU = 1 };
 
-  // ---- one-time loads ------------------------------------------------------------------------------
-  float* mean2 = nullptr;
-  float* istd2 = nullptr;
-  if (A.reward_mode != 0) {
-    load_mlp<HD>(img[0], L.pass[0], disc_params);
-    if (L.npass == 3) {
-      load_mlp<HD>(img[1], L.pass[1], disc_params);
-      const int din = L.pass[2].din;
-      mean2 = img[1] + MlpSm<HD>::size(din);
-      istd2 = mean2 + IMB_MAX_DIN;
-      for (int i = tid; i < din; i += RT) {
-        if (L.pass[2].has_norm) {
-          mean2[i] = L.pass[2].norm[i];
-          istd2[i] = 1.0f / sqrtf(L.pass[2].norm[din + i] + L.pass[2].eps);
-        } else {
-          mean2[i] = 0.f;
-          istd2[i] = 1.f;
-        }
+// OUT[j][r] = act(bias[j] + sum_k A[k][r] * Wk[k][j]) for j < JPx (multiple of 32); 128 threads:
+// warp -> 8-column group, lane -> 4 rows.
+template <int ACT>
+__device__ __forceinline__ void tile_layer(const float* __restrict__ A, int K, const float* __restrict__ Wk, int wld,
+                                           const float* __restrict__ bias, float* __restrict__ OUT, int JPx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int rq[1] = {lane * 4};
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 gq[1] = {z4};
+  for (int jh = 0; jh < JPx / 32; ++jh) {
+    const int j0 = jh * 32 + warp * 8;
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int t = 0; t < 8; ++t) acc[a][t] = 0.f;
+    gemm_acc<1, false>(acc, A, RRS, rq, Wk, wld, j0, K, gq, nullptr);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float b = bias[j0 + t];
+      float4 v;
+      if (ACT == ACT_TANH) {
+        v = make_float4(tanhf(acc[0][t] + b), tanhf(acc[1][t] + b), tanhf(acc[2][t] + b), tanhf(acc[3][t] + b));
+      } else {
+        v = make_float4(fmaxf(acc[0][t] + b, 0.f), fmaxf(acc[1][t] + b, 0.f), fmaxf(acc[2][t] + b, 0.f),
+                        fmaxf(acc[3][t] + b, 0.f));
       }
+      st4(OUT + (j0 + t) * RRS + rq[0], v);
     }
   }
-  load_policy<HP>(psm, S, A.pol, pol_params, pol_norm);
-  const int n_env_p = Do * Do + Do * Da + 2 * Do;
-  for (int i = tid; i < n_env_p; i += RT) esm[i] = env_params[i];
-  __syncthreads();
-  const float* eA = esm;
-  const float* eB = esm + Do * Do;
-  const float* eC = eB + Do * Da;
-  const float* eW = eC + Do;
+}
 
-  const int64_t e = (int64_t)blockIdx.x * RT + tid;
-  if (e >= A.E) return;  // no block-level sync below this point
+__global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const DiscLaunch L,
+                                                   const float* __restrict__ env_params, float* __restrict__ env_obs,
+                                                   const float* __restrict__ pol_params,
+                                                   const float* __restrict__ pol_norm,
+                                                   const float* __restrict__ disc_params, float* __restrict__ rollout,
+                                                   float* __restrict__ ring, float* __restrict__ flat_out,
+                                                   float* __restrict__ aux, const float* __restrict__ noise,
+                                                   const int64_t* __restrict__ state) {
+  extern __shared__ __align__(128) float smem[];
+  const int tid = threadIdx.x;
+  const int Do = A.env.d_obs, Da = A.env.d_act, h = A.pol.hidden, HP = A.HP, JP = A.JP, IP = A.IP, KU = A.KU;
+  const PolImg S(Do, Da, HP);
+  float* psm = smem + A.pol_off;
+  float* esm = smem + A.env_off;   // ABt[KU][IP] | c[IP] | w[IP]
+  float* OBSU = smem + A.obsu_off; // [KU][RRS]: obs rows, then the control (clipped action / one-hot) rows
+  float* XN = smem + A.xn_off;     // [max(KP)][RRS]: normalised MLP inputs
+  float* H1 = smem + A.h1_off;
+  float* H2 = smem + A.h2_off;
+  float* NOBS = smem + A.nobs_off; // [IP][RRS]
+  float* vec = smem + A.vec_off;   // lg[RR]
+  float* lg = vec;
+
+  // ---- one-time loads ------------------------------------------------------------------------------
+  if (A.reward_mode != 0)
+    for (int p = 0; p < L.npass; ++p)
+      load_timg(smem + A.img_off + p * A.img_sz, L.pass[p], JP, disc_params,
+                L.pass[p].has_norm ? L.pass[p].norm : nullptr, L.pass[p].eps);
+  load_policy_img(psm, S, A.pol, HP, pol_params, pol_norm);
+  for (int i = tid; i < (KU + 2) * IP; i += RR) esm[i] = 0.f;
+  __syncthreads();
+  {
+    const float* eA = env_params;
+    const float* eB = eA + Do * Do;
+    const float* eC = eB + Do * Da;
+    const float* eW = eC + Do;
+    for (int i = tid; i < Do * Do; i += RR) {
+      const int r = i / Do, c = i - r * Do;  // A[r][c] -> ABt[c][r]
+      esm[c * IP + r] = eA[i];
+    }
+    for (int i = tid; i < Do * Da; i += RR) {
+      const int r = i / Da, c = i - r * Da;  // B[r][c] -> ABt[Do + c][r]
+      esm[(Do + c) * IP + r] = eB[i];
+    }
+    for (int i = tid; i < Do; i += RR) {
+      esm[KU * IP + i] = eC[i];
+      esm[(KU + 1) * IP + i] = eW[i];
+    }
+  }
+  const float* ecv = esm + KU * IP;
+  const float* ewv = esm + (KU + 1) * IP;
   const int64_t E = A.E, T = A.T, H = A.env.horizon;
+  const int64_t e0 = (int64_t)blockIdx.x * RR;
+  const int64_t e = e0 + tid;
+  const bool live = e < E;
+  for (int k = 0; k < Do; ++k) OBSU[k * RRS + tid] = live ? env_obs[(int64_t)k * E + e] : 0.f;  // coalesced
+  for (int a = 0; a < Da; ++a) OBSU[(Do + a) * RRS + tid] = 0.f;
+  __syncthreads();
+
   const int64_t t0 = state[IMB_ST_EP_STEP];
   int64_t episode = state[IMB_ST_EPISODE];
   const int64_t gstep0 = state[IMB_ST_GLOBAL_STEP];
@@ -232,48 +220,87 @@ __global__ void __launch_bounds__(RT) k_rollout(const RolloutArgs A, const DiscL
   const int64_t skip = (A.ring_capacity > 0 && n_total > A.ring_capacity) ? n_total - A.ring_capacity : 0;
   const int64_t ring_idx0 = state[IMB_ST_RING_IDX];
 
-  for (int k = 0; k < Do; ++k) s_obs[k] = env_obs[(int64_t)k * E + e];
+  // value head on the latent tile H2 (thread per env)
+  auto value_row = [&]() {
+    float v0 = 0.f, v1 = 0.f;
+    int j = 0;
+    for (; j + 2 <= h; j += 2) {
+      v0 = fmaf(psm[S.wv + j], H2[j * RRS + tid], v0);
+      v1 = fmaf(psm[S.wv + j + 1], H2[(j + 1) * RRS + tid], v1);
+    }
+    if (j < h) v0 = fmaf(psm[S.wv + j], H2[j * RRS + tid], v0);
+    return psm[S.bv] + (v0 + v1);
+  };
+  // XN <- feature-normalised copy of a [Do][RRS] observation tile
+  auto norm_obs = [&](const float* __restrict__ SRC) {
+    for (int i = tid; i < Do * (RR / 4); i += RR) {
+      const int k = i / (RR / 4), r4 = (i - k * (RR / 4)) * 4;
+      const float4 x = ld4(SRC + k * RRS + r4);
+      const float m = psm[S.mean + k], is = psm[S.istd + k];
+      st4(XN + k * RRS + r4, make_float4((x.x - m) * is, (x.y - m) * is, (x.z - m) * is, (x.w - m) * is));
+    }
+    __syncthreads();
+  };
+  auto value_of_obs = [&](const float* __restrict__ SRC) {
+    norm_obs(SRC);
+    tile_layer<ACT_TANH>(XN, Do, psm + S.w1v, HP, psm + S.b1v, H1, HP);
+    __syncthreads();
+    tile_layer<ACT_TANH>(H1, h, psm + S.w2v, HP, psm + S.b2v, H2, HP);
+    __syncthreads();
+    const float v = value_row();
+    __syncthreads();
+    return v;
+  };
+
   bool done = false;
-  float lat[HP];
   for (int64_t t = 0; t < T; ++t) {
-    // ---- policy: features, pi tower, value ------------------------------------------------------------
-    for (int k = 0; k < Do; ++k) s_xn[k] = (s_obs[k] - psm[S.mean + k]) * psm[S.istd + k];
-    const float value = value_of<HP>(psm, S, s_xn, Do);
-    tower_fwd<HP>(psm + S.w1t_pi, psm + S.b1_pi, psm + S.w2t_pi, psm + S.b2_pi, s_xn, Do, lat);
     float* row = rollout + (e * T + t) * rw;
+    // ---- policy: value tower, then pi tower (H2 ends up holding the pi latent) ------------------------------
+    const float value = value_of_obs(OBSU);
+    tile_layer<ACT_TANH>(XN, Do, psm + S.w1p, HP, psm + S.b1p, H1, HP);
+    __syncthreads();
+    tile_layer<ACT_TANH>(H1, h, psm + S.w2p, HP, psm + S.b2p, H2, HP);
+    __syncthreads();
+    // ---- action head + sampling, thread per env ----------------------------------------------------------------
     float logp = 0.f;
     if (!A.pol.discrete) {
       for (int a = 0; a < Da; ++a) {
-        float m = psm[S.ba + a];
-#pragma unroll
-        for (int j = 0; j < HP; ++j) m = fmaf(psm[S.wa + a * HP + j], lat[j], m);
+        float m0 = 0.f, m1 = 0.f;
+        const float* wa = psm + S.wa + a * HP;
+        int j = 0;
+        for (; j + 2 <= h; j += 2) {
+          m0 = fmaf(wa[j], H2[j * RRS + tid], m0);
+          m1 = fmaf(wa[j + 1], H2[(j + 1) * RRS + tid], m1);
+        }
+        if (j < h) m0 = fmaf(wa[j], H2[j * RRS + tid], m0);
+        const float m = psm[S.ba + a] + (m0 + m1);
         const float z = A.deterministic ? 0.f
-                        : noise   ? noise[(t * E + e) * Da + a]
+                        : noise   ? (live ? noise[(t * E + e) * Da + a] : 0.f)
                                   : philox_normal(A.env.seed, IMB_STREAM_ACT_NOISE, egid, (uint32_t)(gstep0 + t), a);
         const float ls = psm[S.lstd + a];
         const float sd = expf(ls);
         const float act = fmaf(sd, z, m);
         const float diff = act - m;
         logp += -(diff * diff) / (2.0f * sd * sd) - ls - 0.9189385332046727f;
-        row[Do + a] = act;                               // SB3 stores the UNCLIPPED action
-        s_u[a] = fminf(fmaxf(act, -1.0f), 1.0f);         // the env (and the wrappers) see the clipped one
+        if (live) row[Do + a] = act;                                   // SB3 stores the UNCLIPPED action
+        OBSU[(Do + a) * RRS + tid] = fminf(fmaxf(act, -1.0f), 1.0f);   // env and wrappers see the clipped one
       }
     } else {
-      // categorical over Da logits; inverse-CDF sampling from one uniform
       float mx = -INFINITY;
       for (int a = 0; a < Da; ++a) {
-        float m = psm[S.ba + a];
-#pragma unroll
-        for (int j = 0; j < HP; ++j) m = fmaf(psm[S.wa + a * HP + j], lat[j], m);
-        s_u[a] = m;
+        float m0 = 0.f;
+        const float* wa = psm + S.wa + a * HP;
+        for (int j = 0; j < h; ++j) m0 = fmaf(wa[j], H2[j * RRS + tid], m0);
+        const float m = psm[S.ba + a] + m0;
+        OBSU[(Do + a) * RRS + tid] = m;  // logits, overwritten by the one-hot below
         mx = fmaxf(mx, m);
       }
       float se = 0.f;
-      for (int a = 0; a < Da; ++a) se += expf(s_u[a] - mx);
+      for (int a = 0; a < Da; ++a) se += expf(OBSU[(Do + a) * RRS + tid] - mx);
       const float lse = mx + logf(se);
       float u;
       if (noise) {
-        u = noise[t * E + e];
+        u = live ? noise[t * E + e] : 0.f;
       } else {
         uint32_t k0, k1;
         philox_key(A.env.seed, IMB_STREAM_ACT_NOISE, k0, k1);
@@ -283,7 +310,7 @@ __global__ void __launch_bounds__(RT) k_rollout(const RolloutArgs A, const DiscL
       float cdf = 0.f;
       bool found = false;
       for (int a = 0; a < Da; ++a) {
-        cdf += expf(s_u[a] - lse);
+        cdf += expf(OBSU[(Do + a) * RRS + tid] - lse);
         if (!found && !(u >= cdf)) {
           chosen = a;
           found = true;
@@ -292,97 +319,123 @@ __global__ void __launch_bounds__(RT) k_rollout(const RolloutArgs A, const DiscL
       if (A.deterministic) {
         chosen = 0;
         for (int a = 1; a < Da; ++a)
-          if (s_u[a] > s_u[chosen]) chosen = a;
+          if (OBSU[(Do + a) * RRS + tid] > OBSU[(Do + chosen) * RRS + tid]) chosen = a;
       }
-      logp = s_u[chosen] - lse;
-      for (int a = 0; a < Da; ++a) s_u[a] = (a == chosen) ? 1.f : 0.f;
-      row[Do] = (float)chosen;
+      logp = OBSU[(Do + chosen) * RRS + tid] - lse;
+      for (int a = 0; a < Da; ++a) OBSU[(Do + a) * RRS + tid] = (a == chosen) ? 1.f : 0.f;
+      if (live) row[Do] = (float)chosen;
     }
-    for (int k = 0; k < Do; ++k) row[k] = s_obs[k];
-    row[col_logp] = logp;
-    row[col_val] = value;
+    if (live) {
+      for (int k = 0; k < Do; ++k) row[k] = OBSU[k * RRS + tid];
+      row[col_logp] = logp;
+      row[col_val] = value;
+    }
+    __syncthreads();
 
-    // ---- environment step -------------------------------------------------------------------------------
+    // ---- environment step: NOBS = tanh([obs | u] . [A | B]^T + c) --------------------------------------------------
+    tile_layer<ACT_TANH>(OBSU, KU, esm, IP, ecv, NOBS, IP);
+    __syncthreads();
     float rew_env = 0.f;
-    for (int i = 0; i < Do; ++i) {
-      float pre = eC[i];
-      for (int j = 0; j < Do; ++j) pre = fmaf(eA[i * Do + j], s_obs[j], pre);
-      for (int a = 0; a < Da; ++a) pre = fmaf(eB[i * Da + a], s_u[a], pre);
-      const float v = tanhf(pre);
-      s_no[i] = v;
-      rew_env = fmaf(eW[i], v, rew_env);
-    }
+    for (int i = 0; i < Do; ++i) rew_env = fmaf(ewv[i], NOBS[i * RRS + tid], rew_env);
     if (!A.env.discrete) {
       float pen = 0.f;
-      for (int a = 0; a < Da; ++a) pen = fmaf(s_u[a], s_u[a], pen);
+      for (int a = 0; a < Da; ++a) {
+        const float uu = OBSU[(Do + a) * RRS + tid];
+        pen = fmaf(uu, uu, pen);
+      }
       rew_env -= 0.1f * pen;
     }
     done = ((t0 + t + 1) % H) == 0;
     const float donef = done ? 1.f : 0.f;
 
-    // ---- learned reward on (obs, clipped act, terminal-fixed next obs, done) ---------------------------
+    // ---- learned reward on (obs, clipped act, terminal-fixed next obs, done) ----------------------------------------
     float reward = rew_env;
     if (A.reward_mode != 0) {
-      float h1[HD], h2[HD];
-      float out = 0.f;
       for (int p = 0; p < L.npass; ++p) {
-        const PassDesc& P = L.pass[p];
-        const float* mean = (p == 2) ? mean2 : img[p] + MlpSm<HD>::mean_off(P.din);
-        const float* istd = (p == 2) ? istd2 : img[p] + MlpSm<HD>::istd_off(P.din);
-        for (int k = 0; k < P.din; ++k) {
-          const int r = L.stage_row[P.in_slot[k]];  // batch feature row -> source field
-          float v;
-          if (r < Do) v = s_obs[r];
-          else if (r < Do + Da) v = s_u[r - Do];
-          else if (r < 2 * Do + Da) v = s_no[r - Do - Da];
-          else v = donef;
-          s_xn[k] = (v - mean[k]) * istd[k];
+        const PassDesc& Pd = L.pass[p];
+        const float* img = smem + A.img_off + p * A.img_sz;
+        const int din = Pd.din;
+        const float* mean = img + TImg::mean(din, JP);
+        const float* istd = img + TImg::istd(din, JP);
+        for (int i = tid; i < din * (RR / 4); i += RR) {
+          const int k = i / (RR / 4), r4 = (i - k * (RR / 4)) * 4;
+          const int fr = L.stage_row[Pd.in_slot[k]];  // batch feature row -> source tile row
+          float4 x;
+          if (fr < Do + Da) x = ld4(OBSU + fr * RRS + r4);
+          else if (fr < 2 * Do + Da) x = ld4(NOBS + (fr - Do - Da) * RRS + r4);
+          else x = make_float4(donef, donef, donef, donef);
+          const float m = mean[k], is = istd[k];
+          st4(XN + k * RRS + r4, make_float4((x.x - m) * is, (x.y - m) * is, (x.z - m) * is, (x.w - m) * is));
         }
-        const float o = mlp_forward_row<HD, false>(img[p], P, s_xn, h1, h2);
-        out = fmaf(pass_coef(P.coef_kind, L.gamma, donef), o, out);
+        __syncthreads();
+        const float* HL = XN;
+        int hl = din;
+        if (Pd.n_hidden >= 1) {
+          tile_layer<ACT_RELU>(XN, din, img + TImg::w1t(din, JP), JP, img + TImg::b1(din, JP), H1, JP);
+          __syncthreads();
+          HL = H1;
+          hl = Pd.h1;
+        }
+        if (Pd.n_hidden >= 2) {
+          tile_layer<ACT_RELU>(H1, Pd.h1, img + TImg::w2t(din, JP), JP, img + TImg::b2(din, JP), H2, JP);
+          __syncthreads();
+          HL = H2;
+          hl = Pd.h2;
+        }
+        const float* wf = img + TImg::wf(din, JP);
+        float o0 = 0.f, o1 = 0.f;
+        int j = 0;
+        for (; j + 2 <= hl; j += 2) {
+          o0 = fmaf(wf[j], HL[j * RRS + tid], o0);
+          o1 = fmaf(wf[j + 1], HL[(j + 1) * RRS + tid], o1);
+        }
+        if (j < hl) o0 = fmaf(wf[j], HL[j * RRS + tid], o0);
+        const float o = img[TImg::bf(din, JP)] + (o0 + o1);
+        const float c = pass_coef(Pd.coef_kind, L.gamma, donef);
+        lg[tid] = (p == 0) ? c * o : fmaf(c, o, lg[tid]);
+        __syncthreads();
       }
-      reward = (A.reward_mode == 1) ? softplus_f(out) : out;
+      reward = (A.reward_mode == 1) ? softplus_f(lg[tid]) : lg[tid];
     }
-    row[col_rew] = reward;
+    if (live) row[col_rew] = reward;
 
-    // ---- time-limit bootstrap term gamma * V(terminal obs) (added after reward normalisation) ----------
+    // ---- time-limit bootstrap term gamma * V(terminal obs) (added after reward normalisation) -------------------
     float boot = 0.f;
-    if (done) {
-      for (int k = 0; k < Do; ++k) s_xn[k] = (s_no[k] - psm[S.mean + k]) * psm[S.istd + k];
-      boot = A.hp.gamma * value_of<HP>(psm, S, s_xn, Do);
-    }
-    aux[2 * E + e * T + t] = boot;
-    aux[2 * E + E * T + e * T + t] = rew_env;  // ground-truth env reward (BufferingWrapper records it)
-
-    // ---- flattened transition row (reference order) -> ring / flat_out -----------------------------------
-    const int64_t f = flat_index(e, t, E, T, t0, H);
-    float* dst0 = flat_out ? flat_out + f * tw : nullptr;
-    float* dst1 = nullptr;
-    if (ring && f >= skip) dst1 = ring + ((ring_idx0 + (f - skip)) % A.ring_capacity) * tw;
+    if (done) boot = A.hp.gamma * value_of_obs(NOBS);  // block-uniform branch (lock-step envs)
+    if (live) {
+      aux[2 * E + e * T + t] = boot;
+      aux[2 * E + E * T + e * T + t] = rew_env;  // ground-truth env reward (BufferingWrapper records it)
+      // ---- flattened transition row (reference order) -> ring / flat_out ---------------------------------------
+      const int64_t f = flat_index(e, t, E, T, t0, H);
+      float* dst0 = flat_out ? flat_out + f * tw : nullptr;
+      float* dst1 = nullptr;
+      if (ring && f >= skip) dst1 = ring + ((ring_idx0 + (f - skip)) % A.ring_capacity) * tw;
 #pragma unroll 1
-    for (int q = 0; q < 2; ++q) {
-      float* dst = q == 0 ? dst0 : dst1;
-      if (!dst) continue;
-      for (int k = 0; k < Do; ++k) dst[k] = s_obs[k];
-      for (int a = 0; a < Da; ++a) dst[Do + a] = s_u[a];
-      for (int k = 0; k < Do; ++k) dst[Do + Da + k] = s_no[k];
-      dst[2 * Do + Da] = donef;
+      for (int q = 0; q < 2; ++q) {
+        float* dst = q == 0 ? dst0 : dst1;
+        if (!dst) continue;
+        for (int k = 0; k < Do + Da; ++k) dst[k] = OBSU[k * RRS + tid];
+        for (int k = 0; k < Do; ++k) dst[Do + Da + k] = NOBS[k * RRS + tid];
+        dst[2 * Do + Da] = donef;
+      }
     }
-
-    // ---- advance: on done the next observation is the reset observation ------------------------------------
+    // ---- advance: on done the next observation is the reset observation ------------------------------------------
     if (done) {
       ++episode;
       for (int k = 0; k < Do; ++k)
-        s_obs[k] = 0.1f * philox_normal(A.env.seed, IMB_STREAM_ENV_RESET, egid, (uint32_t)episode, k);
+        OBSU[k * RRS + tid] = 0.1f * philox_normal(A.env.seed, IMB_STREAM_ENV_RESET, egid, (uint32_t)episode, k);
     } else {
-      for (int k = 0; k < Do; ++k) s_obs[k] = s_no[k];
+      for (int k = 0; k < Do; ++k) OBSU[k * RRS + tid] = NOBS[k * RRS + tid];
     }
+    __syncthreads();
   }
   // ---- tail: state back to HBM, V(last obs) for GAE ------------------------------------------------------
-  for (int k = 0; k < Do; ++k) env_obs[(int64_t)k * E + e] = s_obs[k];
-  for (int k = 0; k < Do; ++k) s_xn[k] = (s_obs[k] - psm[S.mean + k]) * psm[S.istd + k];
-  aux[e] = value_of<HP>(psm, S, s_xn, Do);
-  aux[E + e] = done ? 1.f : 0.f;
+  const float vlast = value_of_obs(OBSU);
+  if (live) {
+    for (int k = 0; k < Do; ++k) env_obs[(int64_t)k * E + e] = OBSU[k * RRS + tid];
+    aux[e] = vlast;
+    aux[E + e] = done ? 1.f : 0.f;
+  }
 }
 
 __global__ void k_rollout_advance(int64_t* state, int64_t n_envs, int64_t n_steps, int horizon, int64_t ring_cap) {
@@ -438,43 +491,57 @@ __global__ void k_env_reset(float* __restrict__ env_obs, int64_t E, int d_obs, u
 
 }  // namespace
 
-template <int HP, int HD>
-static int launch_rollout(const RolloutArgs& A, const DiscLaunch& L, const float* env_params, float* env_obs,
+static int launch_rollout(RolloutArgs A, const DiscLaunch& L, const float* env_params, float* env_obs,
                           const float* pol_params, const float* pol_norm, const float* disc_params, float* rollout,
                           float* ring, float* flat_out, float* aux, const float* noise, const int64_t* state,
                           cudaStream_t st) {
   auto al = [](int x) { return (x + 31) / 32 * 32; };
-  int o = 0;
-  int img1_off = 0;
-  if (A.reward_mode != 0) {
-    o += al(MlpSm<HD>::size(L.pass[0].din));
-    img1_off = o;
-    if (L.npass == 3) o += al(MlpSm<HD>::size(L.pass[1].din) + 2 * IMB_MAX_DIN);
-  }
   const int Do = A.env.d_obs, Da = A.env.d_act;
-  const int env_off = o;
-  o += al(Do * Do + Do * Da + 2 * Do);
-  const int pol_off = o;
-  o += al(PolSm<HP>(Do, Da).total);
-  int maxdin = Do;
-  if (A.reward_mode != 0)
-    for (int p = 0; p < L.npass; ++p) maxdin = L.pass[p].din > maxdin ? L.pass[p].din : maxdin;
-  const int scr_ld = (2 * Do + Da + maxdin) | 1;
-  const int scr_off = o;
-  o += al(RT * scr_ld);
+  A.HP = A.pol.hidden <= 32 ? 32 : 64;
+  A.IP = Do <= 32 ? 32 : 64;
+  A.KU = Do + Da;
+  int jp = 32, dmax = Do;
+  if (A.reward_mode != 0) {
+    for (int p = 0; p < L.npass; ++p) {
+      if (L.pass[p].n_hidden >= 1 && L.pass[p].h1 > jp) jp = 64;
+      if (L.pass[p].n_hidden >= 2 && L.pass[p].h2 > jp) jp = 64;
+      if (L.pass[p].din > dmax) dmax = L.pass[p].din;
+    }
+  }
+  A.JP = jp;
+  const int wmax = A.HP > A.JP ? A.HP : A.JP;
+  int o = 0;
+  A.pol_off = o;
+  o += al(PolImg(Do, Da, A.HP).total);
+  A.env_off = o;
+  o += al((A.KU + 2) * A.IP);
+  A.img_off = o;
+  A.img_sz = al(TImg::size(dmax, A.JP));
+  if (A.reward_mode != 0) o += L.npass * A.img_sz;
+  A.obsu_off = o;
+  o += al(A.KU * RRS);
+  A.xn_off = o;
+  o += al(dmax * RRS);
+  A.h1_off = o;
+  o += al(wmax * RRS);
+  A.h2_off = o;
+  o += al(wmax * RRS);
+  A.nobs_off = o;
+  o += al(A.IP * RRS);
+  A.vec_off = o;
+  o += al(RR);
+  A.total = o;
   const size_t bytes = (size_t)o * 4;
   IMB_REQUIRE(bytes <= IMB_SMEM_MAX, "rollout kernel needs %zu B of shared memory", bytes);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(k_rollout<HP, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, IMB_SMEM_MAX);
+  static size_t attr_bytes = 0;
+  if (bytes > attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_bytes = bytes;
   }
-  const int blocks = (int)((A.E + RT - 1) / RT);
-  k_rollout<HP, HD><<<blocks, RT, bytes, st>>>(A, L, env_params, env_obs, pol_params, pol_norm, disc_params, rollout,
-                                               ring, flat_out, aux, noise, state, img1_off, env_off, pol_off, scr_off,
-                                               scr_ld);
+  const int blocks = (int)((A.E + RR - 1) / RR);
+  k_rollout<<<blocks, RR, bytes, st>>>(A, L, env_params, env_obs, pol_params, pol_norm, disc_params, rollout, ring,
+                                       flat_out, aux, noise, state);
   IMB_CHECK_LAUNCH("k_rollout");
   return 0;
 }
-

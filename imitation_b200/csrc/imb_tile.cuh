@@ -12,6 +12,7 @@
 // one LDS.128 phase never collide.
 #pragma once
 #include "imb_common.cuh"
+#include "imb_mlp.cuh"
 
 namespace {
 
@@ -114,5 +115,59 @@ __device__ __forceinline__ void wgrad_acc(float (&acc)[4][8], float (&bacc)[4], 
     }
   }
 }
+
+// Shared-memory image of one MLP, hidden widths padded to JP (32 or 64), everything zero padded:
+//   W1t[din][JP] b1[JP] W2t[JP][JP] W2[JP][JP] b2[JP] wf[64] bf,pad[4] mean[64] istd[64]
+struct TImg {
+  __host__ __device__ static int w1t(int, int) { return 0; }
+  __host__ __device__ static int b1(int din, int JP) { return din * JP; }
+  __host__ __device__ static int w2t(int din, int JP) { return din * JP + JP; }
+  __host__ __device__ static int w2(int din, int JP) { return din * JP + JP + JP * JP; }
+  __host__ __device__ static int b2(int din, int JP) { return din * JP + JP + 2 * JP * JP; }
+  __host__ __device__ static int wf(int din, int JP) { return din * JP + 2 * JP + 2 * JP * JP; }
+  __host__ __device__ static int bf(int din, int JP) { return wf(din, JP) + 64; }
+  __host__ __device__ static int mean(int din, int JP) { return bf(din, JP) + 4; }
+  __host__ __device__ static int istd(int din, int JP) { return mean(din, JP) + 64; }
+  __host__ __device__ static int size(int din, int JP) { return istd(din, JP) + 64; }
+};
+
+__device__ void load_timg(float* sm, const PassDesc& p, int JP, const float* __restrict__ params,
+                          const float* __restrict__ norm, float eps) {
+  const int din = p.din, tid = threadIdx.x, nt = blockDim.x;
+  const float* q = params + p.param_off;
+  for (int i = tid; i < TImg::mean(din, JP); i += nt) sm[i] = 0.f;
+  __syncthreads();
+  int off = 0, hl = din;
+  if (p.n_hidden >= 1) {
+    for (int i = tid; i < p.h1 * din; i += nt) {
+      const int j = i / din, k = i - j * din;
+      sm[TImg::w1t(din, JP) + k * JP + j] = q[off + i];
+    }
+    off += p.h1 * din;
+    for (int i = tid; i < p.h1; i += nt) sm[TImg::b1(din, JP) + i] = q[off + i];
+    off += p.h1;
+    hl = p.h1;
+  }
+  if (p.n_hidden >= 2) {
+    for (int i = tid; i < p.h2 * p.h1; i += nt) {
+      const int j = i / p.h1, ii = i - j * p.h1;
+      const float v = q[off + i];
+      sm[TImg::w2(din, JP) + j * JP + ii] = v;
+      sm[TImg::w2t(din, JP) + ii * JP + j] = v;
+    }
+    off += p.h2 * p.h1;
+    for (int i = tid; i < p.h2; i += nt) sm[TImg::b2(din, JP) + i] = q[off + i];
+    off += p.h2;
+    hl = p.h2;
+  }
+  for (int i = tid; i < hl; i += nt) sm[TImg::wf(din, JP) + i] = q[off + i];
+  off += hl;
+  if (tid == 0) sm[TImg::bf(din, JP)] = q[off];
+  for (int i = tid; i < din; i += nt) {
+    sm[TImg::mean(din, JP) + i] = norm ? norm[i] : 0.f;
+    sm[TImg::istd(din, JP) + i] = norm ? 1.0f / sqrtf(norm[din + i] + eps) : 1.f;
+  }
+}
+
 
 }  // namespace

@@ -14,14 +14,22 @@ import torch as th
 from torch import nn
 
 
+def _set_mode(m: nn.Module, mode: bool) -> None:
+    # nn.Module.train() goes through Module.__setattr__ (Parameter/Module isinstance checks, ~40 us per
+    # submodule); `training` is a plain instance attribute, so write it directly -- this runs around
+    # every discriminator update (common.py:441-443 of the reference).
+    for sub in m.modules():
+        sub.__dict__["training"] = mode
+
+
 @contextlib.contextmanager
 def training_mode(m: nn.Module, mode: bool = False):
     old = m.training
-    m.train(mode)
+    _set_mode(m, mode)
     try:
         yield m
     finally:
-        m.train(old)
+        _set_mode(m, old)
 
 
 training = functools.partial(training_mode, mode=True)
