@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rounds", type=int, default=12, help="rounds of the CPU baseline sample (rank 0, N=1)")
+    ap.add_argument("--host-threads", type=int, default=0, help="torch intra-op threads for host-side ops (0: default)")
     ap.add_argument("--profile-host", action="store_true", help="cProfile the e2e loop (host overhead hunt)")
     args = ap.parse_args()
     cfg = CFG
@@ -253,6 +254,8 @@ def main():
     # ------------------------------------------------------------------------------ our arm
     import torch.distributed as dist
 
+    if args.host_threads > 0:
+        th.set_num_threads(args.host_threads)  # torch CPU ops on the host side of the loop are all tiny
     th.cuda.set_device(local)
     device = th.device("cuda", local)
     if world > 1:
@@ -362,16 +365,38 @@ def main():
     if world > 1:
         dist.barrier()
     if args.profile_host and rank == 0:
-        import cProfile
-        import pstats
+        # wall-clock breakdown of the e2e loop (cProfile's per-call overhead distorts this loop badly)
+        acc = {}
 
-        pr = cProfile.Profile()
-        pr.enable()
+        def wrap(obj, name, label=None):
+            fn = getattr(obj, name)
+            lab = label or name
+
+            def w(*a, **k):
+                t0 = time.perf_counter()
+                try:
+                    return fn(*a, **k)
+                finally:
+                    acc[lab] = acc.get(lab, 0.0) + time.perf_counter() - t0
+            setattr(obj, name, w)
+            return fn
+
+        saved = [(o, n, wrap(o, n)) for o, n in ((tr, "train_gen"), (tr, "_stage_host"), (tr, "train_disc_async"),
+                                                  (tr, "train_disc"), (tr.gen_algo, "collect_rollouts"),
+                                                  (tr.gen_algo, "train"), (tr.gen_algo, "_iteration"),
+                                                  (tr.logger, "dump"), (th.Tensor, "cpu"), (th.Tensor, "copy_"),
+                                                  (th.Tensor, "to"), (tr, "_check_samples"))]
+        t0 = time.perf_counter()
         for _ in range(10):
             round_e2e()
+        t1 = time.perf_counter()
         th.cuda.synchronize()
-        pr.disable()
-        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(35)
+        t2 = time.perf_counter()
+        for o, n, fn in saved:
+            setattr(o, n, fn)
+        sys.stderr.write(f"e2e 10 rounds: {(t1 - t0) * 100:.3f} ms/round host, +{(t2 - t1) * 1e3:.3f} ms final sync\n")
+        for k, v in sorted(acc.items(), key=lambda kv: -kv[1]):
+            sys.stderr.write(f"  {k:<20s} {v * 100:.3f} ms/round\n")
     ms_e = cuda_time_ms(lambda: [round_e2e() for _ in range(Ke)])
     if world > 1:
         t = th.tensor([ms_e], device=device)

@@ -7,7 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libimb.so")
+VARIANT = os.environ.get("IMB_VARIANT", "")  # e.g. "_timing" with IMB_EXTRA_NVCC_FLAGS=-DIMB_PPO_TIMING
+LIB = os.path.join(HERE, "libimb" + VARIANT + ".so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -33,18 +34,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
-    os.makedirs(os.path.join(HERE, "_obj"), exist_ok=True)
+    os.makedirs(os.path.join(HERE, "_obj" + VARIANT), exist_ok=True)
     procs = []
     hdr_t = max(os.path.getmtime(p) for p in glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(ROOT, "include", "imb.h")])
     for src in sources():
-        obj = os.path.join(HERE, "_obj", os.path.basename(src) + ".o")
+        obj = os.path.join(HERE, "_obj" + VARIANT, os.path.basename(src) + ".o")
         objs.append(obj)
         if (not force and not verbose and os.path.exists(obj)
                 and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t)):
             continue  # object is up to date
         cmd = [nvcc, "-c", src, "-o", obj, "-I", os.path.join(ROOT, "include"), "-I", CSRC,
                "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-DIMB_BUILDING"]
+               "-Xcompiler", "-fPIC", "-DIMB_BUILDING"] + os.environ.get("IMB_EXTRA_NVCC_FLAGS", "").split()
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -10,7 +10,7 @@ from typing import Optional
 import torch as th
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libimb.so")
+LIB_PATH = os.path.join(_HERE, "libimb" + os.environ.get("IMB_VARIANT", "") + ".so")  # IMB_VARIANT: profiling builds
 
 IMB_TILE_ROWS = 128
 IMB_MAX_HIDDEN = 64

@@ -152,6 +152,25 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
   x ^= x >> 16;
   return x;
 }
+// 4-byte asynchronous global -> shared copy (LDGSTS); completion via cp_async_wait_all + __syncthreads
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// tanh with ~1e-7 absolute error in a dozen instructions (tanhf's accurate path costs ~5x more and sits on
+// the critical path of every layer of the latency-bound PPO step): odd polynomial below 0.1, else
+// 1 - 2 / (exp(2x) + 1) with the hardware exponential; saturates correctly for large |x|.
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float x2 = x * x;
+  const float poly = x * fmaf(x2, fmaf(x2, 0.13333333f, -0.33333334f), 1.0f);
+  const float t = __expf(2.0f * x);
+  const float big = 1.0f - __fdividef(2.0f, t + 1.0f);
+  return fabsf(x) < 0.1f ? poly : big;
+}
+
 // Feistel permutation of [0,n) with cycle walking (twin of philox.feistel_perm()).
 struct FeistelKey {
   uint32_t k[4];

@@ -16,13 +16,31 @@
 #include "imb_common.cuh"
 #include "imb_tile.cuh"
 
+#ifdef IMB_PPO_TIMING
+// phase timing for profiles/: CTA 0 / thread 0 accumulates clock64() deltas per phase of the optimiser step
+__device__ long long g_ppo_clk[24];
+#define PPO_TICK(i)                                  \
+  do {                                               \
+    if (tid == 0) {                                  \
+      const long long now_ = clock64();              \
+      clk_acc[i] += now_ - clk_last;                 \
+      clk_last = now_;                               \
+    }                                                \
+  } while (0)
+#else
+#define PPO_TICK(i) do {} while (0)
+#endif
+#ifndef PPO_TANH
+#define PPO_TANH(x) tanh_fast(x)
+#endif
+
 namespace {
 
 constexpr int PT = 256;   // threads per CTA: 0..127 = policy tower, 128..255 = value tower
-constexpr int CL = 8;     // CTAs per cluster: each owns RL rows of every minibatch and 1/CL of the parameters
+constexpr int CL = 8;     // CTAs per cluster: each owns RL rows of every minibatch and 1/CL of the gradient reduction
 constexpr int RL = 8;     // minibatch rows per CTA  (CL * RL = 64 >= SB3 batch_size)
 constexpr int PR = CL * RL;
-constexpr int PRS = PR + TILE_PAD;
+constexpr int PRS = PR + 8;  // row stride of the full-minibatch tiles (8-bank stagger: the 4 stat groups of a warp never collide)
 
 struct PpoArgs {
   imb_policy_desc pol;
@@ -30,8 +48,55 @@ struct PpoArgs {
   int64_t n_rows;
   int rw;
   uint64_t seed;
-  int HP, KP, S;  // tower width / obs width padded to 32; parameters per slice (multiple of 4)
+  int HP, KP, S;  // tower width / obs width padded to 32; padded-layout parameters per slice (multiple of 4)
 };
+
+// Padded parameter layout used inside the kernel ("P-layout"): W1 rows have stride ldo = d_obs|1 and W2 rows
+// stride ldh = hidden|1 (odd), so that BOTH access patterns of the step -- lane = output unit (forward,
+// weight gradients) and lane = input unit (backward) -- are shared-memory bank-conflict free straight from the
+// parameter vector; no transposed working copies have to be rebuilt after every optimiser step.  The pad
+// elements have zero value and zero gradient for ever (Adam leaves them at 0).
+struct PLay {
+  int w1[2], b1[2], w2[2], b2[2], wa, ba, wv, bv, ls, ldo, ldh, total;
+};
+__host__ __device__ inline PLay make_play(const imb_policy_desc& pd) {
+  PLay L;
+  const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden;
+  L.ldo = Do | 1;
+  L.ldh = h | 1;
+  int o = 0;
+  for (int t = 0; t < 2; ++t) {
+    L.w1[t] = o; o += h * L.ldo;
+    L.b1[t] = o; o += h;
+    L.w2[t] = o; o += h * L.ldh;
+    L.b2[t] = o; o += h;
+  }
+  L.wa = o; o += Da * h;
+  L.ba = o; o += Da;
+  L.wv = o; o += h;
+  L.bv = o; o += 1;
+  L.ls = o; o += pd.discrete ? 0 : Da;
+  L.total = o;
+  return L;
+}
+// torch-flat parameter index -> P-layout index
+__device__ inline int flat_to_play(const imb_policy_desc& pd, const PLay& L, int p) {
+  const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden;
+  auto in = [&](int off, int len) { return p >= off && p < off + len; };
+  if (in(pd.off_pi_w1, h * Do)) { const int i = p - pd.off_pi_w1; return L.w1[0] + (i / Do) * L.ldo + i % Do; }
+  if (in(pd.off_vf_w1, h * Do)) { const int i = p - pd.off_vf_w1; return L.w1[1] + (i / Do) * L.ldo + i % Do; }
+  if (in(pd.off_pi_w2, h * h)) { const int i = p - pd.off_pi_w2; return L.w2[0] + (i / h) * L.ldh + i % h; }
+  if (in(pd.off_vf_w2, h * h)) { const int i = p - pd.off_vf_w2; return L.w2[1] + (i / h) * L.ldh + i % h; }
+  if (in(pd.off_pi_b1, h)) return L.b1[0] + p - pd.off_pi_b1;
+  if (in(pd.off_vf_b1, h)) return L.b1[1] + p - pd.off_vf_b1;
+  if (in(pd.off_pi_b2, h)) return L.b2[0] + p - pd.off_pi_b2;
+  if (in(pd.off_vf_b2, h)) return L.b2[1] + p - pd.off_vf_b2;
+  if (in(pd.off_act_w, Da * h)) return L.wa + p - pd.off_act_w;
+  if (in(pd.off_act_b, Da)) return L.ba + p - pd.off_act_b;
+  if (in(pd.off_val_w, h)) return L.wv + p - pd.off_val_w;
+  if (p == pd.off_val_b) return L.bv;
+  return L.ls + p - pd.off_log_std;
+}
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
   // red: >= 16 floats of shared memory; all PT threads must call
@@ -46,45 +111,49 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
-// working images rebuilt from the parameters after every optimiser step; per tower:
-//   W1t[KP][HP] (k-major for layer 1), W2t[HP][HP] (k = input unit); the backward pass reads W2 in its
-//   torch layout straight from the parameter vector (row stride h, consecutive lanes = consecutive floats)
-__device__ void build_images(const imb_policy_desc& pd, const float* __restrict__ Pm, float* __restrict__ img,
-                             int HP, int KP) {
-  const int Do = pd.d_obs, h = pd.hidden;
-  const int tsz = KP * HP + HP * HP;
-  for (int i = threadIdx.x; i < h * Do; i += PT) {
-    const int j = i / Do, k = i - j * Do;
-    img[k * HP + j] = Pm[pd.off_pi_w1 + i];
-    img[tsz + k * HP + j] = Pm[pd.off_vf_w1 + i];
-  }
-  for (int i = threadIdx.x; i < h * h; i += PT) {
-    const int j = i / h, ii = i - j * h;
-    img[KP * HP + ii * HP + j] = Pm[pd.off_pi_w2 + i];
-    img[tsz + KP * HP + ii * HP + j] = Pm[pd.off_vf_w2 + i];
-  }
+// sum over the 8 lanes of an aligned lane group; ALL 32 lanes must call it convergently (a per-group member
+// mask makes the compiler serialise the groups through MATCH.ANY: 40x more instructions, measured)
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ float rcp_fast(float x) { return __fdividef(1.0f, x); }
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
-__device__ __forceinline__ float dot8(const float* __restrict__ a, const float* __restrict__ b) {
-  const float4 a0 = ld4(a), a1 = ld4(a + 4), b0 = ld4(b), b1 = ld4(b + 4);
-  float s0 = a0.x * b0.x, s1 = a0.y * b0.y;
-  s0 = fmaf(a0.z, b0.z, s0);
-  s1 = fmaf(a0.w, b0.w, s1);
-  s0 = fmaf(a1.x, b1.x, s0);
-  s1 = fmaf(a1.y, b1.y, s1);
-  s0 = fmaf(a1.z, b1.z, s0);
-  s1 = fmaf(a1.w, b1.w, s1);
+__device__ __forceinline__ float dot8r(const float (&d)[8], const float* __restrict__ b) {
+  const float4 b0 = ld4(b), b1 = ld4(b + 4);
+  float s0 = d[0] * b0.x, s1 = d[1] * b0.y;
+  s0 = fmaf(d[2], b0.z, s0);
+  s1 = fmaf(d[3], b0.w, s1);
+  s0 = fmaf(d[4], b1.x, s0);
+  s1 = fmaf(d[5], b1.y, s1);
+  s0 = fmaf(d[6], b1.z, s0);
+  s1 = fmaf(d[7], b1.w, s1);
   return s0 + s1;
+}
+__device__ __forceinline__ void load8(float (&d)[8], const float* __restrict__ p) {
+  const float4 a = ld4(p), b = ld4(p + 4);
+  d[0] = a.x, d[1] = a.y, d[2] = a.z, d[3] = a.w, d[4] = b.x, d[5] = b.y, d[6] = b.z, d[7] = b.w;
+}
+__device__ __forceinline__ float sum8(const float (&d)[8]) {
+  return ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
 }
 
 // PPO.train for one rollout: n_epochs x ceil(N / batch) optimiser steps, ONE cluster of CL CTAs.
-// Every CTA gathers the whole minibatch (64 x ~26 floats) so that the feature RunningNorm and the
-// advantage normalisation are computed redundantly and identically everywhere; forward/backward
-// run on the CTA's own RL rows; the per-CTA partial gradients are exchanged through distributed
-// shared memory: slice owners sum the CL partials in fixed order, the squared norms of the slices
-// are exchanged for clip_grad_norm_, owners run Adam on their slice and push the new parameters to
-// all CTAs.  Three cluster barriers per optimiser step, no global-memory traffic inside a step
-// except the minibatch gather.
+// Every CTA receives the whole minibatch (64 x ~26 floats, prefetched one step ahead with cp.async) so that
+// the feature RunningNorm and the advantage normalisation are computed redundantly and identically
+// everywhere; forward/backward run on the CTA's own RL rows; the per-CTA partial gradients are staged in
+// local shared memory and exchanged through distributed shared memory with 16-byte stores: slice owners
+// sum the CL partials in fixed order and all-gather the summed slices; every CTA then runs
+// clip_grad_norm_ + Adam on the FULL vector (identical arithmetic everywhere, so the replicas never
+// diverge).  Two cluster barriers per optimiser step; the only global-memory traffic inside a step is the
+// asynchronous minibatch prefetch.
 __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __restrict__ g_params,
                                                       float* __restrict__ g_norm, int32_t* __restrict__ g_norm_count,
                                                       float* __restrict__ g_m, float* __restrict__ g_v,
@@ -99,6 +168,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   __shared__ float bc[8];
   const imb_policy_desc& pd = A.pol;
   const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params, HP = A.HP, KP = A.KP, S = A.S;
+  const PLay PL = make_play(pd);
+  const int ldo = PL.ldo, ldh = PL.ldh;
   const int da_store = pd.discrete ? 1 : Da;
   const int col_logp = Do + da_store, col_adv = col_logp + 3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,18 +178,16 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
 
   // ---- shared-memory carve-up (identical in every CTA: DSMEM addresses are rank + offset) ---------------
   int o = 0;
-  float* Pm = smem + o; o += al(CL * S);        // full parameter vector (padded to CL slices)
-  float* Ms = smem + o; o += al(S);             // Adam moments of the owned slice
-  float* Vs = smem + o; o += al(S);
-  float* GSL = smem + o; o += al(S);            // summed gradient of the owned slice
-  float* RECV = smem + o; o += al(CL * S);      // [source CTA][S]: partial gradients pushed by every CTA
-  float* SSQ = smem + o; o += 32;               // [CL] squared gradient norms of the slices
+  float* Pm = smem + o; o += al(CL * S);        // parameters, P-layout, padded to CL slices
+  float* Ms = smem + o; o += al(CL * S);        // Adam moments (every CTA keeps the full vectors)
+  float* Vs = smem + o; o += al(CL * S);
+  float* GP = smem + o; o += al(CL * S);        // own partial gradient; after barrier (a): the all-gathered sum
+  float* RECV = smem + o; o += al(CL * S);      // [source CTA][S]: partial gradients of the owned slice
   float* LOSS = smem + o; o += 32;              // [CL][3] partial loss sums (read by CTA 0)
-  const int tsz = KP * HP + HP * HP;
-  float* img = smem + o; o += al(2 * tsz);
-  float* XNf = smem + o; o += al(KP * PRS);     // full minibatch, feature-major
   const int DAP = (Da + 3) / 4 * 4;
-  float* MBf = smem + o; o += al((DAP + 3) * PRS);  // act[DAP] | logp_old | adv | ret, full minibatch
+  const int xsz = al(KP * PRS), msz = al((DAP + 3) * PRS);
+  float* XB = smem + o; o += 2 * xsz;           // double-buffered full minibatch, feature-major [k][PRS]
+  float* MB = smem + o; o += 2 * msz;           // act[DAP] | logp_old | adv | ret, [c][PRS]
   // own-row tiles, feature-major [feature][RL]
   float* XNo = smem + o; o += al(KP * RL);
   float* TH1 = smem + o; o += 2 * HP * RL;
@@ -128,456 +197,503 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   float* DM = smem + o; o += DAP * RL;          // dL/d(mean|logits) [a][RL]
   float* DLS = smem + o; o += DAP * RL;         // dL/d(log_std) per row [a][RL]
   float* MEAN = smem + o; o += DAP * RL;        // action means / logits [a][RL]
-  float* DVAL = smem + o; o += 32;              // [RL] dL/dvalue ; VALS at +8 ; ONES at +16
+  float* DVAL = smem + o; o += 32;              // [RL] dL/dvalue ; VALS at +8
   float* VALS = DVAL + 8;
-  float* ONES = DVAL + 16;
-  float* rstat = smem + o; o += al(2 * 64 + 4);
+  float* rstat = smem + o; o += al(3 * 64 + 4);   // mean | var | 1/sqrt(var + eps)
   int* s_idx = reinterpret_cast<int*>(smem + o); o += al(PR);
-  unsigned short* offA = reinterpret_cast<unsigned short*>(smem + o); o += al((CL * S + 1) / 2);
-  unsigned short* offB = reinterpret_cast<unsigned short*>(smem + o); o += al((CL * S + 1) / 2);
-  unsigned short* imgpos = reinterpret_cast<unsigned short*>(smem + o); o += al((CL * S + 1) / 2);  // image slot of p
   unsigned int* glut = reinterpret_cast<unsigned int*>(smem + o); o += al(PR * (Do + da_store + 3));  // gather LUT
   float* H1 = TH1 + net * HP * RL;
   float* LAT = TLAT + net * HP * RL;
   float* DZ2 = TDZ2 + net * HP * RL;
   float* DZ1 = TDZ1 + net * HP * RL;
-  const float* W1t = img + net * tsz;
-  const float* W2t = W1t + KP * HP;
+  const float* W1 = Pm + PL.w1[net];
+  const float* W2 = Pm + PL.w2[net];
 
-  for (int i = tid; i < CL * S; i += PT) {
-    Pm[i] = i < NP ? g_params[i] : 0.f;
-    RECV[i] = 0.f;
-  }
-  for (int i = tid; i < S; i += PT) {
-    const int p = crank * S + i;
-    Ms[i] = p < NP ? g_m[p] : 0.f;
-    Vs[i] = p < NP ? g_v[p] : 0.f;
-  }
-  for (int i = tid; i < al(2 * tsz); i += PT) img[i] = 0.f;
-  for (int i = tid; i < KP * PRS; i += PT) XNf[i] = 0.f;
-  for (int i = tid; i < (DAP + 3) * PRS; i += PT) MBf[i] = 0.f;
-  for (int i = tid; i < KP * RL; i += PT) XNo[i] = 0.f;
-  for (int i = tid; i < 8 * HP * RL; i += PT) TH1[i] = 0.f;   // TH1..TDZ1 contiguous
-  for (int i = tid; i < 3 * DAP * RL + 32; i += PT) DM[i] = 0.f;  // DM, DLS, MEAN, DVAL.. contiguous
+  for (int i = tid; i < CL * S; i += PT) Pm[i] = Ms[i] = Vs[i] = GP[i] = RECV[i] = 0.f;
+  for (int i = tid; i < 2 * xsz; i += PT) XB[i] = 0.f;
+  for (int i = tid; i < 2 * msz; i += PT) MB[i] = 0.f;
+  for (int i = tid; i < al(KP * RL) + 8 * HP * RL + 3 * DAP * RL + 32; i += PT) XNo[i] = 0.f;  // XNo .. DVAL contiguous
   if (tid < 64) {
     rstat[tid] = (pd.has_norm && tid < Do) ? g_norm[tid] : 0.f;
     rstat[64 + tid] = (pd.has_norm && tid < Do) ? g_norm[Do + tid] : 1.f;
-    SSQ[tid & 31] = 0.f;
+    rstat[128 + tid] = 1.f;
     LOSS[tid & 31] = 0.f;
   }
   __syncthreads();
-  if (tid < RL) ONES[tid] = 1.f;
-  // gradient of parameter p = dot over the CTA's RL rows of two feature rows: offA[p], offB[p]
-  // (float offsets into this CTA's shared memory); biases / log_std pair with ONES.
-  for (int p = tid; p < CL * S; p += PT) {
-    int a = (int)(ONES - smem), b2 = a;  // default: harmless
-    if (p < NP) {
-      auto tower = [&](int q, int tw) -> bool {  // q relative to the tower's first parameter
-        const int w1 = h * Do, b1 = w1 + h, w2 = b1 + h * h, bb2 = w2 + h;
-        const float* tDZ1 = TDZ1 + tw * HP * RL, *tDZ2 = TDZ2 + tw * HP * RL, *tH1 = TH1 + tw * HP * RL;
-        if (q < w1) { a = (int)(tDZ1 - smem) + (q / Do) * RL; b2 = (int)(XNo - smem) + (q % Do) * RL; return true; }
-        if (q < b1) { a = (int)(tDZ1 - smem) + (q - w1) * RL; b2 = (int)(ONES - smem); return true; }
-        if (q < w2) { const int r = q - b1; a = (int)(tDZ2 - smem) + (r / h) * RL; b2 = (int)(tH1 - smem) + (r % h) * RL; return true; }
-        if (q < bb2) { a = (int)(tDZ2 - smem) + (q - w2) * RL; b2 = (int)(ONES - smem); return true; }
-        return false;
-      };
-      const int tp = h * Do + h + h * h + h;
-      if (p < tp) tower(p, 0);
-      else if (p < 2 * tp) tower(p - tp, 1);
-      else if (p < pd.off_act_b) { const int r = p - pd.off_act_w; a = (int)(DM - smem) + (r / h) * RL; b2 = (int)(TLAT - smem) + (r % h) * RL; }
-      else if (p < pd.off_val_w) { a = (int)(DM - smem) + (p - pd.off_act_b) * RL; b2 = (int)(ONES - smem); }
-      else if (p < pd.off_val_b) { a = (int)(DVAL - smem); b2 = (int)(TLAT + HP * RL - smem) + (p - pd.off_val_w) * RL; }
-      else if (p == pd.off_val_b) { a = (int)(DVAL - smem); b2 = (int)(ONES - smem); }
-      else { a = (int)(DLS - smem) + (p - pd.off_log_std) * RL; b2 = (int)(ONES - smem); }
-    }
-    offA[p] = (unsigned short)(a / 4);   // all rows are 16-byte aligned: store offset / 4
-    offB[p] = (unsigned short)(b2 / 4);
+  for (int p = tid; p < NP; p += PT) {
+    const int q = flat_to_play(pd, PL, p);
+    Pm[q] = g_params[p];
+    Ms[q] = g_m[p];
+    Vs[q] = g_v[p];
   }
-  // image slot (float offset into img, 0xFFFF = none) of every parameter: W1 -> W1t[k][j], W2 -> W2t[i][j]
-  for (int p = tid; p < CL * S; p += PT) {
-    int pos = 0xFFFF;
-    const int tp = h * Do + h + h * h + h;
-    if (p < 2 * tp) {
-      const int tw = p / tp, q = p - tw * tp, w1 = h * Do, b1 = w1 + h, w2 = b1 + h * h;
-      if (q < w1) pos = tw * tsz + (q % Do) * HP + q / Do;
-      else if (q >= b1 && q < w2) { const int r = q - b1; pos = tw * tsz + KP * HP + (r % h) * HP + r / h; }
-    }
-    imgpos[p] = (unsigned short)pos;
-  }
-  // gather LUT: element e of the minibatch tile -> (row r | source column sc << 8 | dst float offset << 16)
-  const int rwg0 = Do + da_store + 3;
-  for (int e = tid; e < PR * rwg0; e += PT) {
-    const int r = e / rwg0, c = e - r * rwg0;
+  // gather LUT: element e of the minibatch tile -> (row r | source column sc << 8 | dst float offset << 16);
+  // dst is relative to the CTA's shared memory for buffer 0 (buffer 1: + xsz for obs columns, + msz otherwise)
+  const int rwg = Do + da_store + 3;  // gathered columns per row: obs | act | logp_old | adv | ret
+  for (int e = tid; e < PR * rwg; e += PT) {
+    const int r = e / rwg, c = e - r * rwg;
     const int sc = c < col_logp ? c : (c == col_logp ? col_logp : col_adv + (c - col_logp - 1));
-    const int dst = c < Do ? (int)(XNf - smem) + c * PRS + r
-                           : (int)(MBf - smem) + (c - Do + (c >= col_logp ? DAP - da_store : 0)) * PRS + r;
+    const int dst = c < Do ? (int)(XB - smem) + c * PRS + r
+                           : (int)(MB - smem) + (c - Do + (c >= col_logp ? DAP - da_store : 0)) * PRS + r;
     glut[e] = (unsigned)r | ((unsigned)sc << 8) | ((unsigned)dst << 16);
   }
   int32_t run_count = pd.has_norm ? *g_norm_count : 0;
-  __syncthreads();
-  build_images(pd, Pm, img, HP, KP);
-  cluster.sync();
 
   const int64_t N = A.n_rows;
   const int mb = A.hp.batch_size;
   const int64_t steps_per_epoch = (N + mb - 1) / mb;
+  const int64_t n_steps = steps_per_epoch * A.hp.n_epochs;
   int64_t adam_step = state[IMB_ST_PPO_STEP];
   const int64_t perm_draw0 = state[IMB_ST_PPO_EPOCH];
   double b1pow = pow(0.9, (double)adam_step), b2pow = pow(0.999, (double)adam_step);  // beta^t, kept incrementally
-  int64_t log_i = 0;
-  const int rwg = Do + da_store + 3;  // gathered columns per row: obs | act | logp_old | adv | ret
   const int row0 = crank * RL;        // first minibatch row owned by this CTA
-  // own-row GEMM mapping: thread -> column j = tt % HP and RPT = HP / 16 consecutive rows
+  // own-row GEMM mapping: thread -> column gj = tt % HP and RPT = HP / 16 consecutive rows
   const int gj = tt % HP, RPT = HP / 16, gr0 = (tt / HP) * RPT;
+  const bool jlive = gj < h;
+  const int wq = tt / HP, NWQ = 128 / HP;  // weight-gradient mapping: unit gj, every NWQ-th input
+  const int g8 = tid >> 3, gl = tid & 7;   // 8-lane statistic groups
 
-  for (int ep = 0; ep < A.hp.n_epochs; ++ep) {
-    const FeistelKey fk = feistel_key(A.seed, IMB_STREAM_PPO_PERM, (uint64_t)(perm_draw0 + ep), (uint64_t)N);
-    for (int64_t sidx = 0; sidx < steps_per_epoch; ++sidx) {
-      const int64_t start = sidx * mb;
-      const int nb = (int)min((int64_t)mb, N - start);
-      const float inv_nb = 1.0f / (float)nb;
-      // ---- 1. gather the whole minibatch (independent loads, 4 in flight per thread) ------------------------
-      if (tid < PR)
-        s_idx[tid] = tid < nb ? (perm_in ? (int)perm_in[(int64_t)ep * N + start + tid]
-                                         : (int)feistel_perm(fk, (uint64_t)(start + tid), (uint64_t)N))
-                              : 0;
-      __syncthreads();
-      for (int e0 = tid; e0 < PR * rwg; e0 += 8 * PT) {  // up to 8 independent loads in flight per thread
-        float v[8];
-        unsigned lut[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * PT;
-          lut[u] = e < PR * rwg ? glut[e] : 0xFFFFFFFFu;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          v[u] = 0.f;
-          if (lut[u] != 0xFFFFFFFFu) {
-            const int r = lut[u] & 0xFF;
-            if (r < nb) v[u] = rollout[(int64_t)s_idx[r] * A.rw + ((lut[u] >> 8) & 0xFF)];
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (lut[u] != 0xFFFFFFFFu) smem[lut[u] >> 16] = v[u];
-      }
-      __syncthreads();
-      // ---- 2. feature RunningNorm over the whole minibatch (identical in every CTA) -----------------------------
-      if (pd.has_norm) {
-        for (int k = warp; k < Do; k += PT / 32) {
-          const float x0 = lane < nb ? XNf[k * PRS + lane] : 0.f, x1 = lane + 32 < nb ? XNf[k * PRS + lane + 32] : 0.f;
-          const float bmean = warp_sum(x0 + x1) * inv_nb;
-          const float d0 = lane < nb ? x0 - bmean : 0.f, d1 = lane + 32 < nb ? x1 - bmean : 0.f;
-          const float bvar = warp_sum(d0 * d0 + d1 * d1) * inv_nb;
-          if (lane == 0) {
-            float mean = rstat[k], var = rstat[64 + k];
-            const float bn = (float)nb, c = (float)run_count, tot = c + bn, delta = bmean - mean;
-            mean += delta * bn / tot;
-            var *= c;
-            var += bvar * bn;
-            var += delta * delta * c * bn / tot;
-            var /= tot;
-            rstat[k] = mean;
-            rstat[64 + k] = var;
-          }
-        }
-        run_count += nb;
-        __syncthreads();
-      }
-      // own rows, normalised, feature-major [k][RL]
-      for (int e = tid; e < Do * RL; e += PT) {
-        const int k = e / RL, r = e - k * RL;
-        const float x = XNf[k * PRS + row0 + r];
-        XNo[e] = (row0 + r < nb) ? (pd.has_norm ? (x - rstat[k]) / sqrtf(rstat[64 + k] + pd.norm_eps) : x) : 0.f;
-      }
-      // ---- 3. advantage normalisation over the whole minibatch (warp 0, identical in every CTA) ----------------
-      if (warp == 0) {
-        float* adv = MBf + (DAP + 1) * PRS;
-        float am = 0.f, ais = 1.f;
-        if (A.hp.normalize_advantage && nb > 1) {
-          const float a0 = lane < nb ? adv[lane] : 0.f, a1 = lane + 32 < nb ? adv[lane + 32] : 0.f;
-          am = warp_sum(a0 + a1) * inv_nb;
-          const float d0 = lane < nb ? a0 - am : 0.f, d1 = lane + 32 < nb ? a1 - am : 0.f;
-          ais = 1.0f / (sqrtf(warp_sum(d0 * d0 + d1 * d1) / (float)(nb - 1)) + 1e-8f);
-        }
-        if (lane < nb) adv[lane] = (adv[lane] - am) * ais;
-        if (lane + 32 < nb) adv[lane + 32] = (adv[lane + 32] - am) * ais;
-      }
-      __syncthreads();
-
-      // ---- 4. forward on the own rows: thread = (tower, column gj, RPT rows) -----------------------------------------
-      auto own_gemm = [&](const float* __restrict__ Ain, const float* __restrict__ Wk, int wld, int K,
-                          float (&acc)[4]) {
-        acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-#pragma unroll 4
-        for (int k = 0; k < K; ++k) {
-          const float w = Wk[k * wld + gj];
-          const float* ar = Ain + k * RL + gr0;
-          if (RPT == 2) {
-            const float2 a = *reinterpret_cast<const float2*>(ar);
-            acc[0] = fmaf(a.x, w, acc[0]);
-            acc[1] = fmaf(a.y, w, acc[1]);
-          } else {
-            const float4 a = ld4(ar);
-            acc[0] = fmaf(a.x, w, acc[0]);
-            acc[1] = fmaf(a.y, w, acc[1]);
-            acc[2] = fmaf(a.z, w, acc[2]);
-            acc[3] = fmaf(a.w, w, acc[3]);
-          }
-        }
-      };
-      {
-        float acc[4];
-        own_gemm(XNo, W1t, HP, Do, acc);
-        const float b = gj < h ? Pm[(net ? pd.off_vf_b1 : pd.off_pi_b1) + gj] : 0.f;
-        for (int x = 0; x < RPT; ++x) H1[gj * RL + gr0 + x] = tanhf(acc[x] + b);
-      }
-      __syncthreads();
-      {
-        float acc[4];
-        own_gemm(H1, W2t, HP, h, acc);
-        const float b = gj < h ? Pm[(net ? pd.off_vf_b2 : pd.off_pi_b2) + gj] : 0.f;
-        for (int x = 0; x < RPT; ++x) LAT[gj * RL + gr0 + x] = tanhf(acc[x] + b);
-      }
-      __syncthreads();
-
-      // ---- 5. heads -----------------------------------------------------------------------------------------------------
-      // (i) action means / logits: thread (a, r) ; value: 32 threads = (r, quarter of the latent)
-      if (net == 0) {
-        const float* Wa = Pm + pd.off_act_w;
-        for (int w = tt; w < Da * RL; w += 128) {
-          const int a = w / RL, r = w - a * RL;
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          int j = 0;
-          for (; j + 4 <= h; j += 4) {
-            s0 = fmaf(Wa[a * h + j + 0], LAT[(j + 0) * RL + r], s0);
-            s1 = fmaf(Wa[a * h + j + 1], LAT[(j + 1) * RL + r], s1);
-            s2 = fmaf(Wa[a * h + j + 2], LAT[(j + 2) * RL + r], s2);
-            s3 = fmaf(Wa[a * h + j + 3], LAT[(j + 3) * RL + r], s3);
-          }
-          for (; j < h; ++j) s0 = fmaf(Wa[a * h + j], LAT[j * RL + r], s0);
-          MEAN[a * RL + r] = Pm[pd.off_act_b + a] + ((s0 + s1) + (s2 + s3));
-        }
-      } else if (tt < 4 * RL) {
-        const float* wv = Pm + pd.off_val_w;
-        const int r = tt >> 2, q = tt & 3;
-        float s = 0.f;
-        for (int j = q; j < h; j += 4) s = fmaf(wv[j], LAT[j * RL + r], s);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        if (q == 0) VALS[r] = s + Pm[pd.off_val_b];
-      }
-      __syncthreads();
-      // (ii) per-row loss terms and dL/d(head outputs): RL threads per tower
-      float l_pg = 0.f, l_v = 0.f, l_ent = 0.f;
-      if (tt < RL) {
-        const int r = tt, gr = row0 + r;
-        const bool live = gr < nb;
-        if (net == 1) {
-          const float dv = VALS[r] - MBf[(DAP + 2) * PRS + gr];
-          float g = 0.f;
-          if (live) {
-            l_v = dv * dv;
-            g = A.hp.vf_coef * 2.0f * dv * inv_nb;
-          }
-          DVAL[r] = g;
+  // minibatch indices of a step (epoch ep, first row start) -> s_idx, computed by threads 192..255
+  const int Ni = (int)N;
+  auto step_indices = [&](int ep, int start) {
+    const int t = tid - (PT - PR);
+    if (t >= 0) {
+      const int nbx = min(mb, Ni - start);
+      int idx = 0;
+      if (t < nbx) {
+        if (perm_in) {
+          idx = (int)perm_in[(int64_t)ep * N + start + t];
         } else {
-          const float adv = MBf[(DAP + 1) * PRS + gr], logp_old = MBf[DAP * PRS + gr];
-          float logp = 0.f, ent = 0.f;
-          if (!pd.discrete) {
-            const float* lstd = Pm + pd.off_log_std;
-            for (int a = 0; a < Da; ++a) {
-              const float ls = lstd[a], sd = expf(ls), var = sd * sd;
-              const float diff = MBf[a * PRS + gr] - MEAN[a * RL + r];
-              logp += -(diff * diff) / (2.0f * var) - ls - 0.9189385332046727f;
-              ent += 1.4189385332046727f + ls;
-              DM[a * RL + r] = diff / var;                 // d logp / d mean
-              DLS[a * RL + r] = diff * diff / var - 1.0f;  // d logp / d log_std
-            }
-          } else {
-            float mx = -INFINITY;
-            for (int a = 0; a < Da; ++a) mx = fmaxf(mx, MEAN[a * RL + r]);
-            float se = 0.f;
-            for (int a = 0; a < Da; ++a) se += expf(MEAN[a * RL + r] - mx);
-            const float lse = mx + logf(se);
-            const int act = (int)MBf[gr];
-            for (int a = 0; a < Da; ++a) {
-              const float lp = MEAN[a * RL + r] - lse;
-              if (a == act) logp = lp;
-              ent -= expf(lp) * lp;
-              DLS[a * RL + r] = lp;  // temporarily: log p_a
-            }
-          }
-          const float ratio = expf(logp - logp_old);
-          const float lo = 1.0f - A.hp.clip_range, hi = 1.0f + A.hp.clip_range;
-          const float pl1 = adv * ratio, pl2 = adv * fminf(fmaxf(ratio, lo), hi);
-          const bool inside = (ratio >= lo) && (ratio <= hi);
-          float dl_dlogp = (inside || pl1 < pl2) ? -adv * ratio * inv_nb : 0.f;
-          float dent = -A.hp.ent_coef * inv_nb;  // d(ent_coef * ent_loss) / d(entropy)
-          if (live) {
-            l_pg = -fminf(pl1, pl2);
-            l_ent = -ent;
-          } else {
-            dl_dlogp = 0.f;
-            dent = 0.f;
-          }
-          if (!pd.discrete) {
-            for (int a = 0; a < Da; ++a) {
-              DLS[a * RL + r] = dl_dlogp * DLS[a * RL + r] + dent;  // dH/dlog_std = 1
-              DM[a * RL + r] = dl_dlogp * DM[a * RL + r];
-            }
-          } else {
-            const int act = (int)MBf[gr];
-            for (int a = 0; a < Da; ++a) {
-              const float lp = DLS[a * RL + r], pp = expf(lp);
-              DM[a * RL + r] = dl_dlogp * (((a == act) ? 1.f : 0.f) - pp) + dent * (-pp * (lp + ent));
-              DLS[a * RL + r] = 0.f;
-            }
-          }
+          const FeistelKey fk = feistel_key(A.seed, IMB_STREAM_PPO_PERM, (uint64_t)(perm_draw0 + ep), (uint64_t)N);
+          idx = (int)feistel_perm(fk, (uint64_t)(start + t), (uint64_t)N);
         }
       }
-      // partial loss sums of this CTA -> CTA 0 (distributed shared memory)
-      if (loss_log) {  // (uniform) loss terms are only reduced when the caller asked for the log
-        const float s_pg = block_sum(l_pg, red);
-        const float s_v = block_sum(l_v, red);
-        const float s_ent = block_sum(l_ent, red);
-        if (tid == 0) {
-          float* L0 = cluster.map_shared_rank(LOSS, 0);
-          L0[crank * 3 + 0] = s_pg;
-          L0[crank * 3 + 1] = s_v;
-          L0[crank * 3 + 2] = s_ent;
-        }
-      }
-      __syncthreads();
-      // (iii) dL/dz2 = (dL/dlatent) * (1 - lat^2): thread = (tower, column gj, RPT rows)
-      for (int x = 0; x < RPT; ++x) {
-        const int r = gr0 + x;
-        float dl = 0.f;
-        if (gj < h) {
-          if (net == 1) {
-            dl = DVAL[r] * Pm[pd.off_val_w + gj];
-          } else {
-            const float* Wa = Pm + pd.off_act_w;
-            for (int a = 0; a < Da; ++a) dl = fmaf(DM[a * RL + r], Wa[a * h + gj], dl);
-          }
-        }
-        const float l = LAT[gj * RL + r];
-        DZ2[gj * RL + r] = dl * (1.0f - l * l);
-      }
-      __syncthreads();
-      // ---- 6. backward through layer 2 --------------------------------------------------------------------------------------
-      {
-        float acc[4];
-        own_gemm(DZ2, Pm + (net ? pd.off_vf_w2 : pd.off_pi_w2), h, h, acc);  // W2[j][i]: k = j, column = i
-        for (int x = 0; x < RPT; ++x) {
-          const float hh = H1[gj * RL + gr0 + x];
-          DZ1[gj * RL + gr0 + x] = gj < h ? acc[x] * (1.f - hh * hh) : 0.f;
-        }
-      }
-      __syncthreads();
-      // ---- 7. partial gradient of every parameter: one dot product over the RL own rows ----------------------------
-      // ... pushed straight into the owner's receive buffer RECV[this CTA][i]: one 16-byte DSMEM store per
-      // parameter quad (scalar remote accesses are transaction-bound: ~10 k of them per step cost more
-      // than all the arithmetic; see profiles/r01_summary.md)
-      // CTA c starts with the quads owned by CTA c+1, so at any time the 8 senders target 8 different
-      // receivers (all of them hitting owner 0 first made the receiving SM the bottleneck: ~40 % of the step)
-      for (int q = tid; q < CL * S / 4; q += PT) {
-        int qq = q + ((crank + 1) & (CL - 1)) * (S / 4);
-        if (qq >= CL * S / 4) qq -= CL * S / 4;
-        const int p0 = 4 * qq;
-        if (p0 >= NP) continue;
-        float4 g;
-        g.x = dot8(smem + 4 * (int)offA[p0 + 0], smem + 4 * (int)offB[p0 + 0]);
-        g.y = dot8(smem + 4 * (int)offA[p0 + 1], smem + 4 * (int)offB[p0 + 1]);
-        g.z = dot8(smem + 4 * (int)offA[p0 + 2], smem + 4 * (int)offB[p0 + 2]);
-        g.w = dot8(smem + 4 * (int)offA[p0 + 3], smem + 4 * (int)offB[p0 + 3]);
-        const int owner = p0 / S;
-        st4(cluster.map_shared_rank(RECV, owner) + crank * S + (p0 - owner * S), g);
-      }
-      cluster.sync();  // (a) all partial gradients (and partial losses) have landed at their owners
+      s_idx[t] = idx;
+    }
+  };
+  // asynchronous gather of that step's rows into buffer `buf`, issued by `nthr` threads (t0 = rank among them)
+  auto issue_gather = [&](int start, int buf, int t0, int nthr) {
+    const int nbx = min(mb, Ni - start);
+    for (int e = t0; e < PR * rwg; e += nthr) {
+      const unsigned lut = glut[e];
+      const int r = lut & 0xFF, sc = (lut >> 8) & 0xFF;
+      int dst = (int)(lut >> 16);
+      if (buf) dst += (dst < (int)(MB - smem)) ? xsz : msz;
+      if (r < nbx) cp_async4(smem + dst, rollout + (int64_t)s_idx[r] * A.rw + sc);
+      else smem[dst] = 0.f;
+    }
+    cp_async_commit();
+  };
+  __syncthreads();
+  step_indices(0, 0);
+  __syncthreads();
+  issue_gather(0, 0, tid, PT);
+  cluster.sync();
 
-      // ---- 8. slice owners: sum the CL partials in fixed order, exchange squared norms ----------------------------------
-      float ss = 0.f;
-      {
-        for (int i = tid; i < S; i += PT) {
-          const int p = crank * S + i;
-          float g = 0.f;
-          if (p < NP) {
-#pragma unroll
-            for (int c = 0; c < CL; ++c) g += RECV[c * S + i];  // fixed order: deterministic
-          }
-          GSL[i] = g;
-          ss = fmaf(g, g, ss);
-        }
-      }
-      const float my_ssq = block_sum(ss, red);
-      if (tid < CL) cluster.map_shared_rank(SSQ, tid)[crank] = my_ssq;
-      if (crank == 0 && tid == 0 && loss_log) {
-        float pg = 0.f, vl = 0.f, el = 0.f;
-        for (int c = 0; c < CL; ++c) {
-          pg += LOSS[c * 3 + 0];
-          vl += LOSS[c * 3 + 1];
-          el += LOSS[c * 3 + 2];
-        }
-        pg *= inv_nb, vl *= inv_nb, el *= inv_nb;
-        loss_log[log_i * 4 + 0] = pg;
-        loss_log[log_i * 4 + 1] = vl;
-        loss_log[log_i * 4 + 2] = el;
-        loss_log[log_i * 4 + 3] = pg + A.hp.ent_coef * el + A.hp.vf_coef * vl;
-      }
-      ++log_i;
-      cluster.sync();  // (b) all slice norms are in every CTA's SSQ
-
-      // ---- 9. clip_grad_norm_ + Adam on the owned slice; push the new parameters to every CTA ----------------------------
-      float total = 0.f;
-#pragma unroll
-      for (int c = 0; c < CL; ++c) total += SSQ[c];
-      total = sqrtf(total);
-      float clip = A.hp.max_grad_norm / (total + 1e-6f);
-      clip = clip > 1.0f ? 1.0f : clip;
-      ++adam_step;
+#ifdef IMB_PPO_TIMING
+  long long clk_acc[16] = {0}, clk_last = clock64();
+#endif
+  int ep_now = 0, start = 0;  // epoch and first row of the current step
+  for (int64_t gs = 0; gs < n_steps; ++gs) {
+    const int cur = (int)(gs & 1);
+    float* XNf = XB + cur * xsz;
+    float* MBf = MB + cur * msz;
+    const int nb = min(mb, Ni - start);
+    const float inv_nb = 1.0f / (float)nb;
+    int ep_next = ep_now, start_next = start + mb;
+    if (start_next >= Ni) {
+      start_next = 0;
+      ++ep_next;
+    }
+    ++adam_step;
+    if (tid == PT - 1) {  // Adam bias corrections in double, off the critical path (double-buffered by step parity)
       b1pow *= 0.9;
       b2pow *= 0.999;
-      const float step_size = (float)((double)A.hp.lr / (1.0 - b1pow)), bc2s = (float)sqrt(1.0 - b2pow);
-      for (int i0 = 4 * tid; i0 < S; i0 += 4 * PT) {
-        const int p0 = crank * S + i0;
-        float np4[4];
+      bc[2 * cur] = (float)((double)A.hp.lr / (1.0 - b1pow));
+      bc[2 * cur + 1] = (float)sqrt(1.0 - b2pow);
+    }
+    // ---- 1. minibatch of this step has landed (prefetched during the previous step) ----------------------------
+    cp_async_wait_all();
+    __syncthreads();
+    PPO_TICK(0);
+    // ---- 2. feature RunningNorm + advantage normalisation over the whole minibatch: one 8-lane group per
+    //         statistic (identical in every CTA) ---------------------------------------------------------------------
+    // (all lanes run the same code: the shuffles inside are full-mask; idle groups chew on the advantage row)
+    for (int task0 = 0; task0 <= Do; task0 += PT / 8) {
+      const int task = task0 + g8;
+      const bool is_feat = pd.has_norm && task < Do, is_adv = task == Do;
+      float* x = is_feat ? XNf + task * PRS : MBf + (DAP + 1) * PRS;
+      float v[8], s = 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u;
-          const float g = GSL[i] * clip;
-          const float mi = Ms[i] + (g - Ms[i]) * (1.0f - 0.9f);
-          const float vi = Vs[i] * 0.999f + (1.0f - 0.999f) * g * g;
-          Ms[i] = mi;
-          Vs[i] = vi;
-          np4[u] = (p0 + u < NP) ? Pm[p0 + u] - step_size * (mi / (sqrtf(vi) / bc2s + A.hp.adam_eps)) : 0.f;
+      for (int i = 0; i < 8; ++i) {
+        v[i] = (gl + 8 * i < nb) ? x[gl + 8 * i] : 0.f;
+        s += v[i];
+      }
+      const float bmean = group8_sum(s) * inv_nb;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = (gl + 8 * i < nb) ? v[i] - bmean : 0.f;
+        q = fmaf(d, d, q);
+      }
+      const float ssd = group8_sum(q);
+      if (is_feat) {
+        if (gl == 0) {
+          float mean = rstat[task], var = rstat[64 + task];
+          const float bvar = ssd * inv_nb;
+          const float bn = (float)nb, c = (float)run_count, itot = rcp_fast(c + bn), delta = bmean - mean;
+          mean += delta * bn * itot;
+          var *= c;
+          var += bvar * bn;
+          var += delta * delta * c * bn * itot;
+          var *= itot;
+          rstat[task] = mean;
+          rstat[64 + task] = var;
+          rstat[128 + task] = rsqrtf(var + pd.norm_eps);
         }
-        const float4 v4 = make_float4(np4[0], np4[1], np4[2], np4[3]);
+      } else if (is_adv) {
+        float am = 0.f, ais = 1.f;
+        if (A.hp.normalize_advantage && nb > 1) {
+          am = bmean;
+          ais = rcp_fast(sqrt_fast(ssd / (float)(nb - 1)) + 1e-8f);
+        }
 #pragma unroll
-        for (int c = 0; c < CL; ++c)  // rotated start: the 8 owners write to 8 different CTAs at a time
-          st4(cluster.map_shared_rank(Pm, (crank + c) & (CL - 1)) + p0, v4);
+        for (int i = 0; i < 8; ++i)
+          if (gl + 8 * i < nb) x[gl + 8 * i] = (v[i] - am) * ais;
       }
-      cluster.sync();  // (c) every CTA has the new parameters
-      // transposed working copies, rebuilt locally through the position look-up table (no divisions)
-      for (int p = tid; p < 2 * (h * Do + h + h * h + h); p += PT) {
-        const int ip = imgpos[p];
-        if (ip != 0xFFFF) img[ip] = Pm[p];
-      }
-      __syncthreads();
     }
-  }
+    if (pd.has_norm) run_count += nb;
+    __syncthreads();
+    PPO_TICK(1);
+    // ---- 3. own rows, normalised, feature-major [k][RL] ------------------------------------------------------------
+    for (int e = tid; e < Do * RL; e += PT) {
+      const int k = e / RL, r = e - k * RL;
+      const float x = XNf[k * PRS + row0 + r];
+      XNo[e] = (row0 + r < nb) ? (pd.has_norm ? (x - rstat[k]) * rstat[128 + k] : x) : 0.f;
+    }
+    __syncthreads();
+    PPO_TICK(2);
 
-  // ---- write back: slice owners store parameters and moments; CTA 0 stores norm state and counters -------------------
-  for (int i = tid; i < S; i += PT) {
-    const int p = crank * S + i;
-    if (p < NP) {
-      g_params[p] = Pm[p];
-      g_m[p] = Ms[i];
-      g_v[p] = Vs[i];
+    // ---- 4. forward on the own rows: thread = (tower, unit gj, RPT rows) -----------------------------------------------
+    // acc[x] = sum_k Ain[k][gr0 + x] * Wb[k * ks]   (Wb already points at this thread's unit)
+    auto own_gemm = [&](const float* __restrict__ Ain, const float* __restrict__ Wb, int ks, int K, float (&acc)[4]) {
+      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < K; ++k) {
+        const float w = Wb[k * ks];
+        const float* ar = Ain + k * RL + gr0;
+        if (RPT == 2) {
+          const float2 a = *reinterpret_cast<const float2*>(ar);
+          acc[0] = fmaf(a.x, w, acc[0]);
+          acc[1] = fmaf(a.y, w, acc[1]);
+        } else {
+          const float4 a = ld4(ar);
+          acc[0] = fmaf(a.x, w, acc[0]);
+          acc[1] = fmaf(a.y, w, acc[1]);
+          acc[2] = fmaf(a.z, w, acc[2]);
+          acc[3] = fmaf(a.w, w, acc[3]);
+        }
+      }
+    };
+    const int gjc = jlive ? gj : 0;  // clamped unit for addressing; results of dead units are forced to 0
+    {
+      float acc[4];
+      own_gemm(XNo, W1 + gjc * ldo, 1, Do, acc);
+      const float b = Pm[PL.b1[net] + gjc];
+      for (int x = 0; x < RPT; ++x) H1[gj * RL + gr0 + x] = jlive ? PPO_TANH(acc[x] + b) : 0.f;
     }
+    __syncthreads();
+    {
+      float acc[4];
+      own_gemm(H1, W2 + gjc * ldh, 1, h, acc);
+      const float b = Pm[PL.b2[net] + gjc];
+      for (int x = 0; x < RPT; ++x) LAT[gj * RL + gr0 + x] = jlive ? PPO_TANH(acc[x] + b) : 0.f;
+    }
+    __syncthreads();
+    PPO_TICK(3);
+
+    // ---- 5a. head pre-activations: means / logits on the policy tower's threads (a, r, half of the latent),
+    //          values on the value tower's threads (r, 1/16 of the latent) ---------------------------------------------
+    if (net == 0) {
+      const float* Wa = Pm + PL.wa;
+      const int nw = (Da * 16 + 31) & ~31;
+      for (int w = tt; w < nw; w += 128) {
+        const int a = min(w >> 4, Da - 1), r = (w >> 1) & 7, jq = w & 1;
+        float s0 = 0.f, s1 = 0.f;
+        int j = jq;
+        for (; j + 2 < h; j += 4) {
+          s0 = fmaf(Wa[a * h + j], LAT[j * RL + r], s0);
+          s1 = fmaf(Wa[a * h + j + 2], LAT[(j + 2) * RL + r], s1);
+        }
+        for (; j < h; j += 2) s0 = fmaf(Wa[a * h + j], LAT[j * RL + r], s0);
+        float sm = s0 + s1;
+        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+        if (jq == 0 && (w >> 4) < Da) MEAN[a * RL + r] = Pm[PL.ba + a] + sm;
+      }
+    } else {
+      const float* wv = Pm + PL.wv;
+      const int r = tt >> 4, jq = tt & 15;
+      float sm = 0.f;
+      for (int j = jq; j < h; j += 16) sm = fmaf(wv[j], LAT[j * RL + r], sm);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 1);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 2);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 4);
+      sm += __shfl_xor_sync(0xffffffffu, sm, 8);
+      if (jq == 0) VALS[r] = sm + Pm[PL.bv];
+    }
+    __syncthreads();
+    PPO_TICK(4);
+    // ---- 5b. loss terms and dL/d(head outputs): warp 0 (policy; lanes = (a mod 4, row)) and warp 4 (value);
+    //          the six idle warps draw the NEXT minibatch's indices and issue its asynchronous gather --------------
+    float l_pg = 0.f, l_v = 0.f, l_ent = 0.f;
+    if (warp == 4) {
+      if (lane < RL) {
+        const int r = lane, gr = row0 + r;
+        const bool live = gr < nb;
+        const float dv = VALS[r] - MBf[(DAP + 2) * PRS + gr];
+        if (live) l_v = dv * dv;
+        DVAL[r] = live ? A.hp.vf_coef * 2.0f * dv * inv_nb : 0.f;
+      }
+    } else if (warp == 0) {
+      const int r = lane & 7, a4 = lane >> 3, gr = row0 + r;
+      const bool live = gr < nb;
+      const float adv = MBf[(DAP + 1) * PRS + gr], logp_old = MBf[DAP * PRS + gr];
+      float logp = 0.f, ent = 0.f;
+      if (!pd.discrete) {
+        const float* lstd = Pm + PL.ls;
+        for (int a = a4; a < Da; a += 4) {
+          const float ls = lstd[a], ivar = __expf(-2.0f * ls);
+          const float diff = MBf[a * PRS + gr] - MEAN[a * RL + r];
+          const float d2 = diff * diff * ivar;
+          logp += -0.5f * d2 - ls - 0.9189385332046727f;
+          ent += 1.4189385332046727f + ls;
+          DM[a * RL + r] = diff * ivar;   // d logp / d mean
+          DLS[a * RL + r] = d2 - 1.0f;    // d logp / d log_std
+        }
+      } else {
+        float mx = -INFINITY;
+        for (int a = a4; a < Da; a += 4) mx = fmaxf(mx, MEAN[a * RL + r]);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+        float se = 0.f;
+        for (int a = a4; a < Da; a += 4) se += expf(MEAN[a * RL + r] - mx);
+        se += __shfl_xor_sync(0xffffffffu, se, 8);
+        se += __shfl_xor_sync(0xffffffffu, se, 16);
+        const float lse = mx + logf(se);
+        const int act = (int)MBf[gr];
+        for (int a = a4; a < Da; a += 4) {
+          const float lp = MEAN[a * RL + r] - lse;
+          if (a == act) logp = lp;
+          ent -= expf(lp) * lp;
+          DLS[a * RL + r] = lp;  // temporarily: log p_a
+        }
+      }
+      logp += __shfl_xor_sync(0xffffffffu, logp, 8);
+      logp += __shfl_xor_sync(0xffffffffu, logp, 16);
+      ent += __shfl_xor_sync(0xffffffffu, ent, 8);
+      ent += __shfl_xor_sync(0xffffffffu, ent, 16);
+      const float ratio = __expf(logp - logp_old);
+      const float lo = 1.0f - A.hp.clip_range, hi = 1.0f + A.hp.clip_range;
+      const float pl1 = adv * ratio, pl2 = adv * fminf(fmaxf(ratio, lo), hi);
+      const bool inside = (ratio >= lo) && (ratio <= hi);
+      float dl_dlogp = (inside || pl1 < pl2) ? -adv * ratio * inv_nb : 0.f;
+      float dent = -A.hp.ent_coef * inv_nb;  // d(ent_coef * ent_loss) / d(entropy)
+      if (live) {
+        if (a4 == 0) {
+          l_pg = -fminf(pl1, pl2);
+          l_ent = -ent;
+        }
+      } else {
+        dl_dlogp = 0.f;
+        dent = 0.f;
+      }
+      if (!pd.discrete) {
+        for (int a = a4; a < Da; a += 4) {
+          DLS[a * RL + r] = dl_dlogp * DLS[a * RL + r] + dent;  // dH/dlog_std = 1
+          DM[a * RL + r] = dl_dlogp * DM[a * RL + r];
+        }
+      } else {
+        const int act = (int)MBf[gr];
+        for (int a = a4; a < Da; a += 4) {
+          const float lp = DLS[a * RL + r], pp = expf(lp);
+          DM[a * RL + r] = dl_dlogp * (((a == act) ? 1.f : 0.f) - pp) + dent * (-pp * (lp + ent));
+          DLS[a * RL + r] = 0.f;
+        }
+      }
+    } else if (gs + 1 < n_steps) {
+      if (warp >= 6) step_indices(ep_next, start_next);
+      asm volatile("bar.sync 1, 192;" ::: "memory");  // the six idle warps only
+      issue_gather(start_next, cur ^ 1, (warp < 4 ? warp - 1 : warp - 2) * 32 + lane, 192);
+    }
+    // partial loss sums of this CTA -> CTA 0 (distributed shared memory)
+    if (loss_log) {  // (uniform) loss terms are only reduced when the caller asked for the log
+      const float s_pg = block_sum(l_pg, red);
+      const float s_v = block_sum(l_v, red);
+      const float s_ent = block_sum(l_ent, red);
+      if (tid == 0) {
+        float* L0 = cluster.map_shared_rank(LOSS, 0);
+        L0[crank * 3 + 0] = s_pg;
+        L0[crank * 3 + 1] = s_v;
+        L0[crank * 3 + 2] = s_ent;
+      }
+    }
+    __syncthreads();
+    PPO_TICK(13);
+    // ---- 6. dL/dz2 = (dL/dlatent) * (1 - lat^2): thread = (tower, unit gj, RPT rows) ---------------------------------
+    for (int x = 0; x < RPT; ++x) {
+      const int r = gr0 + x;
+      float dl = 0.f;
+      if (jlive) {
+        if (net == 1) {
+          dl = DVAL[r] * Pm[PL.wv + gj];
+        } else {
+          const float* Wa = Pm + PL.wa;
+          for (int a = 0; a < Da; ++a) dl = fmaf(DM[a * RL + r], Wa[a * h + gj], dl);
+        }
+      }
+      const float l = LAT[gj * RL + r];
+      DZ2[gj * RL + r] = dl * (1.0f - l * l);
+    }
+    __syncthreads();
+    PPO_TICK(5);
+    // ---- 7. backward through layer 2: dH1[i] = sum_j DZ2[j] W2[j][i]  (k = j, this thread's unit = i) --------------
+    {
+      float acc[4];
+      own_gemm(DZ2, W2 + gjc, ldh, h, acc);
+      for (int x = 0; x < RPT; ++x) {
+        const float hh = H1[gj * RL + gr0 + x];
+        DZ1[gj * RL + gr0 + x] = jlive ? acc[x] * (1.f - hh * hh) : 0.f;
+      }
+    }
+    __syncthreads();
+    PPO_TICK(6);
+    // ---- 8. partial gradient (own RL rows) of every parameter -> GP (P-layout, local shared memory) ---------------
+    // thread = (tower, unit gj, every NWQ-th input): the unit's dL/dz rows live in registers, the input rows are
+    // warp-uniform broadcasts, the scattered GP stores have odd lane strides (conflict free).
+    if (jlive) {
+      float dz[8];
+      load8(dz, DZ2 + gj * RL);
+      for (int i = wq; i < h; i += NWQ) GP[PL.w2[net] + gj * ldh + i] = dot8r(dz, H1 + i * RL);
+      if (wq == 0) GP[PL.b2[net] + gj] = sum8(dz);
+      load8(dz, DZ1 + gj * RL);
+      for (int k = wq; k < Do; k += NWQ) GP[PL.w1[net] + gj * ldo + k] = dot8r(dz, XNo + k * RL);
+      if (wq == NWQ - 1) GP[PL.b1[net] + gj] = sum8(dz);
+      load8(dz, LAT + gj * RL);
+      if (net == 0) {
+        for (int a = wq; a < Da; a += NWQ) GP[PL.wa + a * h + gj] = dot8r(dz, DM + a * RL);
+      } else if (wq == 0) {
+        GP[PL.wv + gj] = dot8r(dz, DVAL);
+      }
+    }
+    if (net == 1 && wq == NWQ - 1) {  // ba, log_std, bv: plain row sums
+      for (int t = gj; t <= 2 * Da; t += HP) {
+        float dz[8];
+        if (t < Da) {
+          load8(dz, DM + t * RL);
+          GP[PL.ba + t] = sum8(dz);
+        } else if (t < 2 * Da) {
+          if (!pd.discrete) {
+            load8(dz, DLS + (t - Da) * RL);
+            GP[PL.ls + t - Da] = sum8(dz);
+          }
+        } else {
+          load8(dz, DVAL);
+          GP[PL.bv] = sum8(dz);
+        }
+      }
+    }
+    __syncthreads();
+    PPO_TICK(7);
+    // ---- 9. push the partials to the slice owners: RECV[this CTA][i], one 16-byte DSMEM store per quad ----------
+    // CTA c starts with the quads owned by CTA c+1, so at any time the 8 senders target 8 different receivers
+    for (int q = tid; q < CL * S / 4; q += PT) {
+      int qq = q + ((crank + 1) & (CL - 1)) * (S / 4);
+      if (qq >= CL * S / 4) qq -= CL * S / 4;
+      const int p0 = 4 * qq, owner = p0 / S;
+      st4(cluster.map_shared_rank(RECV, owner) + crank * S + (p0 - owner * S), ld4(GP + p0));
+    }
+    PPO_TICK(8);
+    cluster.sync();  // (a) all partial gradients (and partial losses) have landed at their owners
+    PPO_TICK(9);
+
+    // ---- 10. slice owners: sum the CL partials in fixed order, all-gather the summed slice --------------------------
+    for (int i0 = 4 * tid; i0 < S; i0 += 4 * PT) {
+      float4 g = ld4(RECV + i0);
+#pragma unroll
+      for (int c = 1; c < CL; ++c) {  // fixed order: deterministic
+        const float4 t = ld4(RECV + c * S + i0);
+        g.x += t.x, g.y += t.y, g.z += t.z, g.w += t.w;
+      }
+#pragma unroll
+      for (int c = 0; c < CL; ++c)  // rotated start: the 8 owners write to 8 different CTAs at a time
+        st4(cluster.map_shared_rank(GP, (crank + c) & (CL - 1)) + crank * S + i0, g);
+    }
+    if (crank == 0 && tid == 0 && loss_log) {
+      float pg = 0.f, vl = 0.f, el = 0.f;
+      for (int c = 0; c < CL; ++c) {
+        pg += LOSS[c * 3 + 0];
+        vl += LOSS[c * 3 + 1];
+        el += LOSS[c * 3 + 2];
+      }
+      pg *= inv_nb, vl *= inv_nb, el *= inv_nb;
+      loss_log[gs * 4 + 0] = pg;
+      loss_log[gs * 4 + 1] = vl;
+      loss_log[gs * 4 + 2] = el;
+      loss_log[gs * 4 + 3] = pg + A.hp.ent_coef * el + A.hp.vf_coef * vl;
+    }
+    PPO_TICK(10);
+    cluster.sync();  // (b) every CTA holds the full summed gradient in GP
+    PPO_TICK(11);
+
+    // ---- 11. clip_grad_norm_ + Adam on the full vector, identically in every CTA ------------------------------------------
+    float ss = 0.f;
+    for (int i0 = 4 * tid; i0 < CL * S; i0 += 4 * PT) {
+      const float4 g = ld4(GP + i0);
+      ss = fmaf(g.x, g.x, ss);
+      ss = fmaf(g.y, g.y, ss);
+      ss = fmaf(g.z, g.z, ss);
+      ss = fmaf(g.w, g.w, ss);
+    }
+    const float total = sqrtf(block_sum(ss, red));
+    float clip = A.hp.max_grad_norm / (total + 1e-6f);
+    clip = clip > 1.0f ? 1.0f : clip;
+    const float step_size = bc[2 * cur], inv_bc2s = rcp_fast(bc[2 * cur + 1]);
+    for (int i0 = 4 * tid; i0 < CL * S; i0 += 4 * PT) {
+      const float4 g4 = ld4(GP + i0), m4 = ld4(Ms + i0), v4 = ld4(Vs + i0), p4 = ld4(Pm + i0);
+      // approximate sqrt / division (~1e-7 relative on an update that is itself ~lr relative to the weights)
+      auto adam1 = [&](float g, float& m, float& v, float& pw) {
+        g *= clip;
+        m = m + (g - m) * (1.0f - 0.9f);
+        v = v * 0.999f + (1.0f - 0.999f) * g * g;
+        pw -= step_size * __fdividef(m, fmaf(sqrt_fast(v), inv_bc2s, A.hp.adam_eps));
+      };
+      float4 m = m4, v = v4, pw = p4;
+      adam1(g4.x, m.x, v.x, pw.x);
+      adam1(g4.y, m.y, v.y, pw.y);
+      adam1(g4.z, m.z, v.z, pw.z);
+      adam1(g4.w, m.w, v.w, pw.w);
+      st4(Ms + i0, m);
+      st4(Vs + i0, v);
+      st4(Pm + i0, pw);
+    }
+    PPO_TICK(12);
+    ep_now = ep_next;
+    start = start_next;
+    // (the barrier at the top of the next step orders these parameter writes before their first use)
   }
+  __syncthreads();
+#ifdef IMB_PPO_TIMING
+  if (crank == 0 && tid == 0)
+    for (int i = 0; i < 16; ++i) g_ppo_clk[i] = clk_acc[i];
+#endif
+
+  // ---- write back (CTA 0): parameters and moments in torch order, norm state, counters ------------------------------
   if (crank == 0) {
+    for (int p = tid; p < NP; p += PT) {
+      const int q = flat_to_play(pd, PL, p);
+      g_params[p] = Pm[q];
+      g_m[p] = Ms[q];
+      g_v[p] = Vs[q];
+    }
     if (pd.has_norm) {
       if (tid < Do) {
         g_norm[tid] = rstat[tid];
@@ -683,12 +799,10 @@ static size_t ppo_smem_floats(const PpoArgs& A) {
   const int HP = A.HP, KP = A.KP, Da = A.pol.d_act, S = A.S;
   const int DAP = (Da + 3) / 4 * 4;
   size_t o = 0;
-  o += 2 * (size_t)al(CL * S) + 3 * (size_t)al(S) + 64;
-  o += al(2 * (KP * HP + HP * HP));
-  o += al(KP * PRS) + al((DAP + 3) * PRS);
+  o += 5 * (size_t)al(CL * S) + 32;
+  o += 2 * (size_t)al(KP * PRS) + 2 * (size_t)al((DAP + 3) * PRS);
   o += al(KP * RL) + (size_t)8 * HP * RL + (size_t)3 * DAP * RL + 32;
-  o += al(2 * 64 + 4) + al(PR);
-  o += 3 * (size_t)al((CL * S + 1) / 2);
+  o += al(3 * 64 + 4) + al(PR);
   o += al(PR * (A.pol.d_obs + (A.pol.discrete ? 1 : Da) + 3));
   return o;
 }
@@ -699,7 +813,7 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
   IMB_REQUIRE(A.hp.batch_size >= 1 && A.hp.batch_size <= PR, "PPO minibatch size must be in [1, %d]", PR);
   A.HP = A.pol.hidden <= 32 ? 32 : 64;
   A.KP = A.pol.d_obs <= 32 ? 32 : 64;
-  A.S = ((A.pol.n_params + CL - 1) / CL + 3) / 4 * 4;
+  A.S = ((make_play(A.pol).total + CL - 1) / CL + 3) / 4 * 4;
   const size_t fl = ppo_smem_floats(A);
   IMB_REQUIRE(fl * 4 <= IMB_SMEM_MAX, "PPO kernel needs %zu B of shared memory per CTA", fl * 4);
   IMB_REQUIRE(fl < 65536, "PPO kernel: shared-memory float offsets must fit 16 bits (policy too large)");
@@ -782,3 +896,9 @@ extern "C" int imb_policy_logp(const imb_policy_desc* pol, const float* pol_para
   if (pol->hidden <= 32) return launch_logp<32>(pol, pol_params, pol_norm, batch, ld, n, row_logp, (cudaStream_t)stream);
   return launch_logp<64>(pol, pol_params, pol_norm, batch, ld, n, row_logp, (cudaStream_t)stream);
 }
+
+#ifdef IMB_PPO_TIMING
+extern "C" __attribute__((visibility("default"))) int imb_debug_ppo_clocks(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_ppo_clk, 16 * sizeof(long long));
+}
+#endif
