@@ -160,6 +160,10 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// split cluster barrier (release / acquire): DSMEM stores before the arrive are visible after the wait
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // tanh with ~1e-7 absolute error in a dozen instructions (tanhf's accurate path costs ~5x more and sits on
 // the critical path of every layer of the latency-bound PPO step): odd polynomial below 0.1, else
 // 1 - 2 / (exp(2x) + 1) with the hardware exponential; saturates correctly for large |x|.

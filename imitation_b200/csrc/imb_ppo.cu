@@ -154,6 +154,7 @@ __device__ __forceinline__ float sum8(const float (&d)[8]) {
 // clip_grad_norm_ + Adam on the FULL vector (identical arithmetic everywhere, so the replicas never
 // diverge).  Two cluster barriers per optimiser step; the only global-memory traffic inside a step is the
 // asynchronous minibatch prefetch.
+template <int HP>
 __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __restrict__ g_params,
                                                       float* __restrict__ g_norm, int32_t* __restrict__ g_norm_count,
                                                       float* __restrict__ g_m, float* __restrict__ g_v,
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   __shared__ float red[32];
   __shared__ float bc[8];
   const imb_policy_desc& pd = A.pol;
-  const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params, HP = A.HP, KP = A.KP, S = A.S;
+  const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params, KP = A.KP, S = A.S;
   const PLay PL = make_play(pd);
   const int ldo = PL.ldo, ldh = PL.ldh;
   const int da_store = pd.discrete ? 1 : Da;
@@ -206,8 +207,11 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   float* LAT = TLAT + net * HP * RL;
   float* DZ2 = TDZ2 + net * HP * RL;
   float* DZ1 = TDZ1 + net * HP * RL;
-  const float* W1 = Pm + PL.w1[net];
-  const float* W2 = Pm + PL.w2[net];
+  // (selects, not PL.x[net]: a dynamically indexed member would put the whole struct in local memory)
+  const int o_w1 = net ? PL.w1[1] : PL.w1[0], o_b1 = net ? PL.b1[1] : PL.b1[0];
+  const int o_w2 = net ? PL.w2[1] : PL.w2[0], o_b2 = net ? PL.b2[1] : PL.b2[0];
+  const float* W1 = Pm + o_w1;
+  const float* W2 = Pm + o_w2;
 
   for (int i = tid; i < CL * S; i += PT) Pm[i] = Ms[i] = Vs[i] = GP[i] = RECV[i] = 0.f;
   for (int i = tid; i < 2 * xsz; i += PT) XB[i] = 0.f;
@@ -216,7 +220,6 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   if (tid < 64) {
     rstat[tid] = (pd.has_norm && tid < Do) ? g_norm[tid] : 0.f;
     rstat[64 + tid] = (pd.has_norm && tid < Do) ? g_norm[Do + tid] : 1.f;
-    rstat[128 + tid] = 1.f;
     LOSS[tid & 31] = 0.f;
   }
   __syncthreads();
@@ -247,9 +250,11 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   double b1pow = pow(0.9, (double)adam_step), b2pow = pow(0.999, (double)adam_step);  // beta^t, kept incrementally
   const int row0 = crank * RL;        // first minibatch row owned by this CTA
   // own-row GEMM mapping: thread -> column gj = tt % HP and RPT = HP / 16 consecutive rows
-  const int gj = tt % HP, RPT = HP / 16, gr0 = (tt / HP) * RPT;
+  constexpr int RPT = HP / 16;
+  const int gj = tt % HP, gr0 = (tt / HP) * RPT;
   const bool jlive = gj < h;
-  const int wq = tt / HP, NWQ = 128 / HP;  // weight-gradient mapping: unit gj, every NWQ-th input
+  constexpr int NWQ = 128 / HP;
+  const int wq = tt / HP;  // weight-gradient mapping: unit gj, every NWQ-th input
   const int g8 = tid >> 3, gl = tid & 7;   // 8-lane statistic groups
 
   // minibatch indices of a step (epoch ep, first row start) -> s_idx, computed by threads 192..255
@@ -283,10 +288,71 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     }
     cp_async_commit();
   };
+  // Statistics of one minibatch (already gathered into buffer `buf`): feature RunningNorm update + advantage
+  // normalisation over all 64 rows, one 8-lane group per statistic, identically in every CTA; the group of
+  // feature k also writes this CTA's own rows of it, normalised, into XNo[k][RL] (lane = row).  All lanes run the
+  // same code (full-mask shuffles); idle groups chew on the advantage row and discard the result.
+  auto minibatch_stats = [&](int buf, int nbx) {
+    float* XNf = XB + buf * xsz;
+    float* MBf = MB + buf * msz;
+    const float inv_nbx = 1.0f / (float)nbx;
+    cp_async_wait_all();
+    __syncthreads();  // the asynchronous gather of this minibatch (issued by six warps) has landed
+    for (int task0 = 0; task0 <= Do; task0 += PT / 8) {
+      const int task = task0 + g8;
+      const bool is_feat = task < Do, is_adv = task == Do;
+      float* x = is_feat ? XNf + task * PRS : MBf + (DAP + 1) * PRS;
+      float v[8], s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = (gl + 8 * i < nbx) ? x[gl + 8 * i] : 0.f;
+        s += v[i];
+      }
+      const float bmean = group8_sum(s) * inv_nbx;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = (gl + 8 * i < nbx) ? v[i] - bmean : 0.f;
+        q = fmaf(d, d, q);
+      }
+      const float ssd = group8_sum(q);
+      if (is_feat) {
+        float mean = 0.f, istd = 1.f;
+        if (pd.has_norm) {  // every lane of the group computes the update; lane 0 stores it
+          mean = rstat[task];
+          float var = rstat[64 + task];
+          const float bvar = ssd * inv_nbx;
+          const float bn = (float)nbx, c = (float)run_count, itot = rcp_fast(c + bn), delta = bmean - mean;
+          mean += delta * bn * itot;
+          var *= c;
+          var += bvar * bn;
+          var += delta * delta * c * bn * itot;
+          var *= itot;
+          istd = rsqrtf(var + pd.norm_eps);
+          if (gl == 0) {
+            rstat[task] = mean;
+            rstat[64 + task] = var;
+          }
+        }
+        XNo[task * RL + gl] = (row0 + gl < nbx) ? (x[row0 + gl] - mean) * istd : 0.f;
+      } else if (is_adv) {
+        float am = 0.f, ais = 1.f;
+        if (A.hp.normalize_advantage && nbx > 1) {
+          am = bmean;
+          ais = rcp_fast(sqrt_fast(ssd / (float)(nbx - 1)) + 1e-8f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (gl + 8 * i < nbx) x[gl + 8 * i] = (v[i] - am) * ais;
+      }
+    }
+    if (pd.has_norm) run_count += nbx;
+  };
   __syncthreads();
   step_indices(0, 0);
   __syncthreads();
   issue_gather(0, 0, tid, PT);
+  minibatch_stats(0, min(mb, Ni));
   cluster.sync();
 
 #ifdef IMB_PPO_TIMING
@@ -295,8 +361,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   int ep_now = 0, start = 0;  // epoch and first row of the current step
   for (int64_t gs = 0; gs < n_steps; ++gs) {
     const int cur = (int)(gs & 1);
-    float* XNf = XB + cur * xsz;
-    float* MBf = MB + cur * msz;
+    const float* MBf = MB + cur * msz;
     const int nb = min(mb, Ni - start);
     const float inv_nb = 1.0f / (float)nb;
     int ep_next = ep_now, start_next = start + mb;
@@ -311,67 +376,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       bc[2 * cur] = (float)((double)A.hp.lr / (1.0 - b1pow));
       bc[2 * cur + 1] = (float)sqrt(1.0 - b2pow);
     }
-    // ---- 1. minibatch of this step has landed (prefetched during the previous step) ----------------------------
-    cp_async_wait_all();
-    __syncthreads();
+    __syncthreads();  // the parameters written by the previous step's Adam are visible
     PPO_TICK(0);
-    // ---- 2. feature RunningNorm + advantage normalisation over the whole minibatch: one 8-lane group per
-    //         statistic (identical in every CTA) ---------------------------------------------------------------------
-    // (all lanes run the same code: the shuffles inside are full-mask; idle groups chew on the advantage row)
-    for (int task0 = 0; task0 <= Do; task0 += PT / 8) {
-      const int task = task0 + g8;
-      const bool is_feat = pd.has_norm && task < Do, is_adv = task == Do;
-      float* x = is_feat ? XNf + task * PRS : MBf + (DAP + 1) * PRS;
-      float v[8], s = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[i] = (gl + 8 * i < nb) ? x[gl + 8 * i] : 0.f;
-        s += v[i];
-      }
-      const float bmean = group8_sum(s) * inv_nb;
-      float q = 0.f;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float d = (gl + 8 * i < nb) ? v[i] - bmean : 0.f;
-        q = fmaf(d, d, q);
-      }
-      const float ssd = group8_sum(q);
-      if (is_feat) {
-        if (gl == 0) {
-          float mean = rstat[task], var = rstat[64 + task];
-          const float bvar = ssd * inv_nb;
-          const float bn = (float)nb, c = (float)run_count, itot = rcp_fast(c + bn), delta = bmean - mean;
-          mean += delta * bn * itot;
-          var *= c;
-          var += bvar * bn;
-          var += delta * delta * c * bn * itot;
-          var *= itot;
-          rstat[task] = mean;
-          rstat[64 + task] = var;
-          rstat[128 + task] = rsqrtf(var + pd.norm_eps);
-        }
-      } else if (is_adv) {
-        float am = 0.f, ais = 1.f;
-        if (A.hp.normalize_advantage && nb > 1) {
-          am = bmean;
-          ais = rcp_fast(sqrt_fast(ssd / (float)(nb - 1)) + 1e-8f);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (gl + 8 * i < nb) x[gl + 8 * i] = (v[i] - am) * ais;
-      }
-    }
-    if (pd.has_norm) run_count += nb;
-    __syncthreads();
-    PPO_TICK(1);
-    // ---- 3. own rows, normalised, feature-major [k][RL] ------------------------------------------------------------
-    for (int e = tid; e < Do * RL; e += PT) {
-      const int k = e / RL, r = e - k * RL;
-      const float x = XNf[k * PRS + row0 + r];
-      XNo[e] = (row0 + r < nb) ? (pd.has_norm ? (x - rstat[k]) * rstat[128 + k] : x) : 0.f;
-    }
-    __syncthreads();
-    PPO_TICK(2);
 
     // ---- 4. forward on the own rows: thread = (tower, unit gj, RPT rows) -----------------------------------------------
     // acc[x] = sum_k Ain[k][gr0 + x] * Wb[k * ks]   (Wb already points at this thread's unit)
@@ -398,14 +404,16 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     {
       float acc[4];
       own_gemm(XNo, W1 + gjc * ldo, 1, Do, acc);
-      const float b = Pm[PL.b1[net] + gjc];
+      const float b = Pm[o_b1 + gjc];
+#pragma unroll
       for (int x = 0; x < RPT; ++x) H1[gj * RL + gr0 + x] = jlive ? PPO_TANH(acc[x] + b) : 0.f;
     }
     __syncthreads();
     {
       float acc[4];
       own_gemm(H1, W2 + gjc * ldh, 1, h, acc);
-      const float b = Pm[PL.b2[net] + gjc];
+      const float b = Pm[o_b2 + gjc];
+#pragma unroll
       for (int x = 0; x < RPT; ++x) LAT[gj * RL + gr0 + x] = jlive ? PPO_TANH(acc[x] + b) : 0.f;
     }
     __syncthreads();
@@ -539,6 +547,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     __syncthreads();
     PPO_TICK(13);
     // ---- 6. dL/dz2 = (dL/dlatent) * (1 - lat^2): thread = (tower, unit gj, RPT rows) ---------------------------------
+#pragma unroll
     for (int x = 0; x < RPT; ++x) {
       const int r = gr0 + x;
       float dl = 0.f;
@@ -555,28 +564,25 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     }
     __syncthreads();
     PPO_TICK(5);
-    // ---- 7. backward through layer 2: dH1[i] = sum_j DZ2[j] W2[j][i]  (k = j, this thread's unit = i) --------------
+    // ---- 7. backward through layer 2: dH1[i] = sum_j DZ2[j] W2[j][i]  (k = j, this thread's unit = i); in the same
+    //         phase the partial gradients that do not need its result: layer 2, heads ------------------------------------
+    // Partial gradients (own RL rows) go to GP (P-layout, local shared memory): thread = (tower, unit gj, every
+    // NWQ-th input); the unit's dL/dz rows live in registers, the input rows are warp-uniform broadcasts, the
+    // scattered GP stores have odd lane strides (conflict free).
     {
       float acc[4];
       own_gemm(DZ2, W2 + gjc, ldh, h, acc);
+#pragma unroll
       for (int x = 0; x < RPT; ++x) {
         const float hh = H1[gj * RL + gr0 + x];
         DZ1[gj * RL + gr0 + x] = jlive ? acc[x] * (1.f - hh * hh) : 0.f;
       }
     }
-    __syncthreads();
-    PPO_TICK(6);
-    // ---- 8. partial gradient (own RL rows) of every parameter -> GP (P-layout, local shared memory) ---------------
-    // thread = (tower, unit gj, every NWQ-th input): the unit's dL/dz rows live in registers, the input rows are
-    // warp-uniform broadcasts, the scattered GP stores have odd lane strides (conflict free).
     if (jlive) {
       float dz[8];
       load8(dz, DZ2 + gj * RL);
-      for (int i = wq; i < h; i += NWQ) GP[PL.w2[net] + gj * ldh + i] = dot8r(dz, H1 + i * RL);
-      if (wq == 0) GP[PL.b2[net] + gj] = sum8(dz);
-      load8(dz, DZ1 + gj * RL);
-      for (int k = wq; k < Do; k += NWQ) GP[PL.w1[net] + gj * ldo + k] = dot8r(dz, XNo + k * RL);
-      if (wq == NWQ - 1) GP[PL.b1[net] + gj] = sum8(dz);
+      for (int i = wq; i < h; i += NWQ) GP[o_w2 + gj * ldh + i] = dot8r(dz, H1 + i * RL);
+      if (wq == 0) GP[o_b2 + gj] = sum8(dz);
       load8(dz, LAT + gj * RL);
       if (net == 0) {
         for (int a = wq; a < Da; a += NWQ) GP[PL.wa + a * h + gj] = dot8r(dz, DM + a * RL);
@@ -602,6 +608,15 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       }
     }
     __syncthreads();
+    PPO_TICK(6);
+    // ---- 8. partial gradients of layer 1 ------------------------------------------------------------------------------------
+    if (jlive) {
+      float dz[8];
+      load8(dz, DZ1 + gj * RL);
+      for (int k = wq; k < Do; k += NWQ) GP[o_w1 + gj * ldo + k] = dot8r(dz, XNo + k * RL);
+      if (wq == NWQ - 1) GP[o_b1 + gj] = sum8(dz);
+    }
+    __syncthreads();
     PPO_TICK(7);
     // ---- 9. push the partials to the slice owners: RECV[this CTA][i], one 16-byte DSMEM store per quad ----------
     // CTA c starts with the quads owned by CTA c+1, so at any time the 8 senders target 8 different receivers
@@ -612,7 +627,12 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       st4(cluster.map_shared_rank(RECV, owner) + crank * S + (p0 - owner * S), ld4(GP + p0));
     }
     PPO_TICK(8);
-    cluster.sync();  // (a) all partial gradients (and partial losses) have landed at their owners
+    // (a) cluster barrier, split: in its shadow the NEXT step's minibatch statistics and own-row tile (they do
+    //     not depend on the parameters); after the wait all partial gradients / losses have landed at their owners
+    cluster_arrive();
+    if (gs + 1 < n_steps) minibatch_stats(cur ^ 1, min(mb, Ni - start_next));
+    PPO_TICK(1);
+    cluster_wait();
     PPO_TICK(9);
 
     // ---- 10. slice owners: sum the CL partials in fixed order, all-gather the summed slice --------------------------
@@ -811,7 +831,8 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
                       const float* rollout, const int64_t* perm, float* loss_log, int64_t* state, cudaStream_t st) {
   PpoArgs A = A0;
   IMB_REQUIRE(A.hp.batch_size >= 1 && A.hp.batch_size <= PR, "PPO minibatch size must be in [1, %d]", PR);
-  A.HP = A.pol.hidden <= 32 ? 32 : 64;
+  IMB_REQUIRE(A.pol.hidden <= 32, "PPO update kernel: tower width %d > 32 does not fit the shared-memory resident design", A.pol.hidden);
+  A.HP = 32;
   A.KP = A.pol.d_obs <= 32 ? 32 : 64;
   A.S = ((make_play(A.pol).total + CL - 1) / CL + 3) / 4 * 4;
   const size_t fl = ppo_smem_floats(A);
@@ -819,7 +840,7 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
   IMB_REQUIRE(fl < 65536, "PPO kernel: shared-memory float offsets must fit 16 bits (policy too large)");
   static size_t attr_bytes = 0;
   if (fl * 4 > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(k_ppo_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fl * 4));
+    cudaError_t e = cudaFuncSetAttribute(k_ppo_update<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fl * 4));
     if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_bytes = fl * 4;
   }
@@ -835,7 +856,7 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_ppo_update, A, params, norm, norm_count, m, v, rollout, perm, loss_log,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_ppo_update<32>, A, params, norm, norm_count, m, v, rollout, perm, loss_log,
                                      state);
   if (e != cudaSuccess) IMB_FAIL(-2, "k_ppo_update (cluster launch): %s", cudaGetErrorString(e));
   return 0;
