@@ -49,6 +49,7 @@ struct PpoArgs {
   int rw;
   uint64_t seed;
   int HP, KP, S;  // tower width / obs width padded to 32; padded-layout parameters per slice (multiple of 4)
+  int RS2;        // staged row stride in shared memory: >= rw, = 4 (mod 8)
 };
 
 // Padded parameter layout used inside the kernel ("P-layout"): W1 rows have stride ldo = d_obs|1 and W2 rows
@@ -146,14 +147,21 @@ __device__ __forceinline__ float sum8(const float (&d)[8]) {
 }
 
 // PPO.train for one rollout: n_epochs x ceil(N / batch) optimiser steps, ONE cluster of CL CTAs.
-// Every CTA receives the whole minibatch (64 x ~26 floats, prefetched one step ahead with cp.async) so that
-// the feature RunningNorm and the advantage normalisation are computed redundantly and identically
-// everywhere; forward/backward run on the CTA's own RL rows; the per-CTA partial gradients are staged in
-// local shared memory and exchanged through distributed shared memory with 16-byte stores: slice owners
-// sum the CL partials in fixed order and all-gather the summed slices; every CTA then runs
-// clip_grad_norm_ + Adam on the FULL vector (identical arithmetic everywhere, so the replicas never
-// diverge).  Two cluster barriers per optimiser step; the only global-memory traffic inside a step is the
-// asynchronous minibatch prefetch.
+// Data flow of one optimiser step (64-row minibatch, CTA c owns rows 8c..8c+7, every CTA holds all parameters):
+//   * the minibatch rows are staged row-major in shared memory by 64 bulk-async (TMA) row copies issued one
+//     step ahead by two warps (indices drawn on the fly), completion on an mbarrier;
+//   * minibatch statistics (feature RunningNorm update, advantage normalisation) over all 64 rows are computed
+//     redundantly and identically by every CTA -- in the shadow of the previous step's cluster barrier;
+//   * forward + loss + backward to dL/dz run WARP-AUTONOMOUSLY: warp = (tower, 2 own rows), lane = hidden
+//     unit; only __syncwarp() between layers (the two towers interact through the summed loss only), so
+//     the ~8 dependent stages of the chain cost no CTA barrier;
+//   * weight gradients over the CTA's 8 rows: thread = (tower, unit, input subset), staged in local shared
+//     memory in the parameter layout, pushed to the slice owners through distributed shared memory with
+//     16-byte stores; owners sum the CL partials in fixed order and all-gather the summed slices;
+//   * every CTA then runs clip_grad_norm_ + Adam on the FULL vector (identical arithmetic everywhere, so the
+//     replicas never diverge).
+// Two cluster barriers and three CTA barriers per optimiser step; the only global-memory traffic inside a
+// step is the asynchronous minibatch prefetch.
 template <int HP>
 __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __restrict__ g_params,
                                                       float* __restrict__ g_norm, int32_t* __restrict__ g_norm_count,
@@ -161,20 +169,23 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
                                                       const float* __restrict__ rollout,
                                                       const int64_t* __restrict__ perm_in,
                                                       float* __restrict__ loss_log, int64_t* __restrict__ state) {
+  static_assert(HP == 32, "the warp-autonomous chain maps one lane to one hidden unit");
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int crank = (int)cluster.block_rank();
   extern __shared__ __align__(128) float smem[];
   __shared__ float red[32];
   __shared__ float bc[8];
+  __shared__ __align__(8) uint64_t mbar[2];
   const imb_policy_desc& pd = A.pol;
   const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params, KP = A.KP, S = A.S;
   const PLay PL = make_play(pd);
   const int ldo = PL.ldo, ldh = PL.ldh;
   const int da_store = pd.discrete ? 1 : Da;
-  const int col_logp = Do + da_store, col_adv = col_logp + 3;
+  const int col_logp = Do + da_store, col_adv = col_logp + 3, col_ret = col_logp + 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int net = tid >> 7, tt = tid & 127;  // tower, thread within tower
+  const int rw = A.rw, RS2 = A.RS2;          // rollout row width (multiple of 4) / staged row stride (= 4 mod 8)
   auto al = [](int x) { return (x + 31) / 32 * 32; };
 
   // ---- shared-memory carve-up (identical in every CTA: DSMEM addresses are rank + offset) ---------------
@@ -186,9 +197,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   float* RECV = smem + o; o += al(CL * S);      // [source CTA][S]: partial gradients of the owned slice
   float* LOSS = smem + o; o += 32;              // [CL][3] partial loss sums (read by CTA 0)
   const int DAP = (Da + 3) / 4 * 4;
-  const int xsz = al(KP * PRS), msz = al((DAP + 3) * PRS);
-  float* XB = smem + o; o += 2 * xsz;           // double-buffered full minibatch, feature-major [k][PRS]
-  float* MB = smem + o; o += 2 * msz;           // act[DAP] | logp_old | adv | ret, [c][PRS]
+  const int rsz = al(PR * RS2);
+  float* ROWS = smem + o; o += 2 * rsz;         // double-buffered minibatch, row-major [64][RS2]
   // own-row tiles, feature-major [feature][RL]
   float* XNo = smem + o; o += al(KP * RL);
   float* TH1 = smem + o; o += 2 * HP * RL;
@@ -198,11 +208,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   float* DM = smem + o; o += DAP * RL;          // dL/d(mean|logits) [a][RL]
   float* DLS = smem + o; o += DAP * RL;         // dL/d(log_std) per row [a][RL]
   float* MEAN = smem + o; o += DAP * RL;        // action means / logits [a][RL]
-  float* DVAL = smem + o; o += 32;              // [RL] dL/dvalue ; VALS at +8
-  float* VALS = DVAL + 8;
-  float* rstat = smem + o; o += al(3 * 64 + 4);   // mean | var | 1/sqrt(var + eps)
-  int* s_idx = reinterpret_cast<int*>(smem + o); o += al(PR);
-  unsigned int* glut = reinterpret_cast<unsigned int*>(smem + o); o += al(PR * (Do + da_store + 3));  // gather LUT
+  float* DVAL = smem + o; o += 32;              // [RL] dL/dvalue
+  float* rstat = smem + o; o += al(2 * 64 + 4); // running mean | var of the policy's feature RunningNorm
   float* H1 = TH1 + net * HP * RL;
   float* LAT = TLAT + net * HP * RL;
   float* DZ2 = TDZ2 + net * HP * RL;
@@ -214,13 +221,17 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   const float* W2 = Pm + o_w2;
 
   for (int i = tid; i < CL * S; i += PT) Pm[i] = Ms[i] = Vs[i] = GP[i] = RECV[i] = 0.f;
-  for (int i = tid; i < 2 * xsz; i += PT) XB[i] = 0.f;
-  for (int i = tid; i < 2 * msz; i += PT) MB[i] = 0.f;
+  for (int i = tid; i < 2 * rsz; i += PT) ROWS[i] = 0.f;
   for (int i = tid; i < al(KP * RL) + 8 * HP * RL + 3 * DAP * RL + 32; i += PT) XNo[i] = 0.f;  // XNo .. DVAL contiguous
   if (tid < 64) {
     rstat[tid] = (pd.has_norm && tid < Do) ? g_norm[tid] : 0.f;
     rstat[64 + tid] = (pd.has_norm && tid < Do) ? g_norm[Do + tid] : 1.f;
     LOSS[tid & 31] = 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(&mbar[0], PR);
+    mbar_init(&mbar[1], PR);
+    mbar_fence_init();
   }
   __syncthreads();
   for (int p = tid; p < NP; p += PT) {
@@ -229,19 +240,10 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     Ms[q] = g_m[p];
     Vs[q] = g_v[p];
   }
-  // gather LUT: element e of the minibatch tile -> (row r | source column sc << 8 | dst float offset << 16);
-  // dst is relative to the CTA's shared memory for buffer 0 (buffer 1: + xsz for obs columns, + msz otherwise)
-  const int rwg = Do + da_store + 3;  // gathered columns per row: obs | act | logp_old | adv | ret
-  for (int e = tid; e < PR * rwg; e += PT) {
-    const int r = e / rwg, c = e - r * rwg;
-    const int sc = c < col_logp ? c : (c == col_logp ? col_logp : col_adv + (c - col_logp - 1));
-    const int dst = c < Do ? (int)(XB - smem) + c * PRS + r
-                           : (int)(MB - smem) + (c - Do + (c >= col_logp ? DAP - da_store : 0)) * PRS + r;
-    glut[e] = (unsigned)r | ((unsigned)sc << 8) | ((unsigned)dst << 16);
-  }
   int32_t run_count = pd.has_norm ? *g_norm_count : 0;
 
   const int64_t N = A.n_rows;
+  const int Ni = (int)N;
   const int mb = A.hp.batch_size;
   const int64_t steps_per_epoch = (N + mb - 1) / mb;
   const int64_t n_steps = steps_per_epoch * A.hp.n_epochs;
@@ -249,63 +251,53 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   const int64_t perm_draw0 = state[IMB_ST_PPO_EPOCH];
   double b1pow = pow(0.9, (double)adam_step), b2pow = pow(0.999, (double)adam_step);  // beta^t, kept incrementally
   const int row0 = crank * RL;        // first minibatch row owned by this CTA
-  // own-row GEMM mapping: thread -> column gj = tt % HP and RPT = HP / 16 consecutive rows
-  constexpr int RPT = HP / 16;
-  const int gj = tt % HP, gr0 = (tt / HP) * RPT;
-  const bool jlive = gj < h;
+  // weight-gradient mapping: unit gj, every NWQ-th input
   constexpr int NWQ = 128 / HP;
-  const int wq = tt / HP;  // weight-gradient mapping: unit gj, every NWQ-th input
+  const int gj = tt % HP, wq = tt / HP;
+  const bool jlive = gj < h;
   const int g8 = tid >> 3, gl = tid & 7;   // 8-lane statistic groups
 
-  // minibatch indices of a step (epoch ep, first row start) -> s_idx, computed by threads 192..255
-  const int Ni = (int)N;
-  auto step_indices = [&](int ep, int start) {
+  // Asynchronous row gather of one minibatch (epoch ep, first row start) into buffer `buf`, by threads
+  // 192..255 = one per row: draw the row index, then ONE bulk-async copy of the whole rollout row.
+  auto issue_gather = [&](int ep, int start, int buf) {
     const int t = tid - (PT - PR);
-    if (t >= 0) {
-      const int nbx = min(mb, Ni - start);
-      int idx = 0;
-      if (t < nbx) {
-        if (perm_in) {
-          idx = (int)perm_in[(int64_t)ep * N + start + t];
-        } else {
-          const FeistelKey fk = feistel_key(A.seed, IMB_STREAM_PPO_PERM, (uint64_t)(perm_draw0 + ep), (uint64_t)N);
-          idx = (int)feistel_perm(fk, (uint64_t)(start + t), (uint64_t)N);
-        }
-      }
-      s_idx[t] = idx;
-    }
-  };
-  // asynchronous gather of that step's rows into buffer `buf`, issued by `nthr` threads (t0 = rank among them)
-  auto issue_gather = [&](int start, int buf, int t0, int nthr) {
+    if (t < 0) return;
     const int nbx = min(mb, Ni - start);
-    for (int e = t0; e < PR * rwg; e += nthr) {
-      const unsigned lut = glut[e];
-      const int r = lut & 0xFF, sc = (lut >> 8) & 0xFF;
-      int dst = (int)(lut >> 16);
-      if (buf) dst += (dst < (int)(MB - smem)) ? xsz : msz;
-      if (r < nbx) cp_async4(smem + dst, rollout + (int64_t)s_idx[r] * A.rw + sc);
-      else smem[dst] = 0.f;
+    if (t < nbx) {
+      int64_t idx;
+      if (perm_in) {
+        idx = perm_in[(int64_t)ep * N + start + t];
+      } else {
+        const FeistelKey fk = feistel_key(A.seed, IMB_STREAM_PPO_PERM, (uint64_t)(perm_draw0 + ep), (uint64_t)N);
+        idx = (int64_t)feistel_perm(fk, (uint64_t)(start + t), (uint64_t)N);
+      }
+      // the buffer was last touched with ordinary loads/stores (in-place advantage normalisation): order them
+      // before the async-proxy write
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(&mbar[buf], (uint32_t)rw * 4u);
+      bulk_g2s(ROWS + buf * rsz + t * RS2, rollout + idx * rw, (uint32_t)rw * 4u, &mbar[buf]);
+    } else {
+      mbar_arrive(&mbar[buf]);
     }
-    cp_async_commit();
   };
-  // Statistics of one minibatch (already gathered into buffer `buf`): feature RunningNorm update + advantage
+  // Statistics of one minibatch (step gs2, staged in buffer gs2 & 1): feature RunningNorm update + advantage
   // normalisation over all 64 rows, one 8-lane group per statistic, identically in every CTA; the group of
   // feature k also writes this CTA's own rows of it, normalised, into XNo[k][RL] (lane = row).  All lanes run the
-  // same code (full-mask shuffles); idle groups chew on the advantage row and discard the result.
-  auto minibatch_stats = [&](int buf, int nbx) {
-    float* XNf = XB + buf * xsz;
-    float* MBf = MB + buf * msz;
+  // same code (full-mask shuffles); idle groups chew on the advantage column and discard the result.  The
+  // staged row stride RS2 = 4 (mod 8) makes the 32 lanes of a warp (4 features x 8 rows) hit 32 banks.
+  auto minibatch_stats = [&](int64_t gs2, int nbx) {
+    const int buf = (int)(gs2 & 1);
+    float* R = ROWS + buf * rsz;
     const float inv_nbx = 1.0f / (float)nbx;
-    cp_async_wait_all();
-    __syncthreads();  // the asynchronous gather of this minibatch (issued by six warps) has landed
+    mbar_wait(&mbar[buf], (uint32_t)((gs2 >> 1) & 1));  // all 64 row copies have landed
     for (int task0 = 0; task0 <= Do; task0 += PT / 8) {
       const int task = task0 + g8;
       const bool is_feat = task < Do, is_adv = task == Do;
-      float* x = is_feat ? XNf + task * PRS : MBf + (DAP + 1) * PRS;
+      float* x = R + (is_feat ? task : col_adv);
       float v[8], s = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        v[i] = (gl + 8 * i < nbx) ? x[gl + 8 * i] : 0.f;
+        v[i] = (gl + 8 * i < nbx) ? x[(gl + 8 * i) * RS2] : 0.f;
         s += v[i];
       }
       const float bmean = group8_sum(s) * inv_nbx;
@@ -334,7 +326,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
             rstat[64 + task] = var;
           }
         }
-        XNo[task * RL + gl] = (row0 + gl < nbx) ? (x[row0 + gl] - mean) * istd : 0.f;
+        XNo[task * RL + gl] = (row0 + gl < nbx) ? (x[(row0 + gl) * RS2] - mean) * istd : 0.f;
       } else if (is_adv) {
         float am = 0.f, ais = 1.f;
         if (A.hp.normalize_advantage && nbx > 1) {
@@ -343,15 +335,13 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (gl + 8 * i < nbx) x[gl + 8 * i] = (v[i] - am) * ais;
+          if (gl + 8 * i < nbx) x[(gl + 8 * i) * RS2] = (v[i] - am) * ais;
       }
     }
     if (pd.has_norm) run_count += nbx;
   };
   __syncthreads();
-  step_indices(0, 0);
-  __syncthreads();
-  issue_gather(0, 0, tid, PT);
+  issue_gather(0, 0, 0);
   minibatch_stats(0, min(mb, Ni));
   cluster.sync();
 
@@ -361,7 +351,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   int ep_now = 0, start = 0;  // epoch and first row of the current step
   for (int64_t gs = 0; gs < n_steps; ++gs) {
     const int cur = (int)(gs & 1);
-    const float* MBf = MB + cur * msz;
+    const float* Rc = ROWS + cur * rsz;
     const int nb = min(mb, Ni - start);
     const float inv_nb = 1.0f / (float)nb;
     int ep_next = ep_now, start_next = start + mb;
@@ -376,161 +366,178 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       bc[2 * cur] = (float)((double)A.hp.lr / (1.0 - b1pow));
       bc[2 * cur + 1] = (float)sqrt(1.0 - b2pow);
     }
-    __syncthreads();  // the parameters written by the previous step's Adam are visible
+    __syncthreads();  // the parameters written by the previous step's Adam (and XNo, the statistics) are visible
     PPO_TICK(0);
+    if (gs + 1 < n_steps) issue_gather(ep_next, start_next, cur ^ 1);  // warps 6, 7: prefetch of the next minibatch
 
-    // ---- 4. forward on the own rows: thread = (tower, unit gj, RPT rows) -----------------------------------------------
-    // acc[x] = sum_k Ain[k][gr0 + x] * Wb[k * ks]   (Wb already points at this thread's unit)
-    auto own_gemm = [&](const float* __restrict__ Ain, const float* __restrict__ Wb, int ks, int K, float (&acc)[4]) {
-      acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-#pragma unroll 8
-      for (int k = 0; k < K; ++k) {
-        const float w = Wb[k * ks];
-        const float* ar = Ain + k * RL + gr0;
-        if (RPT == 2) {
-          const float2 a = *reinterpret_cast<const float2*>(ar);
-          acc[0] = fmaf(a.x, w, acc[0]);
-          acc[1] = fmaf(a.y, w, acc[1]);
-        } else {
-          const float4 a = ld4(ar);
-          acc[0] = fmaf(a.x, w, acc[0]);
-          acc[1] = fmaf(a.y, w, acc[1]);
-          acc[2] = fmaf(a.z, w, acc[2]);
-          acc[3] = fmaf(a.w, w, acc[3]);
-        }
-      }
-    };
-    const int gjc = jlive ? gj : 0;  // clamped unit for addressing; results of dead units are forced to 0
-    {
-      float acc[4];
-      own_gemm(XNo, W1 + gjc * ldo, 1, Do, acc);
-      const float b = Pm[o_b1 + gjc];
-#pragma unroll
-      for (int x = 0; x < RPT; ++x) H1[gj * RL + gr0 + x] = jlive ? PPO_TANH(acc[x] + b) : 0.f;
-    }
-    __syncthreads();
-    {
-      float acc[4];
-      own_gemm(H1, W2 + gjc * ldh, 1, h, acc);
-      const float b = Pm[o_b2 + gjc];
-#pragma unroll
-      for (int x = 0; x < RPT; ++x) LAT[gj * RL + gr0 + x] = jlive ? PPO_TANH(acc[x] + b) : 0.f;
-    }
-    __syncthreads();
-    PPO_TICK(3);
-
-    // ---- 5a. head pre-activations: means / logits on the policy tower's threads (a, r, half of the latent),
-    //          values on the value tower's threads (r, 1/16 of the latent) ---------------------------------------------
-    if (net == 0) {
-      const float* Wa = Pm + PL.wa;
-      const int nw = (Da * 16 + 31) & ~31;
-      for (int w = tt; w < nw; w += 128) {
-        const int a = min(w >> 4, Da - 1), r = (w >> 1) & 7, jq = w & 1;
-        float s0 = 0.f, s1 = 0.f;
-        int j = jq;
-        for (; j + 2 < h; j += 4) {
-          s0 = fmaf(Wa[a * h + j], LAT[j * RL + r], s0);
-          s1 = fmaf(Wa[a * h + j + 2], LAT[(j + 2) * RL + r], s1);
-        }
-        for (; j < h; j += 2) s0 = fmaf(Wa[a * h + j], LAT[j * RL + r], s0);
-        float sm = s0 + s1;
-        sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-        if (jq == 0 && (w >> 4) < Da) MEAN[a * RL + r] = Pm[PL.ba + a] + sm;
-      }
-    } else {
-      const float* wv = Pm + PL.wv;
-      const int r = tt >> 4, jq = tt & 15;
-      float sm = 0.f;
-      for (int j = jq; j < h; j += 16) sm = fmaf(wv[j], LAT[j * RL + r], sm);
-      sm += __shfl_xor_sync(0xffffffffu, sm, 1);
-      sm += __shfl_xor_sync(0xffffffffu, sm, 2);
-      sm += __shfl_xor_sync(0xffffffffu, sm, 4);
-      sm += __shfl_xor_sync(0xffffffffu, sm, 8);
-      if (jq == 0) VALS[r] = sm + Pm[PL.bv];
-    }
-    __syncthreads();
-    PPO_TICK(4);
-    // ---- 5b. loss terms and dL/d(head outputs): warp 0 (policy; lanes = (a mod 4, row)) and warp 4 (value);
-    //          the six idle warps draw the NEXT minibatch's indices and issue its asynchronous gather --------------
+    // ---- 1. warp-autonomous chain: forward, loss terms, backward to dL/dz for (tower, rows r0, r0 + 1) ---------
     float l_pg = 0.f, l_v = 0.f, l_ent = 0.f;
-    if (warp == 4) {
-      if (lane < RL) {
-        const int r = lane, gr = row0 + r;
-        const bool live = gr < nb;
-        const float dv = VALS[r] - MBf[(DAP + 2) * PRS + gr];
-        if (live) l_v = dv * dv;
-        DVAL[r] = live ? A.hp.vf_coef * 2.0f * dv * inv_nb : 0.f;
-      }
-    } else if (warp == 0) {
-      const int r = lane & 7, a4 = lane >> 3, gr = row0 + r;
+    {
+      const int j = lane, jc = lane < h ? lane : 0, r0 = 2 * (warp & 3);
+      const bool jl = lane < h;
+      const int rr = lane >> 4, la = lane & 15;  // per-row parts: half-warp rr handles row r0 + rr
+      const int gr = row0 + r0 + rr;
       const bool live = gr < nb;
-      const float adv = MBf[(DAP + 1) * PRS + gr], logp_old = MBf[DAP * PRS + gr];
-      float logp = 0.f, ent = 0.f;
-      if (!pd.discrete) {
-        const float* lstd = Pm + PL.ls;
-        for (int a = a4; a < Da; a += 4) {
-          const float ls = lstd[a], ivar = __expf(-2.0f * ls);
-          const float diff = MBf[a * PRS + gr] - MEAN[a * RL + r];
-          const float d2 = diff * diff * ivar;
-          logp += -0.5f * d2 - ls - 0.9189385332046727f;
-          ent += 1.4189385332046727f + ls;
-          DM[a * RL + r] = diff * ivar;   // d logp / d mean
-          DLS[a * RL + r] = d2 - 1.0f;    // d logp / d log_std
-        }
-      } else {
-        float mx = -INFINITY;
-        for (int a = a4; a < Da; a += 4) mx = fmaxf(mx, MEAN[a * RL + r]);
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
-        float se = 0.f;
-        for (int a = a4; a < Da; a += 4) se += expf(MEAN[a * RL + r] - mx);
-        se += __shfl_xor_sync(0xffffffffu, se, 8);
-        se += __shfl_xor_sync(0xffffffffu, se, 16);
-        const float lse = mx + logf(se);
-        const int act = (int)MBf[gr];
-        for (int a = a4; a < Da; a += 4) {
-          const float lp = MEAN[a * RL + r] - lse;
-          if (a == act) logp = lp;
-          ent -= expf(lp) * lp;
-          DLS[a * RL + r] = lp;  // temporarily: log p_a
+      const float* row = Rc + gr * RS2;
+      // layer 1
+      float a0 = 0.f, a1 = 0.f;
+      {
+        const float* wp = W1 + jc * ldo;
+#pragma unroll 8
+        for (int k = 0; k < Do; ++k) {
+          const float w = wp[k];
+          const float2 x = *reinterpret_cast<const float2*>(XNo + k * RL + r0);
+          a0 = fmaf(x.x, w, a0);
+          a1 = fmaf(x.y, w, a1);
         }
       }
-      logp += __shfl_xor_sync(0xffffffffu, logp, 8);
-      logp += __shfl_xor_sync(0xffffffffu, logp, 16);
-      ent += __shfl_xor_sync(0xffffffffu, ent, 8);
-      ent += __shfl_xor_sync(0xffffffffu, ent, 16);
-      const float ratio = __expf(logp - logp_old);
-      const float lo = 1.0f - A.hp.clip_range, hi = 1.0f + A.hp.clip_range;
-      const float pl1 = adv * ratio, pl2 = adv * fminf(fmaxf(ratio, lo), hi);
-      const bool inside = (ratio >= lo) && (ratio <= hi);
-      float dl_dlogp = (inside || pl1 < pl2) ? -adv * ratio * inv_nb : 0.f;
-      float dent = -A.hp.ent_coef * inv_nb;  // d(ent_coef * ent_loss) / d(entropy)
-      if (live) {
-        if (a4 == 0) {
-          l_pg = -fminf(pl1, pl2);
-          l_ent = -ent;
-        }
-      } else {
-        dl_dlogp = 0.f;
-        dent = 0.f;
-      }
-      if (!pd.discrete) {
-        for (int a = a4; a < Da; a += 4) {
-          DLS[a * RL + r] = dl_dlogp * DLS[a * RL + r] + dent;  // dH/dlog_std = 1
-          DM[a * RL + r] = dl_dlogp * DM[a * RL + r];
-        }
-      } else {
-        const int act = (int)MBf[gr];
-        for (int a = a4; a < Da; a += 4) {
-          const float lp = DLS[a * RL + r], pp = expf(lp);
-          DM[a * RL + r] = dl_dlogp * (((a == act) ? 1.f : 0.f) - pp) + dent * (-pp * (lp + ent));
-          DLS[a * RL + r] = 0.f;
+      float b = Pm[o_b1 + jc];
+      const float h10 = jl ? PPO_TANH(a0 + b) : 0.f, h11 = jl ? PPO_TANH(a1 + b) : 0.f;
+      *reinterpret_cast<float2*>(H1 + j * RL + r0) = make_float2(h10, h11);
+      __syncwarp();
+      // layer 2
+      a0 = a1 = 0.f;
+      {
+        const float* wp = W2 + jc * ldh;
+#pragma unroll 8
+        for (int i = 0; i < h; ++i) {
+          const float w = wp[i];
+          const float2 x = *reinterpret_cast<const float2*>(H1 + i * RL + r0);
+          a0 = fmaf(x.x, w, a0);
+          a1 = fmaf(x.y, w, a1);
         }
       }
-    } else if (gs + 1 < n_steps) {
-      if (warp >= 6) step_indices(ep_next, start_next);
-      asm volatile("bar.sync 1, 192;" ::: "memory");  // the six idle warps only
-      issue_gather(start_next, cur ^ 1, (warp < 4 ? warp - 1 : warp - 2) * 32 + lane, 192);
+      b = Pm[o_b2 + jc];
+      const float lat0 = jl ? PPO_TANH(a0 + b) : 0.f, lat1 = jl ? PPO_TANH(a1 + b) : 0.f;
+      *reinterpret_cast<float2*>(LAT + j * RL + r0) = make_float2(lat0, lat1);
+      // heads + loss terms; dl0/dl1 = dL/dlatent of this unit for the two rows
+      // (reductions over the units: lanes < 16 end up with row r0's sum, lanes >= 16 with row r0 + 1's)
+      float dl0 = 0.f, dl1 = 0.f;
+      auto half_reduce = [&](float keep, float send) {
+        keep += __shfl_xor_sync(0xffffffffu, send, 16);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 8);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 4);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 2);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 1);
+        return keep;
+      };
+      auto half16_sum = [&](float v) {
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        return v;
+      };
+      if (net == 1) {
+        const float wvj = jl ? Pm[PL.wv + j] : 0.f;
+        const float p0 = lat0 * wvj, p1 = lat1 * wvj;
+        const float val = half_reduce(rr ? p1 : p0, rr ? p0 : p1) + Pm[PL.bv];
+        const float dv = val - row[col_ret];
+        const float dval = live ? A.hp.vf_coef * 2.0f * dv * inv_nb : 0.f;
+        if (la == 0) {
+          if (live) l_v = dv * dv;
+          DVAL[r0 + rr] = dval;
+        }
+        const float other = __shfl_xor_sync(0xffffffffu, dval, 16);
+        dl0 = (rr ? other : dval) * wvj;
+        dl1 = (rr ? dval : other) * wvj;
+      } else {
+        const float* Wa = Pm + PL.wa;
+#pragma unroll 2
+        for (int a = 0; a < Da; ++a) {
+          const float waj = jl ? Wa[a * h + j] : 0.f;
+          const float p0 = lat0 * waj, p1 = lat1 * waj;
+          const float m = half_reduce(rr ? p1 : p0, rr ? p0 : p1);
+          if (la == 0) MEAN[a * RL + r0 + rr] = m + Pm[PL.ba + a];
+        }
+        __syncwarp();
+        const float adv = row[col_adv], logp_old = row[col_logp];
+        float logp = 0.f, ent = 0.f;
+        int act = 0;
+        if (!pd.discrete) {
+          const float* lstd = Pm + PL.ls;
+          for (int a = la; a < Da; a += 16) {
+            const float ls = lstd[a], ivar = __expf(-2.0f * ls);
+            const float diff = row[Do + a] - MEAN[a * RL + r0 + rr];
+            const float d2 = diff * diff * ivar;
+            logp += -0.5f * d2 - ls - 0.9189385332046727f;
+            ent += 1.4189385332046727f + ls;
+            DM[a * RL + r0 + rr] = diff * ivar;   // d logp / d mean
+            DLS[a * RL + r0 + rr] = d2 - 1.0f;    // d logp / d log_std
+          }
+        } else {
+          float mx = -INFINITY;
+          for (int a = la; a < Da; a += 16) mx = fmaxf(mx, MEAN[a * RL + r0 + rr]);
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          float se = 0.f;
+          for (int a = la; a < Da; a += 16) se += expf(MEAN[a * RL + r0 + rr] - mx);
+          const float lse = mx + logf(half16_sum(se));
+          act = (int)row[Do];
+          for (int a = la; a < Da; a += 16) {
+            const float lp = MEAN[a * RL + r0 + rr] - lse;
+            if (a == act) logp = lp;
+            ent -= expf(lp) * lp;
+            DLS[a * RL + r0 + rr] = lp;  // temporarily: log p_a
+          }
+        }
+        logp = half16_sum(logp);
+        ent = half16_sum(ent);
+        const float ratio = __expf(logp - logp_old);
+        const float lo = 1.0f - A.hp.clip_range, hi = 1.0f + A.hp.clip_range;
+        const float pl1 = adv * ratio, pl2 = adv * fminf(fmaxf(ratio, lo), hi);
+        const bool inside = (ratio >= lo) && (ratio <= hi);
+        float dl_dlogp = (inside || pl1 < pl2) ? -adv * ratio * inv_nb : 0.f;
+        float dent = -A.hp.ent_coef * inv_nb;  // d(ent_coef * ent_loss) / d(entropy)
+        if (live) {
+          if (la == 0) {
+            l_pg = -fminf(pl1, pl2);
+            l_ent = -ent;
+          }
+        } else {
+          dl_dlogp = 0.f;
+          dent = 0.f;
+        }
+        if (!pd.discrete) {
+          for (int a = la; a < Da; a += 16) {
+            DLS[a * RL + r0 + rr] = dl_dlogp * DLS[a * RL + r0 + rr] + dent;  // dH/dlog_std = 1
+            DM[a * RL + r0 + rr] = dl_dlogp * DM[a * RL + r0 + rr];
+          }
+        } else {
+          for (int a = la; a < Da; a += 16) {
+            const float lp = DLS[a * RL + r0 + rr], pp = expf(lp);
+            DM[a * RL + r0 + rr] = dl_dlogp * (((a == act) ? 1.f : 0.f) - pp) + dent * (-pp * (lp + ent));
+            DLS[a * RL + r0 + rr] = 0.f;
+          }
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int a = 0; a < Da; ++a) {
+          const float waj = Wa[a * h + jc];
+          const float2 d = *reinterpret_cast<const float2*>(DM + a * RL + r0);
+          dl0 = fmaf(d.x, waj, dl0);
+          dl1 = fmaf(d.y, waj, dl1);
+        }
+      }
+      // dL/dz2, backward through layer 2 (lane = input unit i: dH1[i] = sum_j DZ2[j] W2[j][i]), dL/dz1
+      *reinterpret_cast<float2*>(DZ2 + j * RL + r0) =
+          make_float2(jl ? dl0 * (1.0f - lat0 * lat0) : 0.f, jl ? dl1 * (1.0f - lat1 * lat1) : 0.f);
+      __syncwarp();
+      a0 = a1 = 0.f;
+      {
+        const float* wp = W2 + jc;
+#pragma unroll 8
+        for (int jj = 0; jj < h; ++jj) {
+          const float w = wp[jj * ldh];
+          const float2 d = *reinterpret_cast<const float2*>(DZ2 + jj * RL + r0);
+          a0 = fmaf(d.x, w, a0);
+          a1 = fmaf(d.y, w, a1);
+        }
+      }
+      *reinterpret_cast<float2*>(DZ1 + j * RL + r0) =
+          make_float2(jl ? a0 * (1.f - h10 * h10) : 0.f, jl ? a1 * (1.f - h11 * h11) : 0.f);
     }
     // partial loss sums of this CTA -> CTA 0 (distributed shared memory)
     if (loss_log) {  // (uniform) loss terms are only reduced when the caller asked for the log
@@ -545,44 +552,20 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       }
     }
     __syncthreads();
-    PPO_TICK(13);
-    // ---- 6. dL/dz2 = (dL/dlatent) * (1 - lat^2): thread = (tower, unit gj, RPT rows) ---------------------------------
-#pragma unroll
-    for (int x = 0; x < RPT; ++x) {
-      const int r = gr0 + x;
-      float dl = 0.f;
-      if (jlive) {
-        if (net == 1) {
-          dl = DVAL[r] * Pm[PL.wv + gj];
-        } else {
-          const float* Wa = Pm + PL.wa;
-          for (int a = 0; a < Da; ++a) dl = fmaf(DM[a * RL + r], Wa[a * h + gj], dl);
-        }
-      }
-      const float l = LAT[gj * RL + r];
-      DZ2[gj * RL + r] = dl * (1.0f - l * l);
-    }
-    __syncthreads();
-    PPO_TICK(5);
-    // ---- 7. backward through layer 2: dH1[i] = sum_j DZ2[j] W2[j][i]  (k = j, this thread's unit = i); in the same
-    //         phase the partial gradients that do not need its result: layer 2, heads ------------------------------------
-    // Partial gradients (own RL rows) go to GP (P-layout, local shared memory): thread = (tower, unit gj, every
-    // NWQ-th input); the unit's dL/dz rows live in registers, the input rows are warp-uniform broadcasts, the
-    // scattered GP stores have odd lane strides (conflict free).
-    {
-      float acc[4];
-      own_gemm(DZ2, W2 + gjc, ldh, h, acc);
-#pragma unroll
-      for (int x = 0; x < RPT; ++x) {
-        const float hh = H1[gj * RL + gr0 + x];
-        DZ1[gj * RL + gr0 + x] = jlive ? acc[x] * (1.f - hh * hh) : 0.f;
-      }
-    }
+    PPO_TICK(3);
+    // ---- 2. partial gradients (own RL rows) -> GP (P-layout, local shared memory): thread = (tower, unit gj,
+    //         every NWQ-th input); the unit's dL/dz rows live in registers, the input rows are warp-uniform
+    //         broadcasts, the scattered GP stores have odd lane strides (conflict free) -------------------------------
     if (jlive) {
       float dz[8];
       load8(dz, DZ2 + gj * RL);
+#pragma unroll 4
       for (int i = wq; i < h; i += NWQ) GP[o_w2 + gj * ldh + i] = dot8r(dz, H1 + i * RL);
       if (wq == 0) GP[o_b2 + gj] = sum8(dz);
+      load8(dz, DZ1 + gj * RL);
+#pragma unroll 4
+      for (int k = wq; k < Do; k += NWQ) GP[o_w1 + gj * ldo + k] = dot8r(dz, XNo + k * RL);
+      if (wq == NWQ - 1) GP[o_b1 + gj] = sum8(dz);
       load8(dz, LAT + gj * RL);
       if (net == 0) {
         for (int a = wq; a < Da; a += NWQ) GP[PL.wa + a * h + gj] = dot8r(dz, DM + a * RL);
@@ -608,17 +591,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       }
     }
     __syncthreads();
-    PPO_TICK(6);
-    // ---- 8. partial gradients of layer 1 ------------------------------------------------------------------------------------
-    if (jlive) {
-      float dz[8];
-      load8(dz, DZ1 + gj * RL);
-      for (int k = wq; k < Do; k += NWQ) GP[o_w1 + gj * ldo + k] = dot8r(dz, XNo + k * RL);
-      if (wq == NWQ - 1) GP[o_b1 + gj] = sum8(dz);
-    }
-    __syncthreads();
     PPO_TICK(7);
-    // ---- 9. push the partials to the slice owners: RECV[this CTA][i], one 16-byte DSMEM store per quad ----------
+    // ---- 3. push the partials to the slice owners: RECV[this CTA][i], one 16-byte DSMEM store per quad ----------
     // CTA c starts with the quads owned by CTA c+1, so at any time the 8 senders target 8 different receivers
     for (int q = tid; q < CL * S / 4; q += PT) {
       int qq = q + ((crank + 1) & (CL - 1)) * (S / 4);
@@ -630,12 +604,12 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     // (a) cluster barrier, split: in its shadow the NEXT step's minibatch statistics and own-row tile (they do
     //     not depend on the parameters); after the wait all partial gradients / losses have landed at their owners
     cluster_arrive();
-    if (gs + 1 < n_steps) minibatch_stats(cur ^ 1, min(mb, Ni - start_next));
+    if (gs + 1 < n_steps) minibatch_stats(gs + 1, min(mb, Ni - start_next));
     PPO_TICK(1);
     cluster_wait();
     PPO_TICK(9);
 
-    // ---- 10. slice owners: sum the CL partials in fixed order, all-gather the summed slice --------------------------
+    // ---- 4. slice owners: sum the CL partials in fixed order, all-gather the summed slice --------------------------
     for (int i0 = 4 * tid; i0 < S; i0 += 4 * PT) {
       float4 g = ld4(RECV + i0);
 #pragma unroll
@@ -664,7 +638,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     cluster.sync();  // (b) every CTA holds the full summed gradient in GP
     PPO_TICK(11);
 
-    // ---- 11. clip_grad_norm_ + Adam on the full vector, identically in every CTA ------------------------------------------
+    // ---- 5. clip_grad_norm_ + Adam on the full vector, identically in every CTA ------------------------------------------
     float ss = 0.f;
     for (int i0 = 4 * tid; i0 < CL * S; i0 += 4 * PT) {
       const float4 g = ld4(GP + i0);
@@ -820,10 +794,9 @@ static size_t ppo_smem_floats(const PpoArgs& A) {
   const int DAP = (Da + 3) / 4 * 4;
   size_t o = 0;
   o += 5 * (size_t)al(CL * S) + 32;
-  o += 2 * (size_t)al(KP * PRS) + 2 * (size_t)al((DAP + 3) * PRS);
+  o += 2 * (size_t)al(PR * A.RS2);
   o += al(KP * RL) + (size_t)8 * HP * RL + (size_t)3 * DAP * RL + 32;
-  o += al(3 * 64 + 4) + al(PR);
-  o += al(PR * (A.pol.d_obs + (A.pol.discrete ? 1 : Da) + 3));
+  o += al(2 * 64 + 4);
   return o;
 }
 
@@ -835,9 +808,10 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
   A.HP = 32;
   A.KP = A.pol.d_obs <= 32 ? 32 : 64;
   A.S = ((make_play(A.pol).total + CL - 1) / CL + 3) / 4 * 4;
+  IMB_REQUIRE(A.rw % 4 == 0, "rollout row width must be a multiple of 4 floats (bulk row copies)");
+  A.RS2 = ((A.rw + 4) % 8 == 4) ? A.rw + 4 : A.rw + 8;
   const size_t fl = ppo_smem_floats(A);
   IMB_REQUIRE(fl * 4 <= IMB_SMEM_MAX, "PPO kernel needs %zu B of shared memory per CTA", fl * 4);
-  IMB_REQUIRE(fl < 65536, "PPO kernel: shared-memory float offsets must fit 16 bits (policy too large)");
   static size_t attr_bytes = 0;
   if (fl * 4 > attr_bytes) {
     cudaError_t e = cudaFuncSetAttribute(k_ppo_update<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fl * 4));

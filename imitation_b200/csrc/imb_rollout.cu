@@ -2,7 +2,9 @@
 #include "imb_rollout_impl.cuh"
 
 extern "C" int imb_rollout_row_width(const imb_policy_desc* pol) {
-  return pol->d_obs + (pol->discrete ? 1 : pol->d_act) + 5;
+  // padded to a multiple of 4 floats: rows are 16-byte aligned, so the PPO update can stage a minibatch row
+  // with one bulk-async copy
+  return (pol->d_obs + (pol->discrete ? 1 : pol->d_act) + 5 + 3) / 4 * 4;
 }
 
 extern "C" int imb_rollout(const imb_env_desc* env, const float* env_params, float* env_obs,

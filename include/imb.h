@@ -223,7 +223,8 @@ int imb_rollout(const imb_env_desc* env, const float* env_params, float* env_obs
                 int reward_mode, const imb_ppo_hparams* hp, int64_t n_envs, int64_t n_steps,
                 float* rollout, float* ring, int64_t ring_capacity, float* flat_out, float* aux,
                 const float* noise, int flags, const int64_t* state, void* stream);
-/* floats per rollout row: d_obs + (discrete ? 1 : d_act) + 5 (logp, value, reward, adv, ret);
+/* floats per rollout row: d_obs + (discrete ? 1 : d_act) + 5 (logp, value, reward, adv, ret), padded
+ * to a multiple of 4 (16-byte aligned rows: imb_ppo_update stages each minibatch row with one bulk copy);
  * aux needs 2*E + 2*E*T floats (V(last obs), last done, per-step time-limit bootstrap,
  * per-step ground-truth env reward). */
 int imb_rollout_row_width(const imb_policy_desc* pol);

@@ -11,9 +11,9 @@ import torch as th
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from imitation_b200 import _desc, _lib  # noqa: E402
 
-NAMES = ["top barrier", "next-step stats (in shadow of sync a)", "-", "F1+F2", "heads (means, values)", "dZ2",
-         "B2 + wgrad L2/heads", "wgrad L1", "push partials", "sync a wait", "slice sum+allgather", "sync b",
-         "ssq+clip+adam", "loss + next-batch issue"]
+NAMES = ["top barrier", "next-step stats (shadow of barrier a)", "-", "warp chain fwd/loss/bwd", "-", "-", "-",
+         "weight gradients -> GP", "push partials", "barrier a wait", "slice sum + all-gather", "barrier b",
+         "ssq + clip + Adam", "-"]
 pd = _desc.policy_desc(17, 6, False, 32, True)
 N = 4096
 rw = _lib.rollout_row_width(pd)
