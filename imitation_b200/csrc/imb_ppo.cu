@@ -19,6 +19,11 @@
 #ifdef IMB_PPO_TIMING
 // phase timing for profiles/: CTA 0 / thread 0 accumulates clock64() deltas per phase of the optimiser step
 __device__ long long g_ppo_clk[24];
+__device__ long long g_ppo_wclk[64];  // [slot][warp]: cycles since the top barrier at points of the warp chain (CTA 0)
+#define PPO_WCLK(slot)                                                                 \
+  do {                                                                                 \
+    if (crank == 0 && lane == 0) g_ppo_wclk[(slot) * 8 + warp] += clock64() - wclk0;  \
+  } while (0)
 #define PPO_TICK(i)                                  \
   do {                                               \
     if (tid == 0) {                                  \
@@ -29,6 +34,7 @@ __device__ long long g_ppo_clk[24];
   } while (0)
 #else
 #define PPO_TICK(i) do {} while (0)
+#define PPO_WCLK(slot) do {} while (0)
 #endif
 #ifndef PPO_TANH
 #define PPO_TANH(x) tanh_fast(x)
@@ -72,7 +78,7 @@ __host__ __device__ inline PLay make_play(const imb_policy_desc& pd) {
     L.w2[t] = o; o += h * L.ldh;
     L.b2[t] = o; o += h;
   }
-  L.wa = o; o += Da * h;
+  L.wa = o; o += Da * L.ldh;
   L.ba = o; o += Da;
   L.wv = o; o += h;
   L.bv = o; o += 1;
@@ -92,7 +98,7 @@ __device__ inline int flat_to_play(const imb_policy_desc& pd, const PLay& L, int
   if (in(pd.off_vf_b1, h)) return L.b1[1] + p - pd.off_vf_b1;
   if (in(pd.off_pi_b2, h)) return L.b2[0] + p - pd.off_pi_b2;
   if (in(pd.off_vf_b2, h)) return L.b2[1] + p - pd.off_vf_b2;
-  if (in(pd.off_act_w, Da * h)) return L.wa + p - pd.off_act_w;
+  if (in(pd.off_act_w, Da * h)) { const int i = p - pd.off_act_w; return L.wa + (i / h) * L.ldh + i % h; }
   if (in(pd.off_act_b, Da)) return L.ba + p - pd.off_act_b;
   if (in(pd.off_val_w, h)) return L.wv + p - pd.off_val_w;
   if (p == pd.off_val_b) return L.bv;
@@ -229,8 +235,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     LOSS[tid & 31] = 0.f;
   }
   if (tid == 0) {
-    mbar_init(&mbar[0], PR);
-    mbar_init(&mbar[1], PR);
+    mbar_init(&mbar[0], 128);
+    mbar_init(&mbar[1], 128);
     mbar_fence_init();
   }
   __syncthreads();
@@ -257,28 +263,30 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   const bool jlive = gj < h;
   const int g8 = tid >> 3, gl = tid & 7;   // 8-lane statistic groups
 
-  // Asynchronous row gather of one minibatch (epoch ep, first row start) into buffer `buf`, by threads
-  // 192..255 = one per row: draw the row index, then ONE bulk-async copy of the whole rollout row.
+  // Asynchronous row gather of one minibatch (epoch ep, first row start) into buffer `buf` by the value tower's
+  // threads (their chain is the shorter one): two threads per row draw the row index and copy half of the
+  // 16-byte aligned rollout row each with 16-byte cp.async (LDGSTS); completion is tracked by the buffer's
+  // mbarrier (one deferred arrival per thread).  (One bulk-async copy per row and lane was tried first: the
+  // 32 per-lane UBLKCP issues serialise, ~2500 cycles per warp.)
   auto issue_gather = [&](int ep, int start, int buf) {
-    const int t = tid - (PT - PR);
+    const int t = tid - 128;
     if (t < 0) return;
+    const int r = t >> 1, half = t & 1;
     const int nbx = min(mb, Ni - start);
-    if (t < nbx) {
+    if (r < nbx) {
       int64_t idx;
       if (perm_in) {
-        idx = perm_in[(int64_t)ep * N + start + t];
+        idx = perm_in[(int64_t)ep * N + start + r];
       } else {
         const FeistelKey fk = feistel_key(A.seed, IMB_STREAM_PPO_PERM, (uint64_t)(perm_draw0 + ep), (uint64_t)N);
-        idx = (int64_t)feistel_perm(fk, (uint64_t)(start + t), (uint64_t)N);
+        idx = (int64_t)feistel_perm(fk, (uint64_t)(start + r), (uint64_t)N);
       }
-      // the buffer was last touched with ordinary loads/stores (in-place advantage normalisation): order them
-      // before the async-proxy write
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      mbar_expect_tx(&mbar[buf], (uint32_t)rw * 4u);
-      bulk_g2s(ROWS + buf * rsz + t * RS2, rollout + idx * rw, (uint32_t)rw * 4u, &mbar[buf]);
-    } else {
-      mbar_arrive(&mbar[buf]);
+      const float* src = rollout + idx * rw;
+      float* dst = ROWS + buf * rsz + r * RS2;
+      const int nq = rw >> 2, q0 = half ? (nq + 1) >> 1 : 0, q1 = half ? nq : (nq + 1) >> 1;
+      for (int q = q0; q < q1; ++q) cp_async16(dst + 4 * q, src + 4 * q);
     }
+    cp_async_mbar_arrive(&mbar[buf]);
   };
   // Statistics of one minibatch (step gs2, staged in buffer gs2 & 1): feature RunningNorm update + advantage
   // normalisation over all 64 rows, one 8-lane group per statistic, identically in every CTA; the group of
@@ -368,7 +376,11 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     }
     __syncthreads();  // the parameters written by the previous step's Adam (and XNo, the statistics) are visible
     PPO_TICK(0);
+#ifdef IMB_PPO_TIMING
+    const long long wclk0 = clock64();
+#endif
     if (gs + 1 < n_steps) issue_gather(ep_next, start_next, cur ^ 1);  // warps 6, 7: prefetch of the next minibatch
+    PPO_WCLK(1);
 
     // ---- 1. warp-autonomous chain: forward, loss terms, backward to dL/dz for (tower, rows r0, r0 + 1) ---------
     float l_pg = 0.f, l_v = 0.f, l_ent = 0.f;
@@ -395,6 +407,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       const float h10 = jl ? PPO_TANH(a0 + b) : 0.f, h11 = jl ? PPO_TANH(a1 + b) : 0.f;
       *reinterpret_cast<float2*>(H1 + j * RL + r0) = make_float2(h10, h11);
       __syncwarp();
+      PPO_WCLK(3);
       // layer 2
       a0 = a1 = 0.f;
       {
@@ -410,6 +423,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       b = Pm[o_b2 + jc];
       const float lat0 = jl ? PPO_TANH(a0 + b) : 0.f, lat1 = jl ? PPO_TANH(a1 + b) : 0.f;
       *reinterpret_cast<float2*>(LAT + j * RL + r0) = make_float2(lat0, lat1);
+      PPO_WCLK(4);
       // heads + loss terms; dl0/dl1 = dL/dlatent of this unit for the two rows
       // (reductions over the units: lanes < 16 end up with row r0's sum, lanes >= 16 with row r0 + 1's)
       float dl0 = 0.f, dl1 = 0.f;
@@ -443,14 +457,28 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
         dl1 = (rr ? dval : other) * wvj;
       } else {
         const float* Wa = Pm + PL.wa;
-#pragma unroll 2
-        for (int a = 0; a < Da; ++a) {
-          const float waj = jl ? Wa[a * h + j] : 0.f;
-          const float p0 = lat0 * waj, p1 = lat1 * waj;
-          const float m = half_reduce(rr ? p1 : p0, rr ? p0 : p1);
-          if (la == 0) MEAN[a * RL + r0 + rr] = m + Pm[PL.ba + a];
+        // action means / logits from the latent tile in shared memory: lane = (action a0 + o / 2, row o % 2, half of
+        // the units); 16-term dot + one shuffle (Wa rows have the odd stride ldh: no bank conflicts)
+        __syncwarp();
+        {
+          const int o16 = lane & 15, part = lane >> 4, rrr = o16 & 1;
+          for (int a0 = 0; a0 < Da; a0 += 8) {
+            const int a = a0 + (o16 >> 1), ac = a < Da ? a : 0;
+            const float* wr = Wa + ac * ldh + part * 16;
+            const float* lr = LAT + part * 16 * RL + r0 + rrr;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 2) {
+              s0 = fmaf(wr[jj], lr[jj * RL], s0);
+              s1 = fmaf(wr[jj + 1], lr[(jj + 1) * RL], s1);
+            }
+            float m = s0 + s1;
+            m += __shfl_xor_sync(0xffffffffu, m, 16);
+            if (part == 0 && a < Da) MEAN[a * RL + r0 + rrr] = m + Pm[PL.ba + a];
+          }
         }
         __syncwarp();
+        PPO_WCLK(5);
         const float adv = row[col_adv], logp_old = row[col_logp];
         float logp = 0.f, ent = 0.f;
         int act = 0;
@@ -484,7 +512,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
           }
         }
         logp = half16_sum(logp);
-        ent = half16_sum(ent);
+        if (pd.discrete || loss_log) ent = half16_sum(ent);  // (Gaussian: the entropy only feeds the loss log)
         const float ratio = __expf(logp - logp_old);
         const float lo = 1.0f - A.hp.clip_range, hi = 1.0f + A.hp.clip_range;
         const float pl1 = adv * ratio, pl2 = adv * fminf(fmaxf(ratio, lo), hi);
@@ -515,12 +543,13 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
         __syncwarp();
 #pragma unroll 4
         for (int a = 0; a < Da; ++a) {
-          const float waj = Wa[a * h + jc];
+          const float waj = Wa[a * ldh + jc];
           const float2 d = *reinterpret_cast<const float2*>(DM + a * RL + r0);
           dl0 = fmaf(d.x, waj, dl0);
           dl1 = fmaf(d.y, waj, dl1);
         }
       }
+      PPO_WCLK(2);
       // dL/dz2, backward through layer 2 (lane = input unit i: dH1[i] = sum_j DZ2[j] W2[j][i]), dL/dz1
       *reinterpret_cast<float2*>(DZ2 + j * RL + r0) =
           make_float2(jl ? dl0 * (1.0f - lat0 * lat0) : 0.f, jl ? dl1 * (1.0f - lat1 * lat1) : 0.f);
@@ -539,6 +568,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       *reinterpret_cast<float2*>(DZ1 + j * RL + r0) =
           make_float2(jl ? a0 * (1.f - h10 * h10) : 0.f, jl ? a1 * (1.f - h11 * h11) : 0.f);
     }
+    PPO_WCLK(0);
     // partial loss sums of this CTA -> CTA 0 (distributed shared memory)
     if (loss_log) {  // (uniform) loss terms are only reduced when the caller asked for the log
       const float s_pg = block_sum(l_pg, red);
@@ -568,7 +598,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       if (wq == NWQ - 1) GP[o_b1 + gj] = sum8(dz);
       load8(dz, LAT + gj * RL);
       if (net == 0) {
-        for (int a = wq; a < Da; a += NWQ) GP[PL.wa + a * h + gj] = dot8r(dz, DM + a * RL);
+        for (int a = wq; a < Da; a += NWQ) GP[PL.wa + a * ldh + gj] = dot8r(dz, DM + a * RL);
       } else if (wq == 0) {
         GP[PL.wv + gj] = dot8r(dz, DVAL);
       }
@@ -601,11 +631,12 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       st4(cluster.map_shared_rank(RECV, owner) + crank * S + (p0 - owner * S), ld4(GP + p0));
     }
     PPO_TICK(8);
-    // (a) cluster barrier, split: in its shadow the NEXT step's minibatch statistics and own-row tile (they do
-    //     not depend on the parameters); after the wait all partial gradients / losses have landed at their owners
-    cluster_arrive();
+    // (a) cluster barrier; before it the NEXT step's minibatch statistics and own-row tile (they do not depend on
+    //     the parameters); after the wait all partial gradients / losses have landed at their owners
+    // (the remote stores above drain while the statistics run, so the release at the arrive is cheap)
     if (gs + 1 < n_steps) minibatch_stats(gs + 1, min(mb, Ni - start_next));
     PPO_TICK(1);
+    cluster_arrive();
     cluster_wait();
     PPO_TICK(9);
 
@@ -895,5 +926,10 @@ extern "C" int imb_policy_logp(const imb_policy_desc* pol, const float* pol_para
 #ifdef IMB_PPO_TIMING
 extern "C" __attribute__((visibility("default"))) int imb_debug_ppo_clocks(long long* out) {
   return (int)cudaMemcpyFromSymbol(out, g_ppo_clk, 16 * sizeof(long long));
+}
+extern "C" __attribute__((visibility("default"))) int imb_debug_ppo_warp_clocks(long long* out, int reset) {
+  static const long long zero[64] = {0};
+  if (reset) return (int)cudaMemcpyToSymbol(g_ppo_wclk, zero, sizeof(zero));
+  return (int)cudaMemcpyFromSymbol(out, g_ppo_wclk, 64 * sizeof(long long));
 }
 #endif

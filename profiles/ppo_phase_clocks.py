@@ -29,6 +29,7 @@ hp = _lib.PpoHparams(gamma=0.95, gae_lambda=0.95, clip_range=0.1, ent_coef=4e-6,
 for _ in range(3):
     _lib.ppo_update(pd, P, PN, PC, M, V, tbl, N, hp, None, 0, None, st)
 th.cuda.synchronize()
+_lib.lib().imb_debug_ppo_warp_clocks(None, 1)
 e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
 e0.record()
 _lib.ppo_update(pd, P, PN, PC, M, V, tbl, N, hp, None, 0, None, st)
@@ -43,3 +44,10 @@ tot = sum(out[:14])
 for n, c in zip(NAMES, out):
     print(f"{n:<18s} {c / steps:9.0f} cycles/step  {100.0 * c / tot:5.1f} %")
 print(f"{'total':<18s} {tot / steps:9.0f} cycles/step")
+
+w = (ctypes.c_longlong * 64)()
+assert _lib.lib().imb_debug_ppo_warp_clocks(w, 0) == 0
+print("per-warp cycles/step since the top barrier (CTA 0; warps 0-3 policy tower, 4-7 value tower):")
+for slot, name in ((1, "after prefetch issue"), (3, "after layer 1"), (4, "after layer 2"), (5, "after means (policy)"),
+                   (2, "after heads/loss"), (0, "chain end")):
+    print(f"  {name:<22s}", [round(w[slot * 8 + i] / steps) for i in range(8)])
