@@ -215,7 +215,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-rounds", type=int, default=12, help="rounds of the CPU baseline sample (rank 0, N=1)")
-    ap.add_argument("--host-threads", type=int, default=0, help="torch intra-op threads for host-side ops (0: default)")
+    ap.add_argument("--host-threads", type=int, default=4,
+                    help="torch intra-op threads for the host side of the loop (all its CPU ops are tiny; the default pool of one thread per core makes the DataLoader-style shuffle ~30x slower); 0: leave torch default")
     ap.add_argument("--profile-host", action="store_true", help="cProfile the e2e loop (host overhead hunt)")
     args = ap.parse_args()
     cfg = CFG
