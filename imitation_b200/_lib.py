@@ -63,6 +63,16 @@ class PpoHparams(C.Structure):
                 ("n_epochs", C.c_int32), ("batch_size", C.c_int32), ("normalize_advantage", C.c_int32)]
 
 
+SYNC_MAX_AVG, SYNC_MAX_NORM = 8, 4
+
+
+class SyncDesc(C.Structure):
+    _fields_ = [("n_avg", C.c_int32), ("n_norm", C.c_int32), ("avg", C.c_void_p * SYNC_MAX_AVG),
+                ("avg_n", C.c_int64 * SYNC_MAX_AVG), ("mean", C.c_void_p * SYNC_MAX_NORM),
+                ("var", C.c_void_p * SYNC_MAX_NORM), ("count", C.c_void_p * SYNC_MAX_NORM),
+                ("k", C.c_int32 * SYNC_MAX_NORM)]
+
+
 _lib: Optional[C.CDLL] = None
 
 # every symbol include/imb.h declares (tests check the library exports each of them)
@@ -71,6 +81,7 @@ SYMBOLS = [
     "imb_disc_reduce", "imb_disc_adam", "imb_reward_forward", "imb_reward_norm_scan", "imb_table_store",
     "imb_ring_advance", "imb_sample_indices", "imb_gather_rows", "imb_rollout", "imb_rollout_row_width", "imb_gae",
     "imb_rollout_advance", "imb_env_reset", "imb_ppo_update", "imb_policy_logp", "imb_state_init",
+    "imb_sync_buffer_doubles", "imb_sync_snapshot", "imb_sync_pack", "imb_sync_unpack",
 ]
 
 
@@ -84,6 +95,7 @@ def lib() -> C.CDLL:
         _lib = C.CDLL(LIB_PATH)
         _lib.imb_last_error.restype = C.c_char_p
         _lib.imb_disc_workspace_floats.restype = C.c_int64
+        _lib.imb_sync_buffer_doubles.restype = C.c_int64
         for name in SYMBOLS:
             getattr(_lib, name)  # AttributeError if the .so is stale
     return _lib
@@ -124,6 +136,39 @@ def _stream():
 
 def disc_workspace_floats(d: DiscDesc) -> int:
     return int(lib().imb_disc_workspace_floats(C.byref(d)))
+
+
+def sync_desc(averaged, norms) -> SyncDesc:
+    """averaged: fp32 CUDA tensors; norms: (mean[k], var[k], int32 count) tensor triples (views are fine as
+    long as they are contiguous)."""
+    if len(averaged) > SYNC_MAX_AVG or len(norms) > SYNC_MAX_NORM:
+        raise ImbError("too many tensors for one imb_sync_desc")
+    d = SyncDesc()
+    d.n_avg, d.n_norm = len(averaged), len(norms)
+    for i, t in enumerate(averaged):
+        d.avg[i], d.avg_n[i] = _p(t, th.float32).value, t.numel()
+    for i, (m, v, c) in enumerate(norms):
+        d.mean[i], d.var[i], d.count[i] = _p(m, th.float32).value, _p(v, th.float32).value, _p(c, th.int32).value
+        d.k[i] = m.numel()
+    return d
+
+
+def sync_buffer_doubles(d: SyncDesc) -> int:
+    return int(lib().imb_sync_buffer_doubles(C.byref(d)))
+
+
+def sync_snapshot(d: SyncDesc, start):
+    _check(lib().imb_sync_snapshot(C.byref(d), _p(start, th.float64), _stream()), "imb_sync_snapshot",
+           1 if d.n_norm else 0)
+
+
+def sync_pack(d: SyncDesc, buf):
+    _check(lib().imb_sync_pack(C.byref(d), _p(buf, th.float64), _stream()), "imb_sync_pack")
+
+
+def sync_unpack(d: SyncDesc, buf, start, world: int):
+    _check(lib().imb_sync_unpack(C.byref(d), _p(buf, th.float64), _p(start, th.float64), C.c_int32(world), _stream()),
+           "imb_sync_unpack")
 
 
 def state_init(state):

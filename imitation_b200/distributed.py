@@ -79,8 +79,20 @@ class RoundSync:
         # float64 staging keeps the sufficient statistics exact; payload is tiny (latency-bound)
         self.buf = th.zeros(n_avg + n_norm, dtype=th.float64, device=dev)
         self.n_avg = n_avg
+        # CUDA tensors: pack / snapshot / unpack are one kernel each (csrc/imb_sync.cu) instead of ~60 tiny torch
+        # ops and a host sync per round; CPU tensors (gloo host-logic tests) keep the torch formulation below.
+        self._fused = None
+        if dev.type == "cuda":
+            from . import _lib
+            self._fused = _lib.sync_desc(self.averaged, [(n.mean, n.var, n.count) for n in self.norms])
+            assert _lib.sync_buffer_doubles(self._fused) == self.buf.numel()
+            self._start = th.zeros(max(n_norm, 1), dtype=th.float64, device=dev)
 
     def begin_round(self) -> None:
+        if self._fused is not None:
+            from . import _lib
+            _lib.sync_snapshot(self._fused, self._start)
+            return
         for n in self.norms:
             n.snapshot()
 
@@ -97,6 +109,12 @@ class RoundSync:
 
     def end_round(self) -> None:
         if self.world == 1:
+            return
+        if self._fused is not None:
+            from . import _lib
+            _lib.sync_pack(self._fused, self.buf)
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)  # the single collective of the round
+            _lib.sync_unpack(self._fused, self.buf, self._start, self.world)
             return
         o = 0
         for t in self.averaged:

@@ -240,9 +240,9 @@ int imb_rollout_advance(int64_t* state, int64_t n_envs, int64_t n_steps, int32_t
 int imb_env_reset(float* env_obs, int64_t n_envs, const imb_env_desc* env, const int64_t* state,
                   void* stream);
 
-/* PPO.train as ONE persistent single-CTA launch: n_epochs x (N/batch) sequential minibatch
- * steps (gather by permutation, evaluate_actions, clipped surrogate + value + entropy loss,
- * backward, clip_grad_norm_, Adam).  perm == NULL -> device Feistel permutations.
+/* PPO.train as ONE persistent launch of an 8-CTA thread-block cluster: n_epochs x (N/batch)
+ * sequential minibatch steps (gather by permutation, evaluate_actions, clipped surrogate + value +
+ * entropy loss, backward, clip_grad_norm_, Adam); batch_size <= 64, tower width <= 32.  perm == NULL -> device Feistel permutations.
  * loss_log (optional) [n_steps_total][4] = pg_loss, value_loss, entropy_loss, total. */
 int imb_ppo_update(const imb_policy_desc* pol, float* pol_params, float* pol_norm,
                    int32_t* pol_norm_count, float* exp_avg, float* exp_avg_sq,
@@ -254,6 +254,29 @@ int imb_ppo_update(const imb_policy_desc* pol, float* pol_params, float* pol_nor
  * ActorCriticPolicy.evaluate_actions), written into the batch's last feature row. */
 int imb_policy_logp(const imb_policy_desc* pol, const float* pol_params, const float* pol_norm,
                     float* batch, int64_t ld, int64_t n, int32_t row_logp, void* stream);
+
+/* ---- multi-GPU: replica state around the ONE all-reduce of a round ---------------------------
+ * (the reference is single-process, so there is no reference interface to
+ * cite: the merge restates RunningNorm's Chan update, util/networks.py:96-134, in its additive
+ * sufficient-statistics form).  avg[i] (avg_n[i] floats) are averaged over the ranks; norm i is
+ * (mean[k], var[k], int32 count) and is merged exactly relative to the round-start snapshot.
+ * Staging buffers are float64: buf has imb_sync_buffer_doubles() entries, start the norm part. */
+#define IMB_SYNC_MAX_AVG 8
+#define IMB_SYNC_MAX_NORM 4
+typedef struct imb_sync_desc {
+  int32_t n_avg, n_norm;
+  float* avg[IMB_SYNC_MAX_AVG];
+  int64_t avg_n[IMB_SYNC_MAX_AVG];
+  float* mean[IMB_SYNC_MAX_NORM];
+  float* var[IMB_SYNC_MAX_NORM];
+  int32_t* count[IMB_SYNC_MAX_NORM];
+  int32_t k[IMB_SYNC_MAX_NORM];
+} imb_sync_desc;
+int64_t imb_sync_buffer_doubles(const imb_sync_desc* d);
+int imb_sync_snapshot(const imb_sync_desc* d, double* start, void* stream);
+int imb_sync_pack(const imb_sync_desc* d, double* buf, void* stream);
+int imb_sync_unpack(const imb_sync_desc* d, const double* buf, const double* start, int32_t world,
+                    void* stream);
 
 /* zero the device-resident counter block */
 int imb_state_init(int64_t* state, void* stream);

@@ -588,3 +588,56 @@ def test_policy_logp_matches_oracle(L):
         PN = th.cat([pol.feat_norm.running_mean, pol.feat_norm.running_var]).cuda()
         L.policy_logp(pd, _policy_flat(pol).cuda(), PN, batch, ld, n, bw - 1)
         np.testing.assert_allclose(batch[bw - 1, :n].cpu().numpy(), want, rtol=1e-4, atol=5e-5)
+
+
+def test_sync_pack_unpack_matches_torch_formulation(L):
+    """Fused replica-state pack/unpack (csrc/imb_sync.cu) == the torch formulation the gloo host-logic test
+    covers (distributed.NormStat / RoundSync), with two ranks emulated in one process."""
+    from imitation_b200.distributed import NormStat
+
+    rng = np.random.default_rng(11)
+    world, k = 2, 17
+
+    def rank_state(seed):
+        r = np.random.default_rng(seed)
+        avg = [th.tensor(r.standard_normal(n), dtype=th.float32, device="cuda") for n in (3501, 7, 1)]
+        return avg
+
+    # common round-start norm state, then each rank applies its own batches (Chan updates)
+    mean0, var0, n0 = rng.standard_normal(k), rng.random(k) + 0.5, 640
+    ranks = []
+    for rk in range(world):
+        r = np.random.default_rng(100 + rk)
+        x = r.standard_normal((256 * (rk + 1), k)) * 2 + 1
+        n1 = n0 + len(x)
+        d = x.mean(0) - mean0
+        mean1 = mean0 + d * len(x) / n1
+        var1 = (var0 * n0 + x.var(0) * len(x) + d * d * n0 * len(x) / n1) / n1
+        ranks.append(dict(avg=rank_state(rk), mean=th.tensor(mean1, dtype=th.float32, device="cuda"),
+                          var=th.tensor(var1, dtype=th.float32, device="cuda"),
+                          count=th.tensor([n1], dtype=th.int32, device="cuda")))
+    start = dict(mean=th.tensor(mean0, dtype=th.float32, device="cuda"), var=th.tensor(var0, dtype=th.float32, device="cuda"),
+                 count=th.tensor([n0], dtype=th.int32, device="cuda"))
+    # torch formulation on CPU copies
+    want_avg = [sum(r["avg"][i].double().cpu() for r in ranks) / world for i in range(3)]
+    ns = NormStat(ranks[0]["mean"].cpu().clone(), ranks[0]["var"].cpu().clone(), ranks[0]["count"].cpu().clone())
+    ns.start = (start["mean"].cpu(), start["var"].cpu(), start["count"].cpu())
+    summed = sum(NormStat(r["mean"].cpu(), r["var"].cpu(), r["count"].cpu()).pack() for r in ranks)
+    ns.unpack(summed, world)
+    # fused kernels: snapshot from the start state, pack per rank, sum, unpack into rank 0's tensors
+    d_start = L.sync_desc([], [(start["mean"], start["var"], start["count"])])
+    snap = th.zeros(1 + 2 * k, dtype=th.float64, device="cuda")
+    L.sync_snapshot(d_start, snap)
+    bufs = []
+    for r in ranks:
+        d = L.sync_desc(r["avg"], [(r["mean"], r["var"], r["count"])])
+        b = th.zeros(L.sync_buffer_doubles(d), dtype=th.float64, device="cuda")
+        L.sync_pack(d, b)
+        bufs.append(b)
+    d0 = L.sync_desc(ranks[0]["avg"], [(ranks[0]["mean"], ranks[0]["var"], ranks[0]["count"])])
+    L.sync_unpack(d0, bufs[0] + bufs[1], snap, world)
+    for got, want in zip(ranks[0]["avg"], want_avg):
+        np.testing.assert_allclose(got.cpu().numpy(), want.float().numpy(), rtol=0, atol=0)
+    np.testing.assert_allclose(ranks[0]["mean"].cpu().numpy(), ns.mean.numpy(), rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(ranks[0]["var"].cpu().numpy(), ns.var.numpy(), rtol=1e-6, atol=1e-7)
+    assert int(ranks[0]["count"]) == int(ns.count) == n0 + 256 + 512
