@@ -20,10 +20,6 @@
 // phase timing for profiles/: CTA 0 / thread 0 accumulates clock64() deltas per phase of the optimiser step
 __device__ long long g_ppo_clk[24];
 __device__ long long g_ppo_wclk[64];  // [slot][warp]: cycles since the top barrier at points of the warp chain (CTA 0)
-#define PPO_WCLK(slot)                                                                 \
-  do {                                                                                 \
-    if (crank == 0 && lane == 0) g_ppo_wclk[(slot) * 8 + warp] += clock64() - wclk0;  \
-  } while (0)
 #define PPO_TICK(i)                                  \
   do {                                               \
     if (tid == 0) {                                  \
@@ -31,6 +27,10 @@ __device__ long long g_ppo_wclk[64];  // [slot][warp]: cycles since the top barr
       clk_acc[i] += now_ - clk_last;                 \
       clk_last = now_;                               \
     }                                                \
+  } while (0)
+#define PPO_WCLK(slot)                                   \
+  do {                                                   \
+    if (lane == 0) wacc[slot] += clock64() - wclk0;      \
   } while (0)
 #else
 #define PPO_TICK(i) do {} while (0)
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
 
 #ifdef IMB_PPO_TIMING
   long long clk_acc[16] = {0}, clk_last = clock64();
+  long long wacc[8] = {0};  // per-warp chain clocks, kept in registers (a global RMW per sample stalls the chain)
 #endif
   int ep_now = 0, start = 0;  // epoch and first row of the current step
   for (int64_t gs = 0; gs < n_steps; ++gs) {
@@ -512,6 +513,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
           }
         }
         logp = half16_sum(logp);
+        PPO_WCLK(6);
         if (pd.discrete || loss_log) ent = half16_sum(ent);  // (Gaussian: the entropy only feeds the loss log)
         const float ratio = __expf(logp - logp_old);
         const float lo = 1.0f - A.hp.clip_range, hi = 1.0f + A.hp.clip_range;
@@ -541,6 +543,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
           }
         }
         __syncwarp();
+        PPO_WCLK(7);
 #pragma unroll 4
         for (int a = 0; a < Da; ++a) {
           const float waj = Wa[a * ldh + jc];
@@ -709,6 +712,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
 #ifdef IMB_PPO_TIMING
   if (crank == 0 && tid == 0)
     for (int i = 0; i < 16; ++i) g_ppo_clk[i] = clk_acc[i];
+  if (crank == 0 && lane == 0)
+    for (int i = 0; i < 8; ++i) g_ppo_wclk[i * 8 + warp] = wacc[i];
 #endif
 
   // ---- write back (CTA 0): parameters and moments in torch order, norm state, counters ------------------------------

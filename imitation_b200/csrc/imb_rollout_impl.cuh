@@ -27,8 +27,10 @@
 
 namespace {
 
-constexpr int RR = 128;              // envs (tile rows) per CTA = threads per CTA
-constexpr int RRS = RR + TILE_PAD;   // tile row stride
+constexpr int RT = 128;              // threads per CTA
+// envs (tile rows) per CTA: RR = 32 * RPL with RPL = 1, 2 or 4 rows per lane in the tiled layers; the launch picks
+// the smallest tile that still fills the GPU (1024 envs -> 32 CTAs of 32 envs: the kernel's time is one CTA's
+// latency, so smaller tiles are faster until the SMs run out); tile row stride RRS = RR + 4.
 
 struct RolloutArgs {
   imb_env_desc env;
@@ -119,38 +121,53 @@ __device__ __forceinline__ int64_t flat_index(int64_t e, int64_t t, int64_t E, i
 enum { ACT_TANH = 0, ACT_RELU = 1 };
 
 // OUT[j][r] = act(bias[j] + sum_k A[k][r] * Wk[k][j]) for j < JPx (multiple of 32); 128 threads:
-// warp -> 8-column group, lane -> 4 rows.
-template <int ACT>
+// warp -> 8-column group, lane -> RPL consecutive rows.
+template <int ACT, int RPL>
 __device__ __forceinline__ void tile_layer(const float* __restrict__ A, int K, const float* __restrict__ Wk, int wld,
                                            const float* __restrict__ bias, float* __restrict__ OUT, int JPx) {
+  constexpr int RRS = 32 * RPL + TILE_PAD;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int rq[1] = {lane * 4};
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 gq[1] = {z4};
+  const int r0 = lane * RPL;
   for (int jh = 0; jh < JPx / 32; ++jh) {
     const int j0 = jh * 32 + warp * 8;
-    float acc[4][8];
+    float acc[RPL][8];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < RPL; ++a)
 #pragma unroll
       for (int t = 0; t < 8; ++t) acc[a][t] = 0.f;
-    gemm_acc<1, false>(acc, A, RRS, rq, Wk, wld, j0, K, gq, nullptr);
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      float av[RPL];
+      if (RPL == 4) {
+        const float4 a4 = ld4(A + k * RRS + r0);
+        av[0] = a4.x, av[1 % RPL] = a4.y, av[2 % RPL] = a4.z, av[3 % RPL] = a4.w;
+      } else if (RPL == 2) {
+        const float2 a2 = *reinterpret_cast<const float2*>(A + k * RRS + r0);
+        av[0] = a2.x, av[1 % RPL] = a2.y;
+      } else {
+        av[0] = A[k * RRS + r0];
+      }
+      const float4 w0 = ld4(Wk + k * wld + j0), w1 = ld4(Wk + k * wld + j0 + 4);
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int x = 0; x < RPL; ++x)
+#pragma unroll
+        for (int t = 0; t < 8; ++t) acc[x][t] = fmaf(av[x], w[t], acc[x][t]);
+    }
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
       const float b = bias[j0 + t];
-      float4 v;
-      if (ACT == ACT_TANH) {
-        v = make_float4(tanhf(acc[0][t] + b), tanhf(acc[1][t] + b), tanhf(acc[2][t] + b), tanhf(acc[3][t] + b));
-      } else {
-        v = make_float4(fmaxf(acc[0][t] + b, 0.f), fmaxf(acc[1][t] + b, 0.f), fmaxf(acc[2][t] + b, 0.f),
-                        fmaxf(acc[3][t] + b, 0.f));
+#pragma unroll
+      for (int x = 0; x < RPL; ++x) {
+        const float z = acc[x][t] + b;
+        OUT[(j0 + t) * RRS + r0 + x] = ACT == ACT_TANH ? tanh_fast(z) : fmaxf(z, 0.f);
       }
-      st4(OUT + (j0 + t) * RRS + rq[0], v);
     }
   }
 }
 
-__global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const DiscLaunch L,
+template <int RPL>
+__global__ void __launch_bounds__(RT, 1) k_rollout(const RolloutArgs A, const DiscLaunch L,
                                                    const float* __restrict__ env_params, float* __restrict__ env_obs,
                                                    const float* __restrict__ pol_params,
                                                    const float* __restrict__ pol_norm,
@@ -158,8 +175,11 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
                                                    float* __restrict__ ring, float* __restrict__ flat_out,
                                                    float* __restrict__ aux, const float* __restrict__ noise,
                                                    const int64_t* __restrict__ state) {
+  constexpr int RR = 32 * RPL, RRS = RR + TILE_PAD;
   extern __shared__ __align__(128) float smem[];
   const int tid = threadIdx.x;
+  const int rt = tid < RR ? tid : RR - 1;  // tile row of this thread in the thread-per-env parts (threads >= RR idle there)
+  const bool rowthread = tid < RR;
   const int Do = A.env.d_obs, Da = A.env.d_act, h = A.pol.hidden, HP = A.HP, JP = A.JP, IP = A.IP, KU = A.KU;
   const PolImg S(Do, Da, HP);
   float* psm = smem + A.pol_off;
@@ -169,7 +189,7 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
   float* H1 = smem + A.h1_off;
   float* H2 = smem + A.h2_off;
   float* NOBS = smem + A.nobs_off; // [IP][RRS]
-  float* vec = smem + A.vec_off;   // lg[RR]
+  float* vec = smem + A.vec_off;   // lg[RT]
   float* lg = vec;
 
   // ---- one-time loads ------------------------------------------------------------------------------
@@ -178,22 +198,22 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
       load_timg(smem + A.img_off + p * A.img_sz, L.pass[p], JP, disc_params,
                 L.pass[p].has_norm ? L.pass[p].norm : nullptr, L.pass[p].eps);
   load_policy_img(psm, S, A.pol, HP, pol_params, pol_norm);
-  for (int i = tid; i < (KU + 2) * IP; i += RR) esm[i] = 0.f;
+  for (int i = tid; i < (KU + 2) * IP; i += RT) esm[i] = 0.f;
   __syncthreads();
   {
     const float* eA = env_params;
     const float* eB = eA + Do * Do;
     const float* eC = eB + Do * Da;
     const float* eW = eC + Do;
-    for (int i = tid; i < Do * Do; i += RR) {
+    for (int i = tid; i < Do * Do; i += RT) {
       const int r = i / Do, c = i - r * Do;  // A[r][c] -> ABt[c][r]
       esm[c * IP + r] = eA[i];
     }
-    for (int i = tid; i < Do * Da; i += RR) {
+    for (int i = tid; i < Do * Da; i += RT) {
       const int r = i / Da, c = i - r * Da;  // B[r][c] -> ABt[Do + c][r]
       esm[(Do + c) * IP + r] = eB[i];
     }
-    for (int i = tid; i < Do; i += RR) {
+    for (int i = tid; i < Do; i += RT) {
       esm[KU * IP + i] = eC[i];
       esm[(KU + 1) * IP + i] = eW[i];
     }
@@ -202,10 +222,12 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
   const float* ewv = esm + (KU + 1) * IP;
   const int64_t E = A.E, T = A.T, H = A.env.horizon;
   const int64_t e0 = (int64_t)blockIdx.x * RR;
-  const int64_t e = e0 + tid;
-  const bool live = e < E;
-  for (int k = 0; k < Do; ++k) OBSU[k * RRS + tid] = live ? env_obs[(int64_t)k * E + e] : 0.f;  // coalesced
-  for (int a = 0; a < Da; ++a) OBSU[(Do + a) * RRS + tid] = 0.f;
+  const int64_t e = e0 + rt;
+  const bool live = rowthread && e < E;
+  if (rowthread) {
+    for (int k = 0; k < Do; ++k) OBSU[k * RRS + tid] = live ? env_obs[(int64_t)k * E + e] : 0.f;  // coalesced
+    for (int a = 0; a < Da; ++a) OBSU[(Do + a) * RRS + tid] = 0.f;
+  }
   __syncthreads();
 
   const int64_t t0 = state[IMB_ST_EP_STEP];
@@ -225,15 +247,15 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
     float v0 = 0.f, v1 = 0.f;
     int j = 0;
     for (; j + 2 <= h; j += 2) {
-      v0 = fmaf(psm[S.wv + j], H2[j * RRS + tid], v0);
-      v1 = fmaf(psm[S.wv + j + 1], H2[(j + 1) * RRS + tid], v1);
+      v0 = fmaf(psm[S.wv + j], H2[j * RRS + rt], v0);
+      v1 = fmaf(psm[S.wv + j + 1], H2[(j + 1) * RRS + rt], v1);
     }
-    if (j < h) v0 = fmaf(psm[S.wv + j], H2[j * RRS + tid], v0);
+    if (j < h) v0 = fmaf(psm[S.wv + j], H2[j * RRS + rt], v0);
     return psm[S.bv] + (v0 + v1);
   };
   // XN <- feature-normalised copy of a [Do][RRS] observation tile
   auto norm_obs = [&](const float* __restrict__ SRC) {
-    for (int i = tid; i < Do * (RR / 4); i += RR) {
+    for (int i = tid; i < Do * (RR / 4); i += RT) {
       const int k = i / (RR / 4), r4 = (i - k * (RR / 4)) * 4;
       const float4 x = ld4(SRC + k * RRS + r4);
       const float m = psm[S.mean + k], is = psm[S.istd + k];
@@ -243,9 +265,9 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
   };
   auto value_of_obs = [&](const float* __restrict__ SRC) {
     norm_obs(SRC);
-    tile_layer<ACT_TANH>(XN, Do, psm + S.w1v, HP, psm + S.b1v, H1, HP);
+    tile_layer<ACT_TANH, RPL>(XN, Do, psm + S.w1v, HP, psm + S.b1v, H1, HP);
     __syncthreads();
-    tile_layer<ACT_TANH>(H1, h, psm + S.w2v, HP, psm + S.b2v, H2, HP);
+    tile_layer<ACT_TANH, RPL>(H1, h, psm + S.w2v, HP, psm + S.b2v, H2, HP);
     __syncthreads();
     const float v = value_row();
     __syncthreads();
@@ -257,22 +279,24 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
     float* row = rollout + (e * T + t) * rw;
     // ---- policy: value tower, then pi tower (H2 ends up holding the pi latent) ------------------------------
     const float value = value_of_obs(OBSU);
-    tile_layer<ACT_TANH>(XN, Do, psm + S.w1p, HP, psm + S.b1p, H1, HP);
+    tile_layer<ACT_TANH, RPL>(XN, Do, psm + S.w1p, HP, psm + S.b1p, H1, HP);
     __syncthreads();
-    tile_layer<ACT_TANH>(H1, h, psm + S.w2p, HP, psm + S.b2p, H2, HP);
+    tile_layer<ACT_TANH, RPL>(H1, h, psm + S.w2p, HP, psm + S.b2p, H2, HP);
     __syncthreads();
     // ---- action head + sampling, thread per env ----------------------------------------------------------------
     float logp = 0.f;
-    if (!A.pol.discrete) {
+    if (!rowthread) {
+      // (threads beyond the tile's rows only take part in the tiled layers)
+    } else if (!A.pol.discrete) {
       for (int a = 0; a < Da; ++a) {
         float m0 = 0.f, m1 = 0.f;
         const float* wa = psm + S.wa + a * HP;
         int j = 0;
         for (; j + 2 <= h; j += 2) {
-          m0 = fmaf(wa[j], H2[j * RRS + tid], m0);
-          m1 = fmaf(wa[j + 1], H2[(j + 1) * RRS + tid], m1);
+          m0 = fmaf(wa[j], H2[j * RRS + rt], m0);
+          m1 = fmaf(wa[j + 1], H2[(j + 1) * RRS + rt], m1);
         }
-        if (j < h) m0 = fmaf(wa[j], H2[j * RRS + tid], m0);
+        if (j < h) m0 = fmaf(wa[j], H2[j * RRS + rt], m0);
         const float m = psm[S.ba + a] + (m0 + m1);
         const float z = A.deterministic ? 0.f
                         : noise   ? (live ? noise[(t * E + e) * Da + a] : 0.f)
@@ -290,7 +314,7 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
       for (int a = 0; a < Da; ++a) {
         float m0 = 0.f;
         const float* wa = psm + S.wa + a * HP;
-        for (int j = 0; j < h; ++j) m0 = fmaf(wa[j], H2[j * RRS + tid], m0);
+        for (int j = 0; j < h; ++j) m0 = fmaf(wa[j], H2[j * RRS + rt], m0);
         const float m = psm[S.ba + a] + m0;
         OBSU[(Do + a) * RRS + tid] = m;  // logits, overwritten by the one-hot below
         mx = fmaxf(mx, m);
@@ -333,14 +357,14 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
     __syncthreads();
 
     // ---- environment step: NOBS = tanh([obs | u] . [A | B]^T + c) --------------------------------------------------
-    tile_layer<ACT_TANH>(OBSU, KU, esm, IP, ecv, NOBS, IP);
+    tile_layer<ACT_TANH, RPL>(OBSU, KU, esm, IP, ecv, NOBS, IP);
     __syncthreads();
     float rew_env = 0.f;
-    for (int i = 0; i < Do; ++i) rew_env = fmaf(ewv[i], NOBS[i * RRS + tid], rew_env);
+    for (int i = 0; i < Do; ++i) rew_env = fmaf(ewv[i], NOBS[i * RRS + rt], rew_env);
     if (!A.env.discrete) {
       float pen = 0.f;
       for (int a = 0; a < Da; ++a) {
-        const float uu = OBSU[(Do + a) * RRS + tid];
+        const float uu = OBSU[(Do + a) * RRS + rt];
         pen = fmaf(uu, uu, pen);
       }
       rew_env -= 0.1f * pen;
@@ -357,7 +381,7 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
         const int din = Pd.din;
         const float* mean = img + TImg::mean(din, JP);
         const float* istd = img + TImg::istd(din, JP);
-        for (int i = tid; i < din * (RR / 4); i += RR) {
+        for (int i = tid; i < din * (RR / 4); i += RT) {
           const int k = i / (RR / 4), r4 = (i - k * (RR / 4)) * 4;
           const int fr = L.stage_row[Pd.in_slot[k]];  // batch feature row -> source tile row
           float4 x;
@@ -371,13 +395,13 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
         const float* HL = XN;
         int hl = din;
         if (Pd.n_hidden >= 1) {
-          tile_layer<ACT_RELU>(XN, din, img + TImg::w1t(din, JP), JP, img + TImg::b1(din, JP), H1, JP);
+          tile_layer<ACT_RELU, RPL>(XN, din, img + TImg::w1t(din, JP), JP, img + TImg::b1(din, JP), H1, JP);
           __syncthreads();
           HL = H1;
           hl = Pd.h1;
         }
         if (Pd.n_hidden >= 2) {
-          tile_layer<ACT_RELU>(H1, Pd.h1, img + TImg::w2t(din, JP), JP, img + TImg::b2(din, JP), H2, JP);
+          tile_layer<ACT_RELU, RPL>(H1, Pd.h1, img + TImg::w2t(din, JP), JP, img + TImg::b2(din, JP), H2, JP);
           __syncthreads();
           HL = H2;
           hl = Pd.h2;
@@ -386,10 +410,10 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
         float o0 = 0.f, o1 = 0.f;
         int j = 0;
         for (; j + 2 <= hl; j += 2) {
-          o0 = fmaf(wf[j], HL[j * RRS + tid], o0);
-          o1 = fmaf(wf[j + 1], HL[(j + 1) * RRS + tid], o1);
+          o0 = fmaf(wf[j], HL[j * RRS + rt], o0);
+          o1 = fmaf(wf[j + 1], HL[(j + 1) * RRS + rt], o1);
         }
-        if (j < hl) o0 = fmaf(wf[j], HL[j * RRS + tid], o0);
+        if (j < hl) o0 = fmaf(wf[j], HL[j * RRS + rt], o0);
         const float o = img[TImg::bf(din, JP)] + (o0 + o1);
         const float c = pass_coef(Pd.coef_kind, L.gamma, donef);
         lg[tid] = (p == 0) ? c * o : fmaf(c, o, lg[tid]);
@@ -422,9 +446,10 @@ __global__ void __launch_bounds__(RR, 1) k_rollout(const RolloutArgs A, const Di
     // ---- advance: on done the next observation is the reset observation ------------------------------------------
     if (done) {
       ++episode;
-      for (int k = 0; k < Do; ++k)
-        OBSU[k * RRS + tid] = 0.1f * philox_normal(A.env.seed, IMB_STREAM_ENV_RESET, egid, (uint32_t)episode, k);
-    } else {
+      if (rowthread)
+        for (int k = 0; k < Do; ++k)
+          OBSU[k * RRS + tid] = 0.1f * philox_normal(A.env.seed, IMB_STREAM_ENV_RESET, egid, (uint32_t)episode, k);
+    } else if (rowthread) {
       for (int k = 0; k < Do; ++k) OBSU[k * RRS + tid] = NOBS[k * RRS + tid];
     }
     __syncthreads();
@@ -491,10 +516,12 @@ __global__ void k_env_reset(float* __restrict__ env_obs, int64_t E, int d_obs, u
 
 }  // namespace
 
-static int launch_rollout(RolloutArgs A, const DiscLaunch& L, const float* env_params, float* env_obs,
-                          const float* pol_params, const float* pol_norm, const float* disc_params, float* rollout,
-                          float* ring, float* flat_out, float* aux, const float* noise, const int64_t* state,
-                          cudaStream_t st) {
+template <int RPL>
+static int launch_rollout_t(RolloutArgs A, const DiscLaunch& L, const float* env_params, float* env_obs,
+                            const float* pol_params, const float* pol_norm, const float* disc_params, float* rollout,
+                            float* ring, float* flat_out, float* aux, const float* noise, const int64_t* state,
+                            cudaStream_t st) {
+  constexpr int RR = 32 * RPL, RRS = RR + TILE_PAD;
   auto al = [](int x) { return (x + 31) / 32 * 32; };
   const int Do = A.env.d_obs, Da = A.env.d_act;
   A.HP = A.pol.hidden <= 32 ? 32 : 64;
@@ -529,19 +556,34 @@ static int launch_rollout(RolloutArgs A, const DiscLaunch& L, const float* env_p
   A.nobs_off = o;
   o += al(A.IP * RRS);
   A.vec_off = o;
-  o += al(RR);
+  o += al(RT);
   A.total = o;
   const size_t bytes = (size_t)o * 4;
   IMB_REQUIRE(bytes <= IMB_SMEM_MAX, "rollout kernel needs %zu B of shared memory", bytes);
   static size_t attr_bytes = 0;
   if (bytes > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(k_rollout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_rollout<RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_bytes = bytes;
   }
   const int blocks = (int)((A.E + RR - 1) / RR);
-  k_rollout<<<blocks, RR, bytes, st>>>(A, L, env_params, env_obs, pol_params, pol_norm, disc_params, rollout, ring,
-                                       flat_out, aux, noise, state);
+  k_rollout<RPL><<<blocks, RT, bytes, st>>>(A, L, env_params, env_obs, pol_params, pol_norm, disc_params, rollout, ring,
+                                            flat_out, aux, noise, state);
   IMB_CHECK_LAUNCH("k_rollout");
   return 0;
+}
+
+static int launch_rollout(const RolloutArgs& A, const DiscLaunch& L, const float* env_params, float* env_obs,
+                          const float* pol_params, const float* pol_norm, const float* disc_params, float* rollout,
+                          float* ring, float* flat_out, float* aux, const float* noise, const int64_t* state,
+                          cudaStream_t st) {
+  // smallest tile that still covers the SMs: the kernel's duration is one CTA's latency
+  const int64_t sms = imb_num_sms();
+#define IMB_RL(R) \
+  return launch_rollout_t<R>(A, L, env_params, env_obs, pol_params, pol_norm, disc_params, rollout, ring, flat_out, aux, \
+                             noise, state, st)
+  if (A.E <= sms * 32) IMB_RL(1);
+  if (A.E <= sms * 64 * 2) IMB_RL(2);
+  IMB_RL(4);
+#undef IMB_RL
 }

@@ -48,6 +48,6 @@ print(f"{'total':<18s} {tot / steps:9.0f} cycles/step")
 w = (ctypes.c_longlong * 64)()
 assert _lib.lib().imb_debug_ppo_warp_clocks(w, 0) == 0
 print("per-warp cycles/step since the top barrier (CTA 0; warps 0-3 policy tower, 4-7 value tower):")
-for slot, name in ((1, "after prefetch issue"), (3, "after layer 1"), (4, "after layer 2"), (5, "after means (policy)"),
+for slot, name in ((1, "after prefetch issue"), (3, "after layer 1"), (4, "after layer 2"), (5, "after means (policy)"), (6, "after logp reduce"), (7, "after dM/dlogstd"),
                    (2, "after heads/loss"), (0, "chain end")):
     print(f"  {name:<22s}", [round(w[slot * 8 + i] / steps) for i in range(8)])
