@@ -176,6 +176,20 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 
+// distributed shared memory: address of the same shared-memory location in CTA `rank` of the cluster, and an
+// asynchronous 16-byte remote store that completes bytes on an mbarrier of the receiving CTA
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_saddr, int rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_v4(uint32_t remote_saddr, const float4& v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   remote_saddr),
+               "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(remote_mbar)
+               : "memory");
+}
+
 // tanh with ~1e-7 absolute error in a dozen instructions (tanhf's accurate path costs ~5x more and sits on
 // the critical path of every layer of the latency-bound PPO step): odd polynomial below 0.1, else
 // 1 - 2 / (exp(2x) + 1) with the hardware exponential; saturates correctly for large |x|.

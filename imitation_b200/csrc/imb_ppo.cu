@@ -166,8 +166,8 @@ __device__ __forceinline__ float sum8(const float (&d)[8]) {
 //     16-byte stores; owners sum the CL partials in fixed order and all-gather the summed slices;
 //   * every CTA then runs clip_grad_norm_ + Adam on the FULL vector (identical arithmetic everywhere, so the
 //     replicas never diverge).
-// Two cluster barriers and three CTA barriers per optimiser step; the only global-memory traffic inside a
-// step is the asynchronous minibatch prefetch.
+// No cluster barrier inside the step loop (the exchanged data signals mbarriers at the receivers), three CTA
+// barriers per optimiser step; the only global-memory traffic inside a step is the asynchronous minibatch prefetch.
 template <int HP>
 __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __restrict__ g_params,
                                                       float* __restrict__ g_norm, int32_t* __restrict__ g_norm_count,
@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   __shared__ float red[32];
   __shared__ float bc[8];
   __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ __align__(8) uint64_t xbar[2];  // [0]: partial gradients of the owned slice have arrived; [1]: all summed slices have
   const imb_policy_desc& pd = A.pol;
   const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params, KP = A.KP, S = A.S;
   const PLay PL = make_play(pd);
@@ -237,6 +238,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   if (tid == 0) {
     mbar_init(&mbar[0], 128);
     mbar_init(&mbar[1], 128);
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -351,6 +354,17 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   __syncthreads();
   issue_gather(0, 0, 0);
   minibatch_stats(0, min(mb, Ni));
+  // The gradient exchange is synchronised by the data itself: every 16-byte DSMEM store (st.async) completes
+  // bytes on an mbarrier of the RECEIVING CTA, which waits until the expected byte count of the phase has
+  // landed -- no cluster-wide barrier inside the step loop.  Each barrier is re-armed (one arrival + expected
+  // bytes) by its owner right after the previous phase completed, which is always before a peer can send for
+  // the next phase (a peer's next-phase data depends on data this CTA sends later).
+  const uint32_t xbytes = (uint32_t)(CL * S * 4);
+  const uint32_t recv_sa = smem_u32(RECV), gp_sa = smem_u32(GP), xbar0_sa = smem_u32(&xbar[0]), xbar1_sa = smem_u32(&xbar[1]);
+  if (tid == 0) {
+    mbar_expect_tx(&xbar[0], xbytes);
+    mbar_expect_tx(&xbar[1], xbytes);
+  }
   cluster.sync();
 
 #ifdef IMB_PPO_TIMING
@@ -631,30 +645,10 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       int qq = q + ((crank + 1) & (CL - 1)) * (S / 4);
       if (qq >= CL * S / 4) qq -= CL * S / 4;
       const int p0 = 4 * qq, owner = p0 / S;
-      st4(cluster.map_shared_rank(RECV, owner) + crank * S + (p0 - owner * S), ld4(GP + p0));
+      st_async_v4(mapa_u32(recv_sa + (uint32_t)(crank * S + (p0 - owner * S)) * 4u, owner), ld4(GP + p0),
+                  mapa_u32(xbar0_sa, owner));
     }
-    PPO_TICK(8);
-    // (a) cluster barrier; before it the NEXT step's minibatch statistics and own-row tile (they do not depend on
-    //     the parameters); after the wait all partial gradients / losses have landed at their owners
-    // (the remote stores above drain while the statistics run, so the release at the arrive is cheap)
-    if (gs + 1 < n_steps) minibatch_stats(gs + 1, min(mb, Ni - start_next));
-    PPO_TICK(1);
-    cluster_arrive();
-    cluster_wait();
-    PPO_TICK(9);
-
-    // ---- 4. slice owners: sum the CL partials in fixed order, all-gather the summed slice --------------------------
-    for (int i0 = 4 * tid; i0 < S; i0 += 4 * PT) {
-      float4 g = ld4(RECV + i0);
-#pragma unroll
-      for (int c = 1; c < CL; ++c) {  // fixed order: deterministic
-        const float4 t = ld4(RECV + c * S + i0);
-        g.x += t.x, g.y += t.y, g.z += t.z, g.w += t.w;
-      }
-#pragma unroll
-      for (int c = 0; c < CL; ++c)  // rotated start: the 8 owners write to 8 different CTAs at a time
-        st4(cluster.map_shared_rank(GP, (crank + c) & (CL - 1)) + crank * S + i0, g);
-    }
+    if (loss_log) cluster.sync();  // (test / logging path only) the partial losses have landed in CTA 0
     if (crank == 0 && tid == 0 && loss_log) {
       float pg = 0.f, vl = 0.f, el = 0.f;
       for (int c = 0; c < CL; ++c) {
@@ -668,8 +662,32 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       loss_log[gs * 4 + 2] = el;
       loss_log[gs * 4 + 3] = pg + A.hp.ent_coef * el + A.hp.vf_coef * vl;
     }
+    PPO_TICK(8);
+    // While the partials travel: the NEXT step's minibatch statistics and own-row tile (they do not depend on the
+    // parameters).  Then wait until the 8 partials of the owned slice have landed.
+    if (gs + 1 < n_steps) minibatch_stats(gs + 1, min(mb, Ni - start_next));
+    PPO_TICK(1);
+    mbar_wait(&xbar[0], (uint32_t)(gs & 1));
+    if (tid == 0) mbar_expect_tx(&xbar[0], xbytes);  // re-arm for the next step
+    PPO_TICK(9);
+
+    // ---- 4. slice owners: sum the CL partials in fixed order, all-gather the summed slice --------------------------
+    for (int i0 = 4 * tid; i0 < S; i0 += 4 * PT) {
+      float4 g = ld4(RECV + i0);
+#pragma unroll
+      for (int c = 1; c < CL; ++c) {  // fixed order: deterministic
+        const float4 t = ld4(RECV + c * S + i0);
+        g.x += t.x, g.y += t.y, g.z += t.z, g.w += t.w;
+      }
+#pragma unroll
+      for (int c = 0; c < CL; ++c) {  // rotated start: the 8 owners write to 8 different CTAs at a time
+        const int dstc = (crank + c) & (CL - 1);
+        st_async_v4(mapa_u32(gp_sa + (uint32_t)(crank * S + i0) * 4u, dstc), g, mapa_u32(xbar1_sa, dstc));
+      }
+    }
     PPO_TICK(10);
-    cluster.sync();  // (b) every CTA holds the full summed gradient in GP
+    mbar_wait(&xbar[1], (uint32_t)(gs & 1));  // every summed slice has landed in GP
+    if (tid == 0) mbar_expect_tx(&xbar[1], xbytes);  // re-arm for the next step
     PPO_TICK(11);
 
     // ---- 5. clip_grad_norm_ + Adam on the full vector, identically in every CTA ------------------------------------------
