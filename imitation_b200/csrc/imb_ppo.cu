@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   // bytes) by its owner right after the previous phase completed, which is always before a peer can send for
   // the next phase (a peer's next-phase data depends on data this CTA sends later).
   const uint32_t xbytes = (uint32_t)(CL * S * 4);
+  const unsigned qmagic = (unsigned)(0x100000000ull / (unsigned)(S / 4)) + 1u;  // exact quotient for the < 2^16 quads here
   const uint32_t recv_sa = smem_u32(RECV), gp_sa = smem_u32(GP), xbar0_sa = smem_u32(&xbar[0]), xbar1_sa = smem_u32(&xbar[1]);
   if (tid == 0) {
     mbar_expect_tx(&xbar[0], xbytes);
@@ -406,6 +407,19 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       const int gr = row0 + r0 + rr;
       const bool live = gr < nb;
       const float* row = Rc + gr * RS2;
+      // policy warps: everything the loss needs that does not depend on the forward pass is fetched now, so its
+      // latency (shared-memory loads, the exponential) hides behind the layers
+      const bool gfast = net == 0 && !pd.discrete && Da <= 16;  // one action per lane of the half-warp
+      float pre_adv = 0.f, pre_lpo = 0.f, pre_act = 0.f, pre_ls = 0.f, pre_ivar = 0.f;
+      if (net == 0) {
+        pre_adv = row[col_adv];
+        pre_lpo = row[col_logp];
+        if (gfast && la < Da) {
+          pre_act = row[Do + la];
+          pre_ls = Pm[PL.ls + la];
+          pre_ivar = __expf(-2.0f * pre_ls);
+        }
+      }
       // layer 1
       float a0 = 0.f, a1 = 0.f;
       {
@@ -494,10 +508,20 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
         }
         __syncwarp();
         PPO_WCLK(5);
-        const float adv = row[col_adv], logp_old = row[col_logp];
+        const float adv = pre_adv, logp_old = pre_lpo;
         float logp = 0.f, ent = 0.f;
+        float r_dm = 0.f, r_dls = 0.f;  // fast path: this lane's d logp / d mean, d logp / d log_std
         int act = 0;
-        if (!pd.discrete) {
+        if (gfast) {
+          if (la < Da) {
+            const float diff = pre_act - MEAN[la * RL + r0 + rr];
+            const float d2 = diff * diff * pre_ivar;
+            logp = -0.5f * d2 - pre_ls - 0.9189385332046727f;
+            ent = 1.4189385332046727f + pre_ls;
+            r_dm = diff * pre_ivar;
+            r_dls = d2 - 1.0f;
+          }
+        } else if (!pd.discrete) {
           const float* lstd = Pm + PL.ls;
           for (int a = la; a < Da; a += 16) {
             const float ls = lstd[a], ivar = __expf(-2.0f * ls);
@@ -544,7 +568,12 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
           dl_dlogp = 0.f;
           dent = 0.f;
         }
-        if (!pd.discrete) {
+        if (gfast) {
+          if (la < Da) {
+            DLS[la * RL + r0 + rr] = dl_dlogp * r_dls + dent;  // dH/dlog_std = 1
+            DM[la * RL + r0 + rr] = dl_dlogp * r_dm;
+          }
+        } else if (!pd.discrete) {
           for (int a = la; a < Da; a += 16) {
             DLS[a * RL + r0 + rr] = dl_dlogp * DLS[a * RL + r0 + rr] + dent;  // dH/dlog_std = 1
             DM[a * RL + r0 + rr] = dl_dlogp * DM[a * RL + r0 + rr];
@@ -644,7 +673,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     for (int q = tid; q < CL * S / 4; q += PT) {
       int qq = q + ((crank + 1) & (CL - 1)) * (S / 4);
       if (qq >= CL * S / 4) qq -= CL * S / 4;
-      const int p0 = 4 * qq, owner = p0 / S;
+      const int p0 = 4 * qq, owner = (int)__umulhi((unsigned)qq, qmagic);  // = qq / (S / 4)
       st_async_v4(mapa_u32(recv_sa + (uint32_t)(crank * S + (p0 - owner * S)) * 4u, owner), ld4(GP + p0),
                   mapa_u32(xbar0_sa, owner));
     }
