@@ -82,6 +82,7 @@ SYMBOLS = [
     "imb_ring_advance", "imb_sample_indices", "imb_gather_rows", "imb_rollout", "imb_rollout_row_width", "imb_gae",
     "imb_rollout_advance", "imb_env_reset", "imb_ppo_update", "imb_policy_logp", "imb_state_init",
     "imb_sync_buffer_doubles", "imb_sync_snapshot", "imb_sync_pack", "imb_sync_unpack",
+    "imb_disc_sample_gather", "imb_sample_advance2", "imb_disc_reduce_adam",
 ]
 
 
@@ -108,6 +109,7 @@ _KERNELS_PER_CALL = {
     "imb_disc_adam": 1, "imb_reward_forward": 1, "imb_reward_norm_scan": 1, "imb_table_store": 1,
     "imb_ring_advance": 1, "imb_sample_indices": 2, "imb_gather_rows": 1, "imb_rollout": 1, "imb_gae": 1,
     "imb_rollout_advance": 1, "imb_env_reset": 1, "imb_ppo_update": 1, "imb_policy_logp": 1,
+    "imb_disc_sample_gather": 1, "imb_sample_advance2": 1, "imb_disc_reduce_adam": 1,
 }
 
 
@@ -227,6 +229,25 @@ def ring_advance(state, capacity, n_stored):
 def sample_indices(kind, idx_out, n, size, seed, state):
     _check(lib().imb_sample_indices(C.c_int(kind), _p(idx_out, th.int64), C.c_int64(n), C.c_int64(size),
                                     C.c_uint64(seed), _p(state, th.int64), _stream()), "imb_sample_indices")
+
+
+def disc_sample_gather(e_table, e_n, ring, ring_cap, tw, mb, start, seed, e_state, g_state, batch, ld):
+    _check(lib().imb_disc_sample_gather(_p(e_table, th.float32), C.c_int64(e_n), _p(ring, th.float32),
+                                        C.c_int64(ring_cap), C.c_int32(tw), C.c_int64(mb), C.c_int64(start),
+                                        C.c_uint64(seed), _p(e_state, th.int64), _p(g_state, th.int64),
+                                        _p(batch, th.float32), C.c_int64(ld), _stream()), "imb_disc_sample_gather")
+
+
+def sample_advance2(n, e_n, e_state, g_state):
+    _check(lib().imb_sample_advance2(C.c_int64(n), C.c_int64(e_n), _p(e_state, th.int64), _p(g_state, th.int64),
+                                     _stream()), "imb_sample_advance2")
+
+
+def disc_reduce_adam(d, opt, params, exp_avg, exp_avg_sq, grad_div, ws, state, stats_out):
+    _check(lib().imb_disc_reduce_adam(C.byref(d), C.byref(opt), _p(params, th.float32), _p(exp_avg, th.float32),
+                                      _p(exp_avg_sq, th.float32), C.c_float(grad_div), _p(ws, th.float32),
+                                      _p(state, th.int64), _p(stats_out, th.float32), _stream()),
+           "imb_disc_reduce_adam")
 
 
 def gather_rows(table, capacity, tw, idx, n, batch, ld, col0):

@@ -349,24 +349,36 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
     def _disc_update_body(self, e_host: bool, g_host: bool, train_mode: bool, out: th.Tensor) -> None:
         B, mb = self.demo_batch_size, self.demo_minibatch_size
         eng = self._fused_net.engine()
-        if not e_host:
+        opt: FusedAdamState = self._disc_opt
+        # device sampling on both sides: index generation and both gathers are ONE launch per minibatch
+        fused_sampling = (not e_host and not g_host and self.sampling == "device" and self._expert_compat is None)
+        if fused_sampling:
+            ring = self._gen_replay_buffer
+        elif not e_host:
             self._sample_expert_indices()
             e_table, e_idx, e_cap = self._expert_table, self._idx_e, self._expert_n
         else:
             e_table, e_idx, e_cap = self._pack_staged("expert"), None, B
-        if not g_host:
+        if fused_sampling:
+            pass
+        elif not g_host:
             self._sample_gen_indices()
             g_table, g_idx, g_cap = self._gen_replay_buffer.table, self._idx_g, self._gen_replay_buffer.capacity
         else:
             g_table, g_idx, g_cap = self._pack_staged("gen"), None, B
         n = 2 * mb
-        for i, start in enumerate(range(0, B, mb)):
-            ei = e_idx[start:start + mb] if e_idx is not None else None
-            gi = g_idx[start:start + mb] if g_idx is not None else None
-            et = e_table if e_idx is not None else e_table[start:start + mb]
-            gt = g_table if g_idx is not None else g_table[start:start + mb]
-            _lib.gather_rows(et, e_cap if e_idx is not None else mb, self._tw, ei, mb, self._batch, self._ld, 0)
-            _lib.gather_rows(gt, g_cap if g_idx is not None else mb, self._tw, gi, mb, self._batch, self._ld, mb)
+        starts = list(range(0, B, mb))
+        for i, start in enumerate(starts):
+            if fused_sampling:
+                _lib.disc_sample_gather(self._expert_table, self._expert_n, ring.table, ring.capacity, self._tw, mb, start,
+                                        self.seed, self._expert_state, self.venv.state, self._batch, self._ld)
+            else:
+                ei = e_idx[start:start + mb] if e_idx is not None else None
+                gi = g_idx[start:start + mb] if g_idx is not None else None
+                et = e_table if e_idx is not None else e_table[start:start + mb]
+                gt = g_table if g_idx is not None else g_table[start:start + mb]
+                _lib.gather_rows(et, e_cap if e_idx is not None else mb, self._tw, ei, mb, self._batch, self._ld, 0)
+                _lib.gather_rows(gt, g_cap if g_idx is not None else mb, self._tw, gi, mb, self._batch, self._ld, mb)
             if self._needs_logp:
                 pp, pn, _ = self.policy.flat_vectors()
                 _lib.policy_logp(self.policy.desc, pp, pn, self._batch, self._ld, n, self._bw - 1)
@@ -374,10 +386,13 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
             if tn:
                 eng.norm_update(self._batch, self._ld, n)
             eng.fwd_bwd(self._batch, self._ld, n, mb, 1.0 / (2 * B), None, self._logits, i == 0, tn)
-            eng.reduce(None)
-        opt: FusedAdamState = self._disc_opt
-        _lib.disc_adam(eng.desc, opt.hp, eng.params, opt.exp_avg, opt.exp_avg_sq, None, 1.0, eng.ws, self.venv.state,
-                       out)
+            if i + 1 < len(starts):
+                eng.reduce(None)
+            else:  # last minibatch: reduction, optimiser step and the statistics in one launch
+                _lib.disc_reduce_adam(eng.desc, opt.hp, eng.params, opt.exp_avg, opt.exp_avg_sq, 1.0, eng.ws,
+                                      self.venv.state, out)
+        if fused_sampling:
+            _lib.sample_advance2(B, self._expert_n, self._expert_state, self.venv.state)
 
     # -- whole round as one CUDA graph (no host work between kernels) ---------------------------------------------
     def _enqueue_round(self) -> None:

@@ -592,6 +592,76 @@ __global__ void __launch_bounds__(1024) k_disc_adam(int P, imb_adam opt, float* 
   }
 }
 
+// reduce + Adam in one launch (the last minibatch of an update): every block reduces its share of the partials
+// like k_disc_reduce; the last block to finish (ticket) runs the optimiser step and the statistics.
+__global__ void __launch_bounds__(256) k_disc_reduce_adam(int P, int G, const float* __restrict__ partial,
+                                                         float* __restrict__ gacc, float* __restrict__ stats,
+                                                         imb_adam opt, float* __restrict__ params,
+                                                         float* __restrict__ m, float* __restrict__ v, float grad_div,
+                                                         const int* __restrict__ meta, int64_t* __restrict__ step_io,
+                                                         float* __restrict__ stats_out,
+                                                         unsigned int* __restrict__ ticket) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int64_t ps = part_stride(P);
+  for (int p = gw; p < P + 5; p += nwarps) {
+    float acc = 0.f;
+    for (int c = lane; c < G; c += 32) acc += partial[(int64_t)c * ps + p];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      if (p < P) gacc[p] += acc;
+      else stats[p - P] = acc;
+    }
+  }
+  __threadfence();
+  __shared__ bool is_last;
+  __shared__ float s_bc[2];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) {
+    const int64_t step = *step_io + 1;
+    const double bc1d = 1.0 - pow((double)opt.beta1, (double)step);
+    const double bc2d = 1.0 - pow((double)opt.beta2, (double)step);
+    s_bc[0] = (float)((double)opt.lr / bc1d);
+    s_bc[1] = (float)sqrt(bc2d);
+    *step_io = step;
+    *ticket = 0u;  // re-arm for the next launch
+  }
+  __syncthreads();
+  const float step_size = s_bc[0], bc2_sqrt = s_bc[1];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) {
+    const float g = __ldcg(gacc + i) / grad_div;
+    const float mi = m[i] + (g - m[i]) * (1.0f - opt.beta1);
+    const float vi = v[i] * opt.beta2 + (1.0f - opt.beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + opt.eps;
+    params[i] -= step_size * (mi / denom);
+  }
+  if (threadIdx.x == 0 && stats_out) {
+    const float n = (float)meta[1], n_exp = (float)meta[2], n_gen = n - n_exp;
+    const float loss_sum = __ldcg(stats + 0), ent_sum = __ldcg(stats + 1), c_exp = __ldcg(stats + 2),
+                c_gen = __ldcg(stats + 3), c_pred = __ldcg(stats + 4);
+    const float nanv = __int_as_float(0x7fc00000);
+    stats_out[0] = loss_sum * reinterpret_cast<const float*>(meta)[3];
+    stats_out[1] = n > 0 ? (c_exp + c_gen) / n : nanv;
+    stats_out[2] = n_exp >= 1 ? c_exp / n_exp : nanv;
+    stats_out[3] = c_gen / fmaxf(1.f, n_gen);
+    stats_out[4] = n > 0 ? ent_sum / n : nanv;
+    stats_out[5] = n > 0 ? n_exp / n : nanv;
+    stats_out[6] = n > 0 ? c_pred / n : nanv;
+    stats_out[7] = n_exp;
+    stats_out[8] = n_gen;
+  }
+}
+
 __global__ void k_state_add(int64_t* state, int idx, int64_t v) { state[idx] += v; }
 __global__ void k_set_meta(int* meta, int G, int64_t n, int64_t n_expert, float loss_scale) {
   meta[0] = G;
@@ -896,6 +966,24 @@ extern "C" int imb_disc_adam(const imb_disc_desc* d, const imb_adam* opt, float*
   k_disc_adam<<<1, 1024, 0, st>>>(P, *opt, params, exp_avg, exp_avg_sq, grad, grad_div, ws + w.stats,
                                   reinterpret_cast<const int*>(ws + w.meta), state + IMB_ST_DISC_STEP, stats_out);
   IMB_CHECK_LAUNCH("k_disc_adam");
+  return 0;
+}
+
+extern "C" int imb_disc_reduce_adam(const imb_disc_desc* d, const imb_adam* opt, float* params, float* exp_avg,
+                                    float* exp_avg_sq, float grad_div, float* ws, int64_t* state, float* stats_out,
+                                    void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const WsLayout w = ws_layout(d->n_params);
+  IMB_REQUIRE(g_last_grid > 0, "imb_disc_reduce_adam called before imb_disc_fwd_bwd");
+  const int P = d->n_params;
+  const int warps = P + 5;
+  int blocks = (warps * 32 + 255) / 256;
+  if (blocks > 2 * imb_num_sms()) blocks = 2 * imb_num_sms();
+  k_disc_reduce_adam<<<blocks, 256, 0, st>>>(P, g_last_grid, ws + w.partial, ws + w.gacc, ws + w.stats, *opt, params,
+                                             exp_avg, exp_avg_sq, grad_div, reinterpret_cast<const int*>(ws + w.meta),
+                                             state + IMB_ST_DISC_STEP, stats_out,
+                                             reinterpret_cast<unsigned int*>(ws + w.ticket) + 8);
+  IMB_CHECK_LAUNCH("k_disc_reduce_adam");
   return 0;
 }
 

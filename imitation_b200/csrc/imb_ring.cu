@@ -128,6 +128,63 @@ __global__ void __launch_bounds__(G_WARPS * 32) k_gather_rows(const float* __res
   }
 }
 
+
+// ---- fused device sampling + gather of one discriminator minibatch ---------------------------------
+// Batch columns [0, mb): expert rows (endless Feistel permutations with drop_last, same stream as
+// k_sample_indices kind 1); columns [mb, 2 mb): generator rows (Philox randint over the ring, kind 0).  `start` is
+// the minibatch's offset inside the update's demo_batch_size draws; the draw counters advance once per update
+// (imb_sample_advance2).  Replaces 2 x (k_sample_indices + k_sample_advance) + 2 x k_gather_rows.
+__global__ void __launch_bounds__(G_WARPS * 32) k_sample_gather(const float* __restrict__ e_table, int64_t e_n,
+                                                                const float* __restrict__ g_table, int64_t g_cap,
+                                                                int tw, int64_t mb, int64_t start, uint64_t seed,
+                                                                const int64_t* __restrict__ e_state,
+                                                                const int64_t* __restrict__ g_state,
+                                                                float* __restrict__ batch, int64_t ld) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t n = 2 * mb, ngroups = (n + 31) / 32;
+  for (int64_t grp = (int64_t)blockIdx.x * G_WARPS + warp; grp < ngroups; grp += (int64_t)gridDim.x * G_WARPS) {
+    const int64_t mine = grp * 32 + lane;
+    if (mine >= n) continue;
+    const float* src;
+    if (mine < mb) {
+      const int64_t i = start + mine;
+      const FeistelKey f = feistel_key(seed, IMB_STREAM_EXPERT, (uint64_t)e_state[IMB_ST_EXPERT_EPOCH], (uint64_t)e_n);
+      const int64_t r = (int64_t)feistel_perm(f, (uint64_t)(e_state[IMB_ST_EXPERT_POS] + i), (uint64_t)e_n);
+      src = e_table + r * tw;
+    } else {
+      const int64_t i = start + (mine - mb);
+      const int64_t size = g_state[IMB_ST_RING_N];
+      const uint64_t draw = (uint64_t)g_state[IMB_ST_REPLAY_DRAW];
+      uint32_t k0, k1;
+      philox_key(seed, IMB_STREAM_REPLAY, k0, k1);
+      const Philox4 p = philox4x32((uint32_t)(i >> 2), (uint32_t)draw, (uint32_t)(draw >> 32), 0u, k0, k1);
+      const uint32_t w = ((i & 3) == 0) ? p.x : ((i & 3) == 1) ? p.y : ((i & 3) == 2) ? p.z : p.w;
+      int64_t r = (int64_t)(((uint64_t)w * (uint64_t)size) >> 32);
+      r = r < 0 ? 0 : (r >= g_cap ? g_cap - 1 : r);
+      src = g_table + r * tw;
+    }
+    float* dst = batch + mine;
+    int c = 0;
+    for (; c + 8 <= tw; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = src[c + u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dst[(int64_t)(c + u) * ld] = v[u];
+    }
+    for (; c < tw; ++c) dst[(int64_t)c * ld] = src[c];
+  }
+}
+__global__ void k_sample_advance2(int64_t n, int64_t e_n, int64_t* e_state, int64_t* g_state) {
+  g_state[IMB_ST_REPLAY_DRAW] += 1;
+  int64_t pos = e_state[IMB_ST_EXPERT_POS] + n;
+  if (pos + n > e_n) {  // the next batch would not fit: drop the tail, start a new permutation
+    pos = 0;
+    e_state[IMB_ST_EXPERT_EPOCH] += 1;
+  }
+  e_state[IMB_ST_EXPERT_POS] = pos;
+}
+
 }  // namespace
 
 extern "C" int imb_table_store(float* table, int64_t capacity, int32_t d_obs, int32_t d_act, const float* obs,
@@ -173,5 +230,28 @@ extern "C" int imb_gather_rows(const float* table, int64_t capacity, int32_t tw,
   if (blocks > cap) blocks = cap;
   k_gather_rows<<<(int)blocks, G_WARPS * 32, 0, (cudaStream_t)stream>>>(table, capacity, tw, idx, n, batch, ld, col0);
   IMB_CHECK_LAUNCH("k_gather_rows");
+  return 0;
+}
+
+extern "C" int imb_disc_sample_gather(const float* expert_table, int64_t n_expert, const float* ring,
+                                      int64_t ring_capacity, int32_t tw, int64_t mb, int64_t start, uint64_t seed,
+                                      const int64_t* expert_state, const int64_t* ring_state, float* batch, int64_t ld,
+                                      void* stream) {
+  IMB_REQUIRE(mb >= 1 && start >= 0 && tw >= 1, "bad minibatch shape");
+  IMB_REQUIRE(n_expert >= mb, "Number of transitions in `demonstrations` %lld is smaller than batch size %lld.",
+              (long long)n_expert, (long long)mb);
+  int64_t blocks = ((2 * mb + 31) / 32 + G_WARPS - 1) / G_WARPS;
+  const int64_t cap = (int64_t)imb_num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  k_sample_gather<<<(int)blocks, G_WARPS * 32, 0, (cudaStream_t)stream>>>(expert_table, n_expert, ring, ring_capacity, tw, mb,
+                                                                        start, seed, expert_state, ring_state, batch, ld);
+  IMB_CHECK_LAUNCH("k_sample_gather");
+  return 0;
+}
+
+extern "C" int imb_sample_advance2(int64_t n, int64_t n_expert, int64_t* expert_state, int64_t* ring_state,
+                                   void* stream) {
+  k_sample_advance2<<<1, 1, 0, (cudaStream_t)stream>>>(n, n_expert, expert_state, ring_state);
+  IMB_CHECK_LAUNCH("k_sample_advance2");
   return 0;
 }

@@ -166,6 +166,18 @@ int imb_ring_advance(int64_t* state, int64_t capacity, int64_t n_stored, void* s
 int imb_sample_indices(int kind, int64_t* idx_out, int64_t n, int64_t size, uint64_t seed,
                        int64_t* state, void* stream);
 
+/* Device sampling + gather of one discriminator minibatch in ONE launch: batch columns [0, mb) =
+ * expert rows drawn like imb_sample_indices(kind 1), columns [mb, 2 mb) = generator-ring rows drawn
+ * like kind 0, both at offset `start` of the update's draws (common.py:552 `sample` + :592-595
+ * concatenate + the DataLoader batch of :208-216).  The draw counters advance once per update:
+ * imb_sample_advance2(demo_batch_size, ...).  Bit-identical to the unfused calls. */
+int imb_disc_sample_gather(const float* expert_table, int64_t n_expert, const float* ring,
+                           int64_t ring_capacity, int32_t tw, int64_t mb, int64_t start,
+                           uint64_t seed, const int64_t* expert_state, const int64_t* ring_state,
+                           float* batch, int64_t ld, void* stream);
+int imb_sample_advance2(int64_t n, int64_t n_expert, int64_t* expert_state, int64_t* ring_state,
+                        void* stream);
+
 /* Gather table rows by index into the feature-major batch at column col0 (idx == NULL ->
  * rows 0..n-1).  A warp loads 32 indices coalesced, then walks them by warp shuffle so that
  * each row is read by consecutive lanes; the 32x tw tile is transposed through shared memory
@@ -254,6 +266,12 @@ int imb_ppo_update(const imb_policy_desc* pol, float* pol_params, float* pol_nor
  * ActorCriticPolicy.evaluate_actions), written into the batch's last feature row. */
 int imb_policy_logp(const imb_policy_desc* pol, const float* pol_params, const float* pol_norm,
                     float* batch, int64_t ld, int64_t n, int32_t row_logp, void* stream);
+
+/* imb_disc_reduce + imb_disc_adam in one launch (last minibatch of an update; gradient taken from
+ * the workspace accumulator). */
+int imb_disc_reduce_adam(const imb_disc_desc* d, const imb_adam* opt, float* params, float* exp_avg,
+                         float* exp_avg_sq, float grad_div, float* ws, int64_t* state,
+                         float* stats_out, void* stream);
 
 /* ---- multi-GPU: replica state around the ONE all-reduce of a round ---------------------------
  * (the reference is single-process, so there is no reference interface to

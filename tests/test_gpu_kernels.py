@@ -223,8 +223,13 @@ def test_disc_update_matches_reference_golden(L, name):
                 L.disc_norm_update(d, batch, ld, n, NS, NC, ws)
             flags = (L.IMB_F_ZERO_GRAD if i == 0 else 0) | (L.IMB_F_TRAIN_NORM if has_norm else 0)
             L.disc_fwd_bwd(d, P, NS, batch, ld, n, mb, 1.0 / (2 * B), None, logits, flags, ws)
-            L.disc_reduce(d, ws, None)
-        L.disc_adam(d, opt, P, M, V, None, 1.0, ws, st, stats_out)
+            # odd steps take the fused reduce + Adam launch of the last minibatch, even steps the two separate ones
+            if s % 2 == 1 and start + mb >= B:
+                L.disc_reduce_adam(d, opt, P, M, V, 1.0, ws, st, stats_out)
+            else:
+                L.disc_reduce(d, ws, None)
+        if s % 2 == 0:
+            L.disc_adam(d, opt, P, M, V, None, 1.0, ws, st, stats_out)
         th.cuda.synchronize()
         got = dict(zip(order, stats_out.cpu().numpy()[:9]))
         want = dict(zip(keys, z[f"step{s}/stats"]))
@@ -641,3 +646,31 @@ def test_sync_pack_unpack_matches_torch_formulation(L):
     np.testing.assert_allclose(ranks[0]["mean"].cpu().numpy(), ns.mean.numpy(), rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(ranks[0]["var"].cpu().numpy(), ns.var.numpy(), rtol=1e-6, atol=1e-7)
     assert int(ranks[0]["count"]) == int(ns.count) == n0 + 256 + 512
+
+
+def test_fused_sample_gather_bit_identical_to_unfused(L):
+    """imb_disc_sample_gather (+ imb_sample_advance2) == 2 x imb_sample_indices + 2 x imb_gather_rows, over several
+    updates (epoch roll-over of the expert stream included) and two minibatches per update."""
+    rng = np.random.default_rng(5)
+    n_e, cap, tw, B, mb, seed = 1000, 512, 41, 192, 96, 1234
+    e_table = dev(rng.standard_normal((n_e, tw)).astype(np.float32))
+    ring = dev(rng.standard_normal((cap, tw)).astype(np.float32))
+    ld = 256
+    st_e1, st_g1, st_e2, st_g2 = (new_state(L) for _ in range(4))
+    for st in (st_g1, st_g2):
+        st[L.ST_RING_N] = 300  # ring not full yet: randint over the stored prefix
+    for upd in range(8):
+        a = th.zeros(tw + 1, ld, device="cuda")
+        b = th.zeros(tw + 1, ld, device="cuda")
+        idx_e = th.empty(B, dtype=th.int64, device="cuda")
+        idx_g = th.empty(B, dtype=th.int64, device="cuda")
+        L.sample_indices(1, idx_e, B, n_e, seed, st_e1)
+        L.sample_indices(0, idx_g, B, 0, seed, st_g1)
+        for start in range(0, B, mb):
+            L.gather_rows(e_table, n_e, tw, idx_e[start:start + mb], mb, a, ld, 0)
+            L.gather_rows(ring, cap, tw, idx_g[start:start + mb], mb, a, ld, mb)
+            L.disc_sample_gather(e_table, n_e, ring, cap, tw, mb, start, seed, st_e2, st_g2, b, ld)
+            np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy(), err_msg=f"update {upd} start {start}")
+        L.sample_advance2(B, n_e, st_e2, st_g2)
+        np.testing.assert_array_equal(st_e1.cpu().numpy(), st_e2.cpu().numpy())
+        np.testing.assert_array_equal(st_g1.cpu().numpy(), st_g2.cpu().numpy())
