@@ -76,12 +76,12 @@ struct NormLaunch {
 // inside the chunk, then the last CTA to finish merges all chunks in index order (Chan et al.)
 // and folds the batch into the running statistics exactly as util/networks.py:111-134 does.
 __global__ void __launch_bounds__(256) k_norm_stats(NormLaunch L, const float* __restrict__ batch, int64_t ld,
-                                                    int64_t n, float* __restrict__ run_mean_var,
+                                                    int64_t n, int chunk_rows, float* __restrict__ run_mean_var,
                                                     int32_t* __restrict__ count, float* __restrict__ snap_out,
                                                     float* __restrict__ part, unsigned int* __restrict__ ticket) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  const int64_t r0 = (int64_t)blockIdx.x * NORM_CHUNK;
-  const int64_t r1 = min(n, r0 + (int64_t)NORM_CHUNK);
+  const int64_t r0 = (int64_t)blockIdx.x * chunk_rows;
+  const int64_t r1 = min(n, r0 + (int64_t)chunk_rows);
   const int cn = (int)(r1 - r0);
   const int PS = 2 * IMB_MAX_DIN + 4;
   float* my = part + (int64_t)blockIdx.x * PS;
@@ -114,9 +114,12 @@ __global__ void __launch_bounds__(256) k_norm_stats(NormLaunch L, const float* _
   if (!is_last) return;
   __threadfence();
   const int32_t old_count = *count;
-  for (int k = threadIdx.x; k < L.din; k += blockDim.x) {
+  // warp per feature: every lane Chan-merges its chunks (lane, lane + 32, ...) in index order, then the 32 lane
+  // results are merged by a fixed butterfly (deterministic; a single thread walking all chunks cost more than
+  // the statistics themselves once the chunks became small enough to fill the GPU)
+  for (int k = warp; k < L.din; k += nw) {
     float na = 0.f, ma = 0.f, m2a = 0.f;
-    for (unsigned int c = 0; c < gridDim.x; ++c) {
+    for (unsigned int c = lane; c < gridDim.x; c += 32) {
       const float* p = part + (int64_t)c * PS;
       const float nb = __ldcg(p + 2 * IMB_MAX_DIN), mb = __ldcg(p + k), m2b = __ldcg(p + IMB_MAX_DIN + k);
       const float nt = na + nb;
@@ -125,21 +128,39 @@ __global__ void __launch_bounds__(256) k_norm_stats(NormLaunch L, const float* _
       m2a = m2a + m2b + dlt * dlt * (na * nb / nt);
       na = nt;
     }
-    const float b_mean = ma, b_var = m2a / na, b_n = na;
-    float mean = run_mean_var[k], var = run_mean_var[L.din + k];
-    const float cnt = (float)old_count;
-    const float tot = cnt + b_n;
-    const float delta = b_mean - mean;
-    mean += delta * b_n / tot;
-    var *= cnt;
-    var += b_var * b_n;
-    var += delta * delta * cnt * b_n / tot;
-    var /= tot;
-    run_mean_var[k] = mean;
-    run_mean_var[L.din + k] = var;
-    if (snap_out) {
-      snap_out[k] = mean;
-      snap_out[L.din + k] = var;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float nb = __shfl_xor_sync(0xffffffffu, na, o), mb = __shfl_xor_sync(0xffffffffu, ma, o),
+                  m2b = __shfl_xor_sync(0xffffffffu, m2a, o);
+      // merge (lower lane, higher lane) in that order on both sides so the pair agrees bit for bit
+      const bool lowme = (lane & o) == 0;
+      const float n1 = lowme ? na : nb, m1 = lowme ? ma : mb, q1 = lowme ? m2a : m2b;
+      const float n2 = lowme ? nb : na, m2v = lowme ? mb : ma, q2 = lowme ? m2b : m2a;
+      const float nt = n1 + n2;
+      if (nt > 0.f) {
+        const float dlt = m2v - m1;
+        ma = m1 + dlt * (n2 / nt);
+        m2a = q1 + q2 + dlt * dlt * (n1 * n2 / nt);
+      }
+      na = nt;
+    }
+    if (lane == 0) {
+      const float b_mean = ma, b_var = m2a / na, b_n = na;
+      float mean = run_mean_var[k], var = run_mean_var[L.din + k];
+      const float cnt = (float)old_count;
+      const float tot = cnt + b_n;
+      const float delta = b_mean - mean;
+      mean += delta * b_n / tot;
+      var *= cnt;
+      var += b_var * b_n;
+      var += delta * delta * cnt * b_n / tot;
+      var /= tot;
+      run_mean_var[k] = mean;
+      run_mean_var[L.din + k] = var;
+      if (snap_out) {
+        snap_out[k] = mean;
+        snap_out[L.din + k] = var;
+      }
     }
   }
   __syncthreads();
@@ -547,6 +568,17 @@ __global__ void __launch_bounds__(256) k_disc_reduce(int P, int G, const float* 
   }
 }
 
+// beta^n for an integer step count by repeated squaring (pow(double, double) costs microseconds on one thread)
+__device__ __forceinline__ double dpowi(double b, int64_t n) {
+  double r = 1.0;
+  while (n > 0) {
+    if (n & 1) r *= b;
+    b *= b;
+    n >>= 1;
+  }
+  return r;
+}
+
 // single block: every thread reads the step counter before thread 0 commits the increment (no race,
 // no extra launch); P <= ~8.5k parameters = a handful of iterations per thread.
 __global__ void __launch_bounds__(1024) k_disc_adam(int P, imb_adam opt, float* __restrict__ params,
@@ -559,8 +591,8 @@ __global__ void __launch_bounds__(1024) k_disc_adam(int P, imb_adam opt, float* 
   __shared__ float s_bc[2];
   if (threadIdx.x == 0) {
     const int64_t step = *step_io + 1;
-    const double bc1d = 1.0 - pow((double)opt.beta1, (double)step);
-    const double bc2d = 1.0 - pow((double)opt.beta2, (double)step);
+    const double bc1d = 1.0 - dpowi((double)opt.beta1, step);
+    const double bc2d = 1.0 - dpowi((double)opt.beta2, step);
     s_bc[0] = (float)((double)opt.lr / bc1d);
     s_bc[1] = (float)sqrt(bc2d);
     *step_io = step;
@@ -627,8 +659,8 @@ __global__ void __launch_bounds__(256) k_disc_reduce_adam(int P, int G, const fl
   __threadfence();
   if (threadIdx.x == 0) {
     const int64_t step = *step_io + 1;
-    const double bc1d = 1.0 - pow((double)opt.beta1, (double)step);
-    const double bc2d = 1.0 - pow((double)opt.beta2, (double)step);
+    const double bc1d = 1.0 - dpowi((double)opt.beta1, step);
+    const double bc2d = 1.0 - dpowi((double)opt.beta2, step);
     s_bc[0] = (float)((double)opt.lr / bc1d);
     s_bc[1] = (float)sqrt(bc2d);
     *step_io = step;
@@ -821,9 +853,12 @@ static int norm_launch(const imb_mlp& m, const short* rows, const float* batch, 
   NormLaunch NL;
   NL.din = m.din;
   for (int k = 0; k < m.din; ++k) NL.row[k] = rows[k];
-  const int chunks = (int)((n + NORM_CHUNK - 1) / NORM_CHUNK);
+  // chunk size: small enough to fill the GPU at the tuned batch sizes (16 384 rows -> 128 CTAs), larger for the
+  // multi-million-row sweeps so the chunk table stays bounded
+  const int chunk_rows = n <= (int64_t)128 * 2048 ? 128 : NORM_CHUNK;
+  const int chunks = (int)((n + chunk_rows - 1) / chunk_rows);
   IMB_REQUIRE(chunks >= 1 && chunks <= MAXCHUNKS, "norm update: n=%lld out of range", (long long)n);
-  k_norm_stats<<<chunks, 256, 0, st>>>(NL, batch, ld, n, norm_state + m.norm_off, norm_count + m.count_idx, snap,
+  k_norm_stats<<<chunks, 256, 0, st>>>(NL, batch, ld, n, chunk_rows, norm_state + m.norm_off, norm_count + m.count_idx, snap,
                                        ws + w.normpart, reinterpret_cast<unsigned int*>(ws + w.ticket));
   IMB_CHECK_LAUNCH("k_norm_stats");
   return 0;
