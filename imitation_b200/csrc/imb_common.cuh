@@ -190,6 +190,12 @@ __device__ __forceinline__ void st_async_v4(uint32_t remote_saddr, const float4&
                : "memory");
 }
 
+__device__ __forceinline__ void st_async_f32(uint32_t remote_saddr, float v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];" ::"r"(remote_saddr),
+               "f"(v), "r"(remote_mbar)
+               : "memory");
+}
+
 // tanh with ~1e-7 absolute error in a dozen instructions (tanhf's accurate path costs ~5x more and sits on
 // the critical path of every layer of the latency-bound PPO step): odd polynomial below 0.1, else
 // 1 - 2 / (exp(2x) + 1) with the hardware exponential; saturates correctly for large |x|.

@@ -163,9 +163,9 @@ __device__ __forceinline__ float sum8(const float (&d)[8]) {
 //     the ~8 dependent stages of the chain cost no CTA barrier;
 //   * weight gradients over the CTA's 8 rows: thread = (tower, unit, input subset), staged in local shared
 //     memory in the parameter layout, pushed to the slice owners through distributed shared memory with
-//     16-byte stores; owners sum the CL partials in fixed order and all-gather the summed slices;
-//   * every CTA then runs clip_grad_norm_ + Adam on the FULL vector (identical arithmetic everywhere, so the
-//     replicas never diverge).
+//     16-byte stores; owners sum the CL partials in fixed order, exchange the squared slice norms, run
+//     clip_grad_norm_ + Adam on their slice (the moments never leave their owner) and all-gather the new
+//     parameters into every CTA's copy.
 // No cluster barrier inside the step loop (the exchanged data signals mbarriers at the receivers), three CTA
 // barriers per optimiser step; the only global-memory traffic inside a step is the asynchronous minibatch prefetch.
 template <int HP>
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   __shared__ float red[32];
   __shared__ float bc[8];
   __shared__ __align__(8) uint64_t mbar[2];
-  __shared__ __align__(8) uint64_t xbar[2];  // [0]: partial gradients of the owned slice have arrived; [1]: all summed slices have
+  __shared__ __align__(8) uint64_t xbar[3];  // [0]: partial gradients of the owned slice arrived; [1]: all new parameter slices; [2]: all slice norms
+  __shared__ float SSQ[CL];                  // squared gradient norms of the 8 slices (each written by its owner)
   const imb_policy_desc& pd = A.pol;
   const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden, NP = pd.n_params, KP = A.KP, S = A.S;
   const PLay PL = make_play(pd);
@@ -198,9 +199,9 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   // ---- shared-memory carve-up (identical in every CTA: DSMEM addresses are rank + offset) ---------------
   int o = 0;
   float* Pm = smem + o; o += al(CL * S);        // parameters, P-layout, padded to CL slices
-  float* Ms = smem + o; o += al(CL * S);        // Adam moments (every CTA keeps the full vectors)
+  float* Ms = smem + o; o += al(CL * S);        // Adam moments (P-layout indexing; only the owned slice is live)
   float* Vs = smem + o; o += al(CL * S);
-  float* GP = smem + o; o += al(CL * S);        // own partial gradient; after barrier (a): the all-gathered sum
+  float* GP = smem + o; o += al(CL * S);        // own partial gradient (staging for the push)
   float* RECV = smem + o; o += al(CL * S);      // [source CTA][S]: partial gradients of the owned slice
   float* LOSS = smem + o; o += 32;              // [CL][3] partial loss sums (read by CTA 0)
   const int DAP = (Da + 3) / 4 * 4;
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     mbar_init(&mbar[1], 128);
     mbar_init(&xbar[0], 1);
     mbar_init(&xbar[1], 1);
+    mbar_init(&xbar[2], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -361,10 +363,12 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   // the next phase (a peer's next-phase data depends on data this CTA sends later).
   const uint32_t xbytes = (uint32_t)(CL * S * 4);
   const unsigned qmagic = (unsigned)(0x100000000ull / (unsigned)(S / 4)) + 1u;  // exact quotient for the < 2^16 quads here
-  const uint32_t recv_sa = smem_u32(RECV), gp_sa = smem_u32(GP), xbar0_sa = smem_u32(&xbar[0]), xbar1_sa = smem_u32(&xbar[1]);
+  const uint32_t recv_sa = smem_u32(RECV), pm_sa = smem_u32(Pm), ssq_sa = smem_u32(SSQ);
+  const uint32_t xbar0_sa = smem_u32(&xbar[0]), xbar1_sa = smem_u32(&xbar[1]), xbar2_sa = smem_u32(&xbar[2]);
   if (tid == 0) {
     mbar_expect_tx(&xbar[0], xbytes);
     mbar_expect_tx(&xbar[1], xbytes);
+    mbar_expect_tx(&xbar[2], (uint32_t)(CL * 4));
   }
   cluster.sync();
 
@@ -700,56 +704,62 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     if (tid == 0) mbar_expect_tx(&xbar[0], xbytes);  // re-arm for the next step
     PPO_TICK(9);
 
-    // ---- 4. slice owners: sum the CL partials in fixed order, all-gather the summed slice --------------------------
-    for (int i0 = 4 * tid; i0 < S; i0 += 4 * PT) {
-      float4 g = ld4(RECV + i0);
+    // ---- 4. slice owners: sum the CL partials in fixed order (one quad per thread), exchange the squared slice
+    //         norms for clip_grad_norm_ (4 bytes to every CTA, same st.async + mbarrier mechanism) ------------------------
+    const int i0 = 4 * tid;
+    const bool own = i0 < S;  // S / 4 <= PT is checked by the launcher
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ss = 0.f;
+    if (own) {
+      g = ld4(RECV + i0);
 #pragma unroll
       for (int c = 1; c < CL; ++c) {  // fixed order: deterministic
         const float4 t = ld4(RECV + c * S + i0);
         g.x += t.x, g.y += t.y, g.z += t.z, g.w += t.w;
       }
-#pragma unroll
-      for (int c = 0; c < CL; ++c) {  // rotated start: the 8 owners write to 8 different CTAs at a time
-        const int dstc = (crank + c) & (CL - 1);
-        st_async_v4(mapa_u32(gp_sa + (uint32_t)(crank * S + i0) * 4u, dstc), g, mapa_u32(xbar1_sa, dstc));
-      }
+      ss = (g.x * g.x + g.y * g.y) + (g.z * g.z + g.w * g.w);
     }
+    const float my_ssq = block_sum(ss, red);
+    if (tid < CL) st_async_f32(mapa_u32(ssq_sa + (uint32_t)crank * 4u, tid), my_ssq, mapa_u32(xbar2_sa, tid));
     PPO_TICK(10);
-    mbar_wait(&xbar[1], (uint32_t)(gs & 1));  // every summed slice has landed in GP
-    if (tid == 0) mbar_expect_tx(&xbar[1], xbytes);  // re-arm for the next step
+    mbar_wait(&xbar[2], (uint32_t)(gs & 1));
+    if (tid == 0) mbar_expect_tx(&xbar[2], (uint32_t)(CL * 4));  // re-arm for the next step
     PPO_TICK(11);
 
-    // ---- 5. clip_grad_norm_ + Adam on the full vector, identically in every CTA ------------------------------------------
-    float ss = 0.f;
-    for (int i0 = 4 * tid; i0 < CL * S; i0 += 4 * PT) {
-      const float4 g = ld4(GP + i0);
-      ss = fmaf(g.x, g.x, ss);
-      ss = fmaf(g.y, g.y, ss);
-      ss = fmaf(g.z, g.z, ss);
-      ss = fmaf(g.w, g.w, ss);
-    }
-    const float total = sqrtf(block_sum(ss, red));
+    // ---- 5. clip_grad_norm_ + Adam on the OWNED slice (moments never leave their owner); the new parameters are
+    //         all-gathered into every CTA's parameter vector ----------------------------------------------------------
+    float total = 0.f;
+#pragma unroll
+    for (int c = 0; c < CL; ++c) total += SSQ[c];  // same order everywhere: the replicas' clip factors agree bit for bit
+    total = sqrtf(total);
     float clip = A.hp.max_grad_norm / (total + 1e-6f);
     clip = clip > 1.0f ? 1.0f : clip;
-    const float step_size = bc[2 * cur], inv_bc2s = rcp_fast(bc[2 * cur + 1]);
-    for (int i0 = 4 * tid; i0 < CL * S; i0 += 4 * PT) {
-      const float4 g4 = ld4(GP + i0), m4 = ld4(Ms + i0), v4 = ld4(Vs + i0), p4 = ld4(Pm + i0);
+    if (own) {
+      const float step_size = bc[2 * cur], inv_bc2s = rcp_fast(bc[2 * cur + 1]);
+      const int q0 = crank * S + i0;
+      const float4 m4 = ld4(Ms + q0), v4 = ld4(Vs + q0), p4 = ld4(Pm + q0);
       // approximate sqrt / division (~1e-7 relative on an update that is itself ~lr relative to the weights)
-      auto adam1 = [&](float g, float& m, float& v, float& pw) {
-        g *= clip;
-        m = m + (g - m) * (1.0f - 0.9f);
-        v = v * 0.999f + (1.0f - 0.999f) * g * g;
+      auto adam1 = [&](float gg, float& m, float& v, float& pw) {
+        gg *= clip;
+        m = m + (gg - m) * (1.0f - 0.9f);
+        v = v * 0.999f + (1.0f - 0.999f) * gg * gg;
         pw -= step_size * __fdividef(m, fmaf(sqrt_fast(v), inv_bc2s, A.hp.adam_eps));
       };
       float4 m = m4, v = v4, pw = p4;
-      adam1(g4.x, m.x, v.x, pw.x);
-      adam1(g4.y, m.y, v.y, pw.y);
-      adam1(g4.z, m.z, v.z, pw.z);
-      adam1(g4.w, m.w, v.w, pw.w);
-      st4(Ms + i0, m);
-      st4(Vs + i0, v);
-      st4(Pm + i0, pw);
+      adam1(g.x, m.x, v.x, pw.x);
+      adam1(g.y, m.y, v.y, pw.y);
+      adam1(g.z, m.z, v.z, pw.z);
+      adam1(g.w, m.w, v.w, pw.w);
+      st4(Ms + q0, m);
+      st4(Vs + q0, v);
+#pragma unroll
+      for (int c = 0; c < CL; ++c) {  // rotated start: the 8 owners write to 8 different CTAs at a time
+        const int dstc = (crank + c) & (CL - 1);
+        st_async_v4(mapa_u32(pm_sa + (uint32_t)q0 * 4u, dstc), pw, mapa_u32(xbar1_sa, dstc));
+      }
     }
+    mbar_wait(&xbar[1], (uint32_t)(gs & 1));  // every CTA's new parameter slice has landed in Pm
+    if (tid == 0) mbar_expect_tx(&xbar[1], xbytes);  // re-arm for the next step
     PPO_TICK(12);
     ep_now = ep_next;
     start = start_next;
@@ -764,13 +774,15 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
 #endif
 
   // ---- write back (CTA 0): parameters and moments in torch order, norm state, counters ------------------------------
-  if (crank == 0) {
-    for (int p = tid; p < NP; p += PT) {
-      const int q = flat_to_play(pd, PL, p);
-      g_params[p] = Pm[q];
+  for (int p = tid; p < NP; p += PT) {  // moments live with their slice owner
+    const int q = flat_to_play(pd, PL, p);
+    if (q / S == crank) {
       g_m[p] = Ms[q];
       g_v[p] = Vs[q];
     }
+  }
+  if (crank == 0) {
+    for (int p = tid; p < NP; p += PT) g_params[p] = Pm[flat_to_play(pd, PL, p)];
     if (pd.has_norm) {
       if (tid < Do) {
         g_norm[tid] = rstat[tid];
@@ -891,6 +903,7 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
   A.HP = 32;
   A.KP = A.pol.d_obs <= 32 ? 32 : 64;
   A.S = ((make_play(A.pol).total + CL - 1) / CL + 3) / 4 * 4;
+  IMB_REQUIRE(A.S / 4 <= PT, "policy too large for the PPO update kernel (%d parameters per slice)", A.S);
   IMB_REQUIRE(A.rw % 4 == 0, "rollout row width must be a multiple of 4 floats (bulk row copies)");
   A.RS2 = ((A.rw + 4) % 8 == 4) ? A.rw + 4 : A.rw + 8;
   const size_t fl = ppo_smem_floats(A);

@@ -12,8 +12,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from imitation_b200 import _desc, _lib  # noqa: E402
 
 NAMES = ["top barrier", "next-step stats (shadow of barrier a)", "-", "warp chain fwd/loss/bwd", "-", "-", "-",
-         "weight gradients -> GP", "push partials", "barrier a wait", "slice sum + all-gather", "barrier b",
-         "ssq + clip + Adam", "-"]
+         "weight gradients -> GP", "push partials", "barrier a wait", "slice sum + norm exchange issue", "wait: slice norms landed",
+         "clip + Adam (own slice) + parameter all-gather + wait", "-"]
 pd = _desc.policy_desc(17, 6, False, 32, True)
 N = 4096
 rw = _lib.rollout_row_width(pd)
