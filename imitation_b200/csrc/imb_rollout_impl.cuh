@@ -77,11 +77,13 @@ __device__ void load_policy_img(float* sm, const PolImg& S, const imb_policy_des
   const int Do = pd.d_obs, Da = pd.d_act, h = pd.hidden;
   for (int i = tid; i < S.total; i += nt) sm[i] = 0.f;
   __syncthreads();
+#pragma unroll 4
   for (int i = tid; i < h * Do; i += nt) {
     const int j = i / Do, k = i - j * Do;
     sm[S.w1p + k * HP + j] = q[pd.off_pi_w1 + i];
     sm[S.w1v + k * HP + j] = q[pd.off_vf_w1 + i];
   }
+#pragma unroll 4
   for (int i = tid; i < h * h; i += nt) {
     const int j = i / h, ii = i - j * h;
     sm[S.w2p + ii * HP + j] = q[pd.off_pi_w2 + i];
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(RT, 1) k_rollout(const RolloutArgs A, const Di
     if (!rowthread) {
       // (threads beyond the tile's rows only take part in the tiled layers)
     } else if (!A.pol.discrete) {
+      float z4[4] = {0.f, 0.f, 0.f, 0.f};
       for (int a = 0; a < Da; ++a) {
         float m0 = 0.f, m1 = 0.f;
         const float* wa = psm + S.wa + a * HP;
@@ -298,9 +301,9 @@ __global__ void __launch_bounds__(RT, 1) k_rollout(const RolloutArgs A, const Di
         }
         if (j < h) m0 = fmaf(wa[j], H2[j * RRS + rt], m0);
         const float m = psm[S.ba + a] + (m0 + m1);
-        const float z = A.deterministic ? 0.f
-                        : noise   ? (live ? noise[(t * E + e) * Da + a] : 0.f)
-                                  : philox_normal(A.env.seed, IMB_STREAM_ACT_NOISE, egid, (uint32_t)(gstep0 + t), a);
+        if (!A.deterministic && !noise && (a & 3) == 0)
+          philox_normal4(A.env.seed, IMB_STREAM_ACT_NOISE, egid, (uint32_t)(gstep0 + t), a >> 2, z4);
+        const float z = A.deterministic ? 0.f : noise ? (live ? noise[(t * E + e) * Da + a] : 0.f) : ((a & 3) == 0 ? z4[0] : (a & 3) == 1 ? z4[1] : (a & 3) == 2 ? z4[2] : z4[3]);
         const float ls = psm[S.lstd + a];
         const float sd = expf(ls);
         const float act = fmaf(sd, z, m);

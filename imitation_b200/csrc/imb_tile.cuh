@@ -138,7 +138,10 @@ __device__ void load_timg(float* sm, const PassDesc& p, int JP, const float* __r
   for (int i = tid; i < TImg::mean(din, JP); i += nt) sm[i] = 0.f;
   __syncthreads();
   int off = 0, hl = din;
+  // (loops unrolled so that the global loads of 8 iterations are in flight together: the image build is the
+  //  whole prologue of a CTA that processes a single tile)
   if (p.n_hidden >= 1) {
+#pragma unroll 8
     for (int i = tid; i < p.h1 * din; i += nt) {
       const int j = i / din, k = i - j * din;
       sm[TImg::w1t(din, JP) + k * JP + j] = q[off + i];
@@ -149,6 +152,7 @@ __device__ void load_timg(float* sm, const PassDesc& p, int JP, const float* __r
     hl = p.h1;
   }
   if (p.n_hidden >= 2) {
+#pragma unroll 8
     for (int i = tid; i < p.h2 * p.h1; i += nt) {
       const int j = i / p.h1, ii = i - j * p.h1;
       const float v = q[off + i];
