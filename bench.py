@@ -42,6 +42,10 @@ CFG = dict(d_obs=17, d_act=6, horizon=1000, envs_per_gpu=1024, ppo_batch=4096, p
                     learning_rate=0.00026250519057717037, max_grad_norm=0.8, vf_coef=0.11483689492120866))
 
 
+PPO_DRAM_BYTES_NCU = 598528 + 0       # bytes per launch, profiles/ncu_ppo_r01k_selected.csv (read + write)
+DISC_DRAM_BYTES_NCU_16K = 1611776 + 0  # k_disc_fwdbwd at 16 384 rows, profiles/ncu_disc_r01k_selected.csv
+
+
 # -------------------------------------------------------------------------------------------------
 def synth_expert(env_params: np.ndarray, d_obs, d_act, horizon, n_episodes, seed):
     """Synthetic expert: fixed random linear-tanh policy + small noise, rolled out in the env."""
@@ -420,7 +424,10 @@ def main():
         ach = ppo_bytes / (ms_ppo / 1e3) / 1e9
         roof = {"kernel": "k_ppo_update (persistent 8-CTA cluster, DSMEM gradient exchange; PPO.train = 320 sequential "
                           "minibatch steps)",
-                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this
+                # configuration (profiles/ncu_ppo_r01k_selected.csv): the rollout table stays in L2
+                "traffic": PPO_DRAM_BYTES_NCU if (cfg["envs_per_gpu"], cfg["ppo_epochs"]) == (1024, 5) else None,
                 "peak_source": peak_src, "ms_per_launch": ms_ppo, "share_of_step": ms_ppo / (ms / K),
                 "algorithmic_bytes_per_launch": ppo_bytes,
                 "note": "latency-bound by construction: 320 dependent optimiser steps of 64 rows each (1.3 MFLOP, 6.6 KB "
@@ -444,7 +451,8 @@ def main():
         ach_d = disc_bytes / (ms_d / 1e3) / 1e9
         roof_disc = {"kernel": "k_disc_fwdbwd<32> (fused BasicRewardNet fwd + BCE + bwd), 2^20 rows, Din 23, 32x32",
                      "bound": "hbm", "achieved": ach_d, "peak": peak, "unit": "GB/s", "frac": ach_d / peak,
-                     "traffic": None, "ms_per_launch": ms_d, "algorithmic_bytes_per_row": 96,
+                     "traffic": None, "traffic_at_16384_rows": DISC_DRAM_BYTES_NCU_16K,
+                     "algorithmic_bytes_at_16384_rows": 16384 * 96, "ms_per_launch": ms_d, "algorithmic_bytes_per_row": 96,
                      "fp32_tflops": n_big * 9280 / (ms_d / 1e3) / 1e12,
                      "note": "includes the gradient-accumulator memset node; fp32 FFMA path: compute-bound at "
                              "9280 flop/row (AI 97 flop/B; fp32 peak ~72 TFLOP/s = 11% of the HBM roofline) -- DESIGN.md"}
