@@ -124,28 +124,69 @@ enum { ACT_TANH = 0, ACT_RELU = 1 };
 
 // OUT[j][r] = act(bias[j] + sum_k A[k][r] * Wk[k][j]) for j < JPx (multiple of 32); 128 threads:
 // warp -> 8-column group, lane -> RPL consecutive rows.
+// rows per tile for a rows-per-lane parameter (RPL = 0: the 8-row tile, lane = (row, column pair))
+__host__ __device__ constexpr int rows_of(int rpl) { return rpl == 0 ? 8 : 32 * rpl; }
+
+// 8-row tile: warp -> 8-column group, lane -> (row = lane % 8, columns 2 * (lane / 8), +1): two FMAs per input and
+// lane, so a layer's latency is ~K x 10 cycles and the grid covers all SMs at 1024 envs (128 CTAs)
+template <int ACT>
+__device__ __forceinline__ void tile_layer8(const float* __restrict__ A, int K, const float* __restrict__ Wk, int wld,
+                                            const float* __restrict__ bias, float* __restrict__ OUT, int JPx) {
+  constexpr int RRS = 8 + TILE_PAD;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = lane & 7, c2 = 2 * (lane >> 3);
+  for (int jh = 0; jh < JPx / 32; ++jh) {
+    const int j0 = jh * 32 + warp * 8 + c2;
+    float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;  // two accumulator pairs (even / odd k)
+    int k = 0;
+#pragma unroll 4
+    for (; k + 2 <= K; k += 2) {
+      const float x0 = A[k * RRS + r], x1 = A[(k + 1) * RRS + r];
+      const float2 w0 = *reinterpret_cast<const float2*>(Wk + k * wld + j0);
+      const float2 w1 = *reinterpret_cast<const float2*>(Wk + (k + 1) * wld + j0);
+      a0 = fmaf(x0, w0.x, a0);
+      a1 = fmaf(x0, w0.y, a1);
+      b0 = fmaf(x1, w1.x, b0);
+      b1 = fmaf(x1, w1.y, b1);
+    }
+    if (k < K) {
+      const float x0 = A[k * RRS + r];
+      const float2 w0 = *reinterpret_cast<const float2*>(Wk + k * wld + j0);
+      a0 = fmaf(x0, w0.x, a0);
+      a1 = fmaf(x0, w0.y, a1);
+    }
+    const float z0 = (a0 + b0) + bias[j0], z1 = (a1 + b1) + bias[j0 + 1];
+    OUT[j0 * RRS + r] = ACT == ACT_TANH ? tanh_fast(z0) : fmaxf(z0, 0.f);
+    OUT[(j0 + 1) * RRS + r] = ACT == ACT_TANH ? tanh_fast(z1) : fmaxf(z1, 0.f);
+  }
+}
+
 template <int ACT, int RPL>
 __device__ __forceinline__ void tile_layer(const float* __restrict__ A, int K, const float* __restrict__ Wk, int wld,
                                            const float* __restrict__ bias, float* __restrict__ OUT, int JPx) {
+  if (RPL == 0) {
+    tile_layer8<ACT>(A, K, Wk, wld, bias, OUT, JPx);
+    return;
+  }
   constexpr int RRS = 32 * RPL + TILE_PAD;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r0 = lane * RPL;
   for (int jh = 0; jh < JPx / 32; ++jh) {
     const int j0 = jh * 32 + warp * 8;
-    float acc[RPL][8];
+    float acc[RPL > 0 ? RPL : 1][8];
 #pragma unroll
     for (int a = 0; a < RPL; ++a)
 #pragma unroll
       for (int t = 0; t < 8; ++t) acc[a][t] = 0.f;
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-      float av[RPL];
+      float av[RPL > 0 ? RPL : 1];
       if (RPL == 4) {
         const float4 a4 = ld4(A + k * RRS + r0);
-        av[0] = a4.x, av[1 % RPL] = a4.y, av[2 % RPL] = a4.z, av[3 % RPL] = a4.w;
+        av[0] = a4.x, av[RPL > 1 ? 1 : 0] = a4.y, av[RPL > 2 ? 2 : 0] = a4.z, av[RPL > 3 ? 3 : 0] = a4.w;
       } else if (RPL == 2) {
         const float2 a2 = *reinterpret_cast<const float2*>(A + k * RRS + r0);
-        av[0] = a2.x, av[1 % RPL] = a2.y;
+        av[0] = a2.x, av[RPL > 1 ? 1 : 0] = a2.y;
       } else {
         av[0] = A[k * RRS + r0];
       }
@@ -177,7 +218,7 @@ __global__ void __launch_bounds__(RT, 1) k_rollout(const RolloutArgs A, const Di
                                                    float* __restrict__ ring, float* __restrict__ flat_out,
                                                    float* __restrict__ aux, const float* __restrict__ noise,
                                                    const int64_t* __restrict__ state) {
-  constexpr int RR = 32 * RPL, RRS = RR + TILE_PAD;
+  constexpr int RR = rows_of(RPL), RRS = RR + TILE_PAD;
   extern __shared__ __align__(128) float smem[];
   const int tid = threadIdx.x;
   const int rt = tid < RR ? tid : RR - 1;  // tile row of this thread in the thread-per-env parts (threads >= RR idle there)
@@ -524,7 +565,7 @@ static int launch_rollout_t(RolloutArgs A, const DiscLaunch& L, const float* env
                             const float* pol_params, const float* pol_norm, const float* disc_params, float* rollout,
                             float* ring, float* flat_out, float* aux, const float* noise, const int64_t* state,
                             cudaStream_t st) {
-  constexpr int RR = 32 * RPL, RRS = RR + TILE_PAD;
+  constexpr int RR = rows_of(RPL), RRS = RR + TILE_PAD;
   auto al = [](int x) { return (x + 31) / 32 * 32; };
   const int Do = A.env.d_obs, Da = A.env.d_act;
   A.HP = A.pol.hidden <= 32 ? 32 : 64;
@@ -585,6 +626,7 @@ static int launch_rollout(const RolloutArgs& A, const DiscLaunch& L, const float
 #define IMB_RL(R) \
   return launch_rollout_t<R>(A, L, env_params, env_obs, pol_params, pol_norm, disc_params, rollout, ring, flat_out, aux, \
                              noise, state, st)
+  if (A.E <= sms * 8 * 2) IMB_RL(0);
   if (A.E <= sms * 32) IMB_RL(1);
   if (A.E <= sms * 64 * 2) IMB_RL(2);
   IMB_RL(4);
