@@ -17,6 +17,7 @@ IMB_MAX_HIDDEN = 64
 IMB_MAX_DIN = 64
 IMB_F_ZERO_GRAD = 1
 IMB_F_TRAIN_NORM = 2
+IMB_RF_DETERMINISTIC = 1  # imb_rollout flags
 
 # device-resident counter block (include/imb.h enum)
 ST_RING_IDX, ST_RING_N, ST_EP_STEP, ST_EPISODE, ST_GLOBAL_STEP, ST_REPLAY_DRAW = 0, 1, 2, 3, 4, 5

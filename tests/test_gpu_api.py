@@ -365,3 +365,97 @@ def test_host_compat_sampling_is_bit_exact_with_reference_streams():
     z = G.load("replay_buffer")
     np.random.seed(5)
     np.testing.assert_array_equal(np.random.randint(512, size=8192), z["randint_512_x8192"])
+
+
+# ---- the steps after the path: evaluation rollouts, rollout_stats, checkpoint round trip ---------------
+def _port_policy_from(policy, Do, Da):
+    from oracle import ppo_port
+
+    pol = ppo_port.ActorCriticPort(Do, Da)
+    psd = {k: v.cpu() for k, v in policy.state_dict().items()}
+    pol.load_state_dict({"pi.0.weight": psd["mlp_extractor.policy_net.0.weight"],
+                         "pi.0.bias": psd["mlp_extractor.policy_net.0.bias"],
+                         "pi.2.weight": psd["mlp_extractor.policy_net.2.weight"],
+                         "pi.2.bias": psd["mlp_extractor.policy_net.2.bias"],
+                         "vf.0.weight": psd["mlp_extractor.value_net.0.weight"],
+                         "vf.0.bias": psd["mlp_extractor.value_net.0.bias"],
+                         "vf.2.weight": psd["mlp_extractor.value_net.2.weight"],
+                         "vf.2.bias": psd["mlp_extractor.value_net.2.bias"],
+                         "action_net.weight": psd["action_net.weight"], "action_net.bias": psd["action_net.bias"],
+                         "value_net.weight": psd["value_net.weight"], "value_net.bias": psd["value_net.bias"],
+                         "log_std": psd["log_std"]})
+    return pol
+
+
+def test_generate_trajectories_and_rollout_stats_match_oracle():
+    """rollout.generate_trajectories(deterministic_policy=True) + rollout_stats on the device VecEnv vs the CPU
+    restatement of the same env / policy stepped by hand (data/rollout.py:382-560 semantics: whole episodes,
+    terminal observation appended, clipped actions recorded, trajectories shuffled with the caller's rng)."""
+    from imitation_b200.data import rollout
+    from oracle import synth_env
+
+    E, H, Do, Da = 5, 12, 7, 3
+    tr, _ = _mk(Do=Do, Da=Da, E=E, T=4, H=H, B=16, net_kwargs={}, seed=4)
+    from imitation_b200 import _lib
+
+    # a second reset() of the device env starts the next episode of its counter-based reset stream
+    ep0 = int(tr.venv.state[_lib.ST_EPISODE]) + (1 if tr.venv._reset_done else 0)
+    trajs = rollout.generate_trajectories(tr.policy, tr.venv, rollout.make_min_episodes(2 * E),
+                                          np.random.default_rng(7), deterministic_policy=True)
+    assert len(trajs) == 2 * E and all(len(t) == H and t.terminal for t in trajs)
+    spec = synth_env.SynthEnvSpec(Do, Da, horizon=H, seed=4)
+    venv = synth_env.SynthVecEnv(spec, E)
+    venv.episode[:] = ep0
+    pol = _port_policy_from(tr.policy, Do, Da)
+    want = []
+    obs = venv.reset()
+    for _ in range(2):  # two consecutive episodes per env (auto-reset)
+        O, Ac, R = [obs], [], []
+        for t in range(H):
+            with th.no_grad():
+                act = pol.forward(th.as_tensor(obs), deterministic=True)[0].numpy()
+            act = np.clip(act, -1.0, 1.0)
+            venv.step_async(act)
+            nobs, rew, done, infos = venv.step_wait()
+            Ac.append(act), R.append(rew)
+            O.append(np.stack([i["terminal_observation"] for i in infos]) if done.all() else nobs)
+            obs = nobs
+        for e in range(E):
+            want.append(dict(obs=np.stack([o[e] for o in O]), acts=np.stack([a[e] for a in Ac]),
+                             rews=np.asarray([r[e] for r in R], np.float32)))
+    np.random.default_rng(7).shuffle(want)
+    for got, w in zip(trajs, want):
+        np.testing.assert_allclose(got.obs, w["obs"], rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(got.acts, w["acts"], rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(got.rews, w["rews"], rtol=1e-3, atol=2e-4)
+    stats = rollout.rollout_stats(trajs)
+    rets = np.asarray([w["rews"].sum() for w in want])
+    assert stats["n_traj"] == 2 * E and stats["len_mean"] == H and stats["len_min"] == H
+    np.testing.assert_allclose([stats["return_mean"], stats["return_std"], stats["return_min"], stats["return_max"]],
+                               [rets.mean(), rets.std(), rets.min(), rets.max()], rtol=1e-3, atol=1e-3)
+
+
+def test_checkpoint_round_trip_through_state_dicts():
+    """th.save / load_state_dict of reward net and policy (scripts/train_adversarial.py:25-35): a fresh trainer loaded
+    from the checkpoint continues bit-identically (the fused engines re-alias the loaded tensors)."""
+    tr, _ = _mk(E=8, T=4, B=32, seed=6, norm_features=True)
+    tr.train(2 * tr.gen_train_timesteps)
+    buf = io.BytesIO()
+    th.save({"reward": tr._reward_net.state_dict(), "policy": tr.policy.state_dict()}, buf)
+    buf.seek(0)
+    ck = th.load(buf)
+    tr2, _ = _mk(E=8, T=4, B=32, seed=6, norm_features=True)
+    tr2._reward_net.load_state_dict(ck["reward"])
+    tr2.policy.load_state_dict(ck["policy"])
+    for (k, a), (_, b) in zip(tr._reward_net.state_dict().items(), tr2._reward_net.state_dict().items()):
+        assert th.equal(a, b), k
+    for (k, a), (_, b) in zip(tr.policy.state_dict().items(), tr2.policy.state_dict().items()):
+        assert th.equal(a, b), k
+    # the kernels see the loaded values: identical reward predictions and policy log-probs on the same inputs
+    rng = np.random.default_rng(0)
+    obs = rng.standard_normal((16, 17)).astype(np.float32)
+    acts = rng.uniform(-1, 1, (16, 6)).astype(np.float32)
+    nobs = rng.standard_normal((16, 17)).astype(np.float32)
+    done = np.zeros(16, bool)
+    np.testing.assert_array_equal(tr.reward_train.predict(obs, acts, nobs, done),
+                                  tr2.reward_train.predict(obs, acts, nobs, done))
