@@ -132,3 +132,61 @@ def test_round_sync_world2_gloo():
         th.testing.assert_close(m, union.mean(0), rtol=1e-5, atol=1e-6)
         th.testing.assert_close(v, union.var(0, unbiased=False), rtol=1e-5, atol=1e-6)
         assert c == len(union)
+
+
+def test_demo_ingest_npz_round_trip(tmp_path):
+    """data/serialize: the legacy .npz layout (indices-split, one extra observation per trajectory) round-trips and
+    flattens into the transition arrays the device expert table is built from."""
+    from imitation_b200.data import serialize, types
+
+    rng = np.random.default_rng(0)
+    trajs = []
+    for n, term in ((5, True), (3, False), (7, True)):
+        trajs.append(types.TrajectoryWithRew(obs=rng.standard_normal((n + 1, 4)).astype(np.float32),
+                                             acts=rng.integers(0, 2, n), infos=None, terminal=term,
+                                             rews=rng.standard_normal(n).astype(np.float32)))
+    p = tmp_path / "demos" / "final.npz"
+    serialize.save(p, trajs)
+    raw = np.load(p, allow_pickle=True)
+    np.testing.assert_array_equal(raw["indices"], [5, 8])  # the reference's split points (serialize.py:56-60)
+    assert raw["obs"].shape == (5 + 3 + 7 + 3, 4)
+    back = serialize.load_with_rewards(p)
+    assert len(back) == 3
+    for a, b in zip(trajs, back):
+        np.testing.assert_array_equal(a.obs, b.obs)
+        np.testing.assert_array_equal(a.acts, b.acts)
+        np.testing.assert_array_equal(a.rews, b.rews)
+        assert a.terminal == b.terminal
+    flat = types.flatten_trajectories(back)
+    assert len(flat) == 15 and flat.dones.sum() == 2 and flat.dones[4] and flat.dones[14] and not flat.dones[7]
+    np.testing.assert_array_equal(flat.next_obs[:5], trajs[0].obs[1:])
+
+
+@pytest.mark.refsrc
+def test_demo_ingest_reads_reference_npz_fixture():
+    """The reference's own legacy-format fixture (tests/testdata/npz_format_rollout.npz) loads with the same split
+    the reference applies (container-only: /root/reference is not on the GPU box)."""
+    import os
+
+    from imitation_b200.data import serialize
+
+    path = "/root/reference/tests/testdata/npz_format_rollout.npz"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    with open(path, "rb") as f:
+        if f.read(7) == b"version":
+            pytest.skip("fixture is a git-lfs pointer in this checkout")
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        trajs = serialize.load_with_rewards(path)
+    raw = np.load(path, allow_pickle=True)
+    idx = raw["indices"]
+    want_obs = np.split(raw["obs"], idx + np.arange(len(idx)) + 1)
+    want_acts = np.split(raw["acts"], idx)
+    assert len(trajs) == len(want_acts) == len(raw["terminal"])
+    for t, o, a in zip(trajs, want_obs, want_acts):
+        np.testing.assert_array_equal(t.obs, o)
+        np.testing.assert_array_equal(t.acts, a)
+        assert len(t.obs) == len(t.acts) + 1
