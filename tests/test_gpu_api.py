@@ -459,3 +459,50 @@ def test_checkpoint_round_trip_through_state_dicts():
     done = np.zeros(16, bool)
     np.testing.assert_array_equal(tr.reward_train.predict(obs, acts, nobs, done),
                                   tr2.reward_train.predict(obs, acts, nobs, done))
+
+
+# ---- BASELINE.json's full size, through size-independent properties ----------------------------------------------------
+def test_full_size_round_properties():
+    """The bench configuration (1024 envs x 4 steps, demo batch 8192, replay capacity 512, 8 disc updates per round,
+    PPO 4096 / 64 / 5 epochs): captured-graph rounds == eager rounds bit for bit; the generator ring holds exactly
+    the tail of the reference's flattened order (Buffer.store truncation, data/buffer.py:174-178); counters and
+    statistics obey the closed forms."""
+    from imitation_b200 import _lib
+
+    E, T, B, cap, nd = 1024, 4, 8192, 512, 8
+    kw = dict(E=E, T=T, H=1000, B=B, cap=cap, n_disc=nd, norm_features=True, seed=9)
+    a, _ = _mk(**kw)
+    b, _ = _mk(**kw)
+    for tr in (a, b):
+        tr.gen_algo.batch_size, tr.gen_algo.n_epochs = 64, 5
+        tr.gen_algo.hp.batch_size, tr.gen_algo.hp.n_epochs = 64, 5
+        tr.train(2 * E * T)
+    b.capture_round()
+    for _ in range(2):
+        a.train(E * T)
+        stats = b.replay_round()
+    th.cuda.synchronize()
+    for p, q in zip(a._reward_net.parameters(), b._reward_net.parameters()):
+        th.testing.assert_close(p, q, rtol=0, atol=0)
+    for p, q in zip(a.policy.parameters(), b.policy.parameters()):
+        th.testing.assert_close(p, q, rtol=0, atol=0)
+    th.testing.assert_close(a.venv.state, b.venv.state, rtol=0, atol=0)
+    st = a.venv.state.cpu().numpy()
+    rounds = 4
+    assert st[_lib.ST_EP_STEP] == rounds * T and st[_lib.ST_EPISODE] == 0 and st[_lib.ST_GLOBAL_STEP] == rounds * T
+    assert st[_lib.ST_RING_N] == cap and st[_lib.ST_RING_IDX] == (rounds * cap) % cap
+    assert st[_lib.ST_REPLAY_DRAW] == rounds * nd and st[_lib.ST_DISC_STEP] == rounds * nd
+    assert st[_lib.ST_PPO_STEP] == rounds * 5 * (E * T // 64) and st[_lib.ST_PPO_EPOCH] == rounds * 5
+    # ring = last `cap` rows of the flattened rollout: envs E - cap/T .. E-1, T consecutive steps each, no terminal rows
+    ring = a._gen_replay_buffer.table.cpu().numpy()
+    Do, Da = 17, 6
+    assert ring.shape[0] == cap and not ring[:, -1].any()
+    obs, nobs = ring[:, :Do].reshape(cap // T, T, Do), ring[:, Do + Da:2 * Do + Da].reshape(cap // T, T, Do)
+    np.testing.assert_array_equal(obs[:, 1:], nobs[:, :-1])  # consecutive steps of one env are adjacent rows
+    last = a.venv.obs.t().cpu().numpy()[E - cap // T:]       # current env state = next_obs of each env's last row
+    np.testing.assert_array_equal(nobs[:, -1], last)
+    # statistics of the last update: both halves have demo_batch_size rows, accuracies are proportions
+    s = stats[-1, :9].cpu().numpy()
+    assert s[7] == B and s[8] == B and 0.0 <= s[1] <= 1.0 and abs(s[5] - 0.5) < 1e-6 and np.isfinite(s).all()
+    # feature RunningNorm of the policy: every PPO minibatch row counted once per epoch
+    assert int(a.policy.flat_vectors()[2][0]) == rounds * 5 * E * T
