@@ -280,6 +280,7 @@ def main():
         for _ in range(cfg["n_disc"]):
             tr.train_disc_async(check_ring=False)
         tr.disc_train_mode = False
+        tr.join()  # (the discriminator updates run on their own stream beside the PPO update)
         if sync:
             sync.end_round()
 
@@ -361,6 +362,7 @@ def main():
             with networks.training(tr.reward_train):
                 tr.train_disc(expert_samples=next_host_batch())  # H2D copy + update + 9-float D2H
         if sync:
+            tr.join()
             sync.end_round()
 
     Ke = max(3, min(K, 50))

@@ -15,6 +15,7 @@ Additive keyword arguments: `sampling` ("device" = Philox/Feistel on the GPU, "h
 the reference's NumPy/torch RNG streams for bit-exact index parity), `seed`.
 """
 import abc
+import contextlib
 import itertools
 from typing import Callable, Dict, Iterator, Mapping, Optional, Type
 
@@ -187,6 +188,13 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         self._capturing = False
         self._graph = None
         self.use_cuda_graph = True   # replay warm kernel sequences from CUDA graphs (device sampling only)
+        # GAIL: a discriminator update needs the round's rollouts but not the PPO update (which needs the rollouts but
+        # not the discriminator), so the two run concurrently: the PPO kernel occupies the 8 SMs of one cluster, the
+        # discriminator kernels the rest.  Results are bit-identical to the serial order.  AIRL's logit needs
+        # log pi of the UPDATED policy (common.py:606-615), so it stays on one stream.
+        self.overlap_disc_with_gen = True
+        self._disc_stream = None
+        self._ev_disc = None
         self._disc_graphs = {}
         self._stage = {}
 
@@ -254,6 +262,32 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
                              dones, n, False, st)
         return table
 
+    # -- generator update and discriminator updates on two streams (GAIL) -------------------------------------------
+    def _overlap(self) -> bool:
+        return bool(self._fused and self.overlap_disc_with_gen and not self._needs_logp and self._device.type == "cuda")
+
+    def _disc_ctx(self):
+        """Stream context of the discriminator updates: a side stream that starts from the generator's "rollout done"
+        event (no-op context when the overlap is off, e.g. AIRL)."""
+        if not self._overlap():
+            return contextlib.nullcontext()
+        if self._disc_stream is None:
+            self._disc_stream = th.cuda.Stream(device=self._device)
+            self._ev_disc = th.cuda.Event()
+        self._disc_stream.wait_event(self.gen_algo.ev_rollout)
+        return th.cuda.stream(self._disc_stream)
+
+    def join(self) -> None:
+        """Order the current stream after every discriminator update enqueued so far (callers of `train_disc_async`
+        that go on to touch the reward network on the current stream, e.g. the multi-GPU round sync)."""
+        self._join_disc()
+
+    def _join_disc(self) -> None:
+        """Make the current stream wait for the discriminator updates enqueued so far (the next rollout relabels its
+        rewards with the updated reward network)."""
+        if self._disc_stream is not None and self._ev_disc is not None:
+            th.cuda.current_stream().wait_event(self._ev_disc)
+
     # -- discriminator update -------------------------------------------------------------------------------------------
     def _sample_expert_indices(self) -> None:
         if self._expert_compat is not None:
@@ -306,6 +340,15 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
             raise NotImplementedError("train_disc_async needs the fused Adam path")
         if gen_samples is None and check_ring and self._gen_replay_buffer.size() == 0:
             raise RuntimeError("No generator samples for training. Call `train_gen()` first.")
+        if self._capturing:  # (whole-round capture: the caller forks / joins the streams itself)
+            return self._train_disc_async_on_stream(expert_samples, gen_samples, stats_out)
+        with self._disc_ctx():
+            out = self._train_disc_async_on_stream(expert_samples, gen_samples, stats_out)
+            if self._disc_stream is not None and self._overlap():
+                self._ev_disc.record(self._disc_stream)
+        return out
+
+    def _train_disc_async_on_stream(self, expert_samples, gen_samples, stats_out) -> th.Tensor:
         e_host, g_host = expert_samples is not None, gen_samples is not None
         if e_host:
             self._stage_host(self._check_samples(expert_samples, "expert"), "expert")
@@ -398,13 +441,27 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
     def _enqueue_round(self) -> None:
         gen = self.gen_algo
         gen.collect_rollouts()
+        side = None
+        if self._overlap():  # fork: the discriminator updates run beside the PPO update (two branches of the graph)
+            if self._disc_stream is None:
+                self._disc_stream = th.cuda.Stream(device=self._device)
+                self._ev_disc = th.cuda.Event()
+            side = self._disc_stream
+            fork = th.cuda.Event()
+            fork.record()
+            side.wait_event(fork)
         gen.train()
         self.disc_train_mode = True
         try:
-            for k in range(self.n_disc_updates_per_round):
-                self.train_disc_async(stats_out=self._round_stats[k], check_ring=False)
+            with (th.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                for k in range(self.n_disc_updates_per_round):
+                    self.train_disc_async(stats_out=self._round_stats[k], check_ring=False)
         finally:
             self.disc_train_mode = False
+        if side is not None:  # join
+            done = th.cuda.Event()
+            done.record(side)
+            th.cuda.current_stream().wait_event(done)
 
     def capture_round(self) -> None:
         """Capture [rollout -> GAE -> PPO update -> n_disc x discriminator update] into a CUDA graph.
@@ -430,6 +487,7 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
     def replay_round(self) -> th.Tensor:
         """Run one captured round; returns the device stats [n_disc][16] (no synchronisation)."""
         t0 = self.venv.host_ep_step
+        self._join_disc()
         self._graph.replay()
         _lib.LAUNCHES["count"] += self._graph_launches
         self.gen_algo.after_rollout_host(t0)
@@ -461,7 +519,8 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
             if self._fused:
                 stats_t = self.train_disc_async(expert_samples=expert_samples, gen_samples=gen_samples,
                                                 check_ring=False)
-                vals = stats_t[:9].cpu().numpy()  # the one D2H read the Mapping[str, float] return needs
+                with self._disc_ctx():  # (read back on the stream that produced them: does not wait for the PPO update)
+                    vals = stats_t[:9].cpu().numpy()  # the one D2H read the Mapping[str, float] return needs
                 train_stats = {k: float(v) for k, v in zip(STAT_KEYS, vals)}
             else:
                 train_stats = self._train_disc_generic(expert_samples, gen_samples)
@@ -511,6 +570,7 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         """gen_algo.learn + pop/flatten/store (common.py:391-425); the store is fused into the rollout."""
         if total_timesteps is None:
             total_timesteps = self.gen_train_timesteps
+        self._join_disc()  # the rollouts are relabelled with the reward network the previous updates produced
         with self.logger.accumulate_means("gen"):
             self.gen_algo.learn(total_timesteps=total_timesteps, reset_num_timesteps=False,
                                 callback=self.gen_callback, **(learn_kwargs or {}))

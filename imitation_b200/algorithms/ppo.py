@@ -63,6 +63,7 @@ class DevicePPO:
         self._graph_key = None
         self._graph_launches = 0
         self._eager_iters = 0
+        self.ev_rollout = th.cuda.Event()  # recorded after every rollout: generator samples are in the ring
 
     # -- SB3 surface ---------------------------------------------------------------------------------------------
     def set_env(self, env, force_reset: bool = True) -> None:
@@ -156,13 +157,10 @@ class DevicePPO:
         """One collect_rollouts + train, replayed from a CUDA graph once it is warm (the kernels read every
         per-call scalar from the device counter block, so the captured launch sequence is exact)."""
         plain = self.noise is None and self.perm is None and self.loss_log is None
-        if not (self.use_cuda_graph and plain):
+        if not (self.use_cuda_graph and plain) or self._eager_iters < 1 or self._tbl is None:
             self.collect_rollouts()
-            self.train()
-            self._eager_iters += 1
-            return
-        if self._eager_iters < 1 or self._tbl is None:
-            self.collect_rollouts()
+            if not self._capturing:
+                self.ev_rollout.record()
             self.train()
             self._eager_iters += 1
             return
@@ -171,17 +169,22 @@ class DevicePPO:
             before = _lib.LAUNCHES["count"]
             self._capturing = True
             try:
-                g = th.cuda.CUDAGraph()
-                with th.cuda.graph(g):
+                # two graphs with the "rollout done" event between them: the adversarial trainer's discriminator
+                # stream starts from that event while the PPO update is still running
+                g_roll, g_train = th.cuda.CUDAGraph(), th.cuda.CUDAGraph()
+                with th.cuda.graph(g_roll):
                     self.collect_rollouts()
+                with th.cuda.graph(g_train, pool=g_roll.pool()):
                     self.train()
             finally:
                 self._capturing = False
-            self._graph, self._graph_key = g, key
+            self._graph, self._graph_key = (g_roll, g_train), key
             self._graph_launches = _lib.LAUNCHES["count"] - before
             _lib.LAUNCHES["count"] = before
         t0 = self._base_env.host_ep_step
-        self._graph.replay()
+        self._graph[0].replay()
+        self.ev_rollout.record()
+        self._graph[1].replay()
         _lib.LAUNCHES["count"] += self._graph_launches
         self.after_rollout_host(t0)
 
