@@ -234,6 +234,8 @@ def main():
                           "NormalizeFeaturesExtractor",
               "envs_per_gpu": E, "n_steps": T, "env_steps_per_round_per_gpu": E * T, "parallelism": f"dp{world}",
               "sync": "one all-reduce per round (params+Adam moments averaged, RunningNorm merged exactly)",
+              "streams": "the 8 discriminator updates run on a second stream beside the PPO update (independent given "
+                         "the rollouts; bit-identical to the serial order)",
               "l2_policy": "working set (rollout 0.5 MB, ring 84 KB, disc batch 2.8 MB, expert table 9.8 MB) is L2-resident "
                            "by construction at the tuned sizes; roofline sweep point uses 2^20 rows (176 MB > L2)"}
 
