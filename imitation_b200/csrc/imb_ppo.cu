@@ -5,10 +5,10 @@
 // unpinned by the reference).  PPO.train is n_epochs x (N / batch_size)
 // strictly sequential optimiser steps on 64-row minibatches: each step is ~1.3 MFLOP, far below
 // launch latency, so the whole loop runs inside one kernel with parameters, gradients and Adam
-// moments resident in shared memory:
-//   gather minibatch rows by permutation -> [feature RunningNorm update] -> advantage
-//   normalisation -> phase A (thread per row per tower: forward, loss, backward to dL/dz) ->
-//   phase B (warps split output units: weight gradients) -> clip_grad_norm_ -> Adam.
+// moments resident in the shared memory of an 8-CTA thread-block cluster (see k_ppo_update):
+//   prefetch minibatch rows by permutation -> [feature RunningNorm update] -> advantage
+//   normalisation -> warp-autonomous forward / loss / backward chain -> weight gradients ->
+//   DSMEM exchange (st.async + mbarriers) -> clip_grad_norm_ -> Adam on the owned slice -> parameter all-gather.
 // Also: imb_policy_logp = ActorCriticPolicy.evaluate_actions()[1] for the AIRL discriminator
 // batch (common.py:476-519).
 #include <cooperative_groups.h>
@@ -46,7 +46,6 @@ constexpr int PT = 256;   // threads per CTA: 0..127 = policy tower, 128..255 = 
 constexpr int CL = 8;     // CTAs per cluster: each owns RL rows of every minibatch and 1/CL of the gradient reduction
 constexpr int RL = 8;     // minibatch rows per CTA  (CL * RL = 64 >= SB3 batch_size)
 constexpr int PR = CL * RL;
-constexpr int PRS = PR + 8;  // row stride of the full-minibatch tiles (8-bank stagger: the 4 stat groups of a warp never collide)
 
 struct PpoArgs {
   imb_policy_desc pol;
