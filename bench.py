@@ -42,8 +42,8 @@ CFG = dict(d_obs=17, d_act=6, horizon=1000, envs_per_gpu=1024, ppo_batch=4096, p
                     learning_rate=0.00026250519057717037, max_grad_norm=0.8, vf_coef=0.11483689492120866))
 
 
-PPO_DRAM_BYTES_NCU = 598528 + 0       # bytes per launch, profiles/ncu_ppo_r01k_selected.csv (read + write)
-DISC_DRAM_BYTES_NCU_16K = 1611776 + 0  # k_disc_fwdbwd at 16 384 rows, profiles/ncu_disc_r01k_selected.csv
+PPO_DRAM_BYTES_NCU = 599552 + 0       # bytes per launch, profiles/ncu_ppo_r01m_selected.csv (read + write)
+DISC_DRAM_BYTES_NCU_16K = 1611776 + 0  # k_disc_fwdbwd at 16 384 rows, profiles/ncu_disc_r01m_selected.csv
 
 
 # -------------------------------------------------------------------------------------------------
@@ -430,7 +430,7 @@ def main():
                           "minibatch steps)",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this
-                # configuration (profiles/ncu_ppo_r01k_selected.csv): the rollout table stays in L2
+                # configuration (profiles/ncu_ppo_r01m_selected.csv): the rollout table stays in L2
                 "traffic": PPO_DRAM_BYTES_NCU if (cfg["envs_per_gpu"], cfg["ppo_epochs"]) == (1024, 5) else None,
                 "peak_source": peak_src, "ms_per_launch": ms_ppo, "share_of_step": ms_ppo / (ms / K),
                 "algorithmic_bytes_per_launch": ppo_bytes,
