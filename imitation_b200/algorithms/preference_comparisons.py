@@ -1,0 +1,566 @@
+"""Reward learning from preference comparisons on the fused reward networks.
+
+Mirror of the reward-model side of imitation.algorithms.preference_comparisons: `RandomFragmenter` (:564-665),
+`SyntheticGatherer` (:821-906), `PreferenceDataset` (:909-997), `PreferenceModel` (:345-530),
+`CrossEntropyRewardLoss` (:1043-1090), `BasicRewardTrainer` (:1139-1323), `EnsembleTrainer` (:1326-1438) and the
+`PreferenceComparisons` loop (:1482-1700) driven by a `TrajectoryDataset` (:99-124).  Same names, arguments, errors
+and random-number consumption (fragment choice, bagging sampler, DataLoader shuffling), so preference datasets and
+minibatch orders are identical to the reference's for the same seeds.
+
+What is different is where the arithmetic runs.  The reference evaluates the reward network once per fragment in a
+Python loop (`PreferenceModel.forward`, :441-454: 2 x pairs x members small forward passes per minibatch); here the
+2 x P fragments of a minibatch are flattened into ONE batch of 2*P*L transition rows, pushed through the fused MLP
+kernels (`reward_nets._FusedForward`: forward = imb_reward_forward, backward = imb_disc_fwd_bwd with the upstream
+gradient of every row), and the segmented discounted return -> clipped Boltzmann probability -> BCE is a handful
+of tensor ops on [P, L] device arrays.  Online RL on the learned reward (`AgentTrainer`) is out of scope of this
+row (the GAIL/AIRL generator is the on-device RL path); pass a `TrajectoryDataset`.
+"""
+import abc
+import math
+import pickle
+import re
+from collections import defaultdict
+from typing import Any, Callable, Dict, List, Mapping, NamedTuple, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch as th
+from torch import nn
+from torch.utils import data as data_th
+
+from ..data import rollout, types
+from ..data.types import TrajectoryWithRew
+from ..rewards import reward_nets
+from ..util import logger as imit_logger
+
+TrajectoryWithRewPair = Tuple[TrajectoryWithRew, TrajectoryWithRew]
+
+
+def make_seeds(rng: np.random.Generator, n: Optional[int] = None):
+    """util/util.py:181-199."""
+    seeds = rng.integers(0, (1 << 31) - 1, (n if n is not None else 1,)).tolist()
+    return seeds[0] if n is None else seeds
+
+
+# ------------------------------------------------------------------------------------------------
+# trajectory sources
+# ------------------------------------------------------------------------------------------------
+class TrajectoryGenerator(abc.ABC):
+    def __init__(self, custom_logger: Optional[imit_logger.HierarchicalLogger] = None):
+        self.logger = custom_logger or imit_logger.configure()
+
+    @abc.abstractmethod
+    def sample(self, steps: int) -> Sequence[TrajectoryWithRew]:
+        """Sample trajectories with at least `steps` transitions in total."""
+
+    def train(self, steps: int, **kwargs: Any) -> None:
+        """Train the agent, if any (no-op for fixed datasets)."""
+
+
+def _get_trajectories(trajectories: Sequence[TrajectoryWithRew], steps: int) -> Sequence[TrajectoryWithRew]:
+    """Prefix of `trajectories` with at least `steps` transitions (:319-342)."""
+    if steps == 0:
+        return []
+    available = sum(len(t) for t in trajectories)
+    if available < steps:
+        raise RuntimeError(f"Asked for {steps} transitions but only {available} available")
+    total, out = 0, []
+    for t in trajectories:
+        out.append(t)
+        total += len(t)
+        if total >= steps:
+            break
+    return out
+
+
+class TrajectoryDataset(TrajectoryGenerator):
+    """A fixed set of trajectories, shuffled at every `sample` (:99-124)."""
+
+    def __init__(self, trajectories: Sequence[TrajectoryWithRew], rng: np.random.Generator,
+                 custom_logger: Optional[imit_logger.HierarchicalLogger] = None):
+        super().__init__(custom_logger=custom_logger)
+        self._trajectories = trajectories
+        self.rng = rng
+
+    def sample(self, steps: int) -> Sequence[TrajectoryWithRew]:
+        trajectories = list(self._trajectories)
+        self.rng.shuffle(trajectories)  # type: ignore[arg-type]
+        return _get_trajectories(trajectories, steps)
+
+
+# ------------------------------------------------------------------------------------------------
+# fragments and synthetic preferences (host side, NumPy: identical random streams to the reference)
+# ------------------------------------------------------------------------------------------------
+class Fragmenter(abc.ABC):
+    def __init__(self, custom_logger: Optional[imit_logger.HierarchicalLogger] = None):
+        self.logger = custom_logger or imit_logger.configure()
+
+    @abc.abstractmethod
+    def __call__(self, trajectories: Sequence[TrajectoryWithRew], fragment_length: int, num_pairs: int
+                 ) -> Sequence[TrajectoryWithRewPair]:
+        """Create fragment pairs out of a sequence of trajectories."""
+
+
+class RandomFragmenter(Fragmenter):
+    """Uniformly random fragments, trajectories weighted by length, with replacement (:564-665)."""
+
+    def __init__(self, rng: np.random.Generator, warning_threshold: int = 10,
+                 custom_logger: Optional[imit_logger.HierarchicalLogger] = None) -> None:
+        super().__init__(custom_logger)
+        self.rng = rng
+        self.warning_threshold = warning_threshold
+
+    def __call__(self, trajectories, fragment_length: int, num_pairs: int) -> Sequence[TrajectoryWithRewPair]:
+        n_before = len(trajectories)
+        trajectories = [t for t in trajectories if len(t) >= fragment_length]
+        if len(trajectories) == 0:
+            raise ValueError(f"No trajectories are long enough for the desired fragment length of {fragment_length}.")
+        if n_before != len(trajectories):
+            self.logger.log(f"Discarded {n_before - len(trajectories)} out of {n_before} trajectories because they "
+                            f"are shorter than the desired length of {fragment_length}.")
+        weights = [len(t) for t in trajectories]
+        num_transitions = 2 * num_pairs * fragment_length
+        if sum(weights) < num_transitions:
+            self.logger.warn("Fewer transitions available than needed for desired number of fragment pairs. "
+                             "Some transitions will appear multiple times.")
+        elif self.warning_threshold and sum(weights) < self.warning_threshold * num_transitions:
+            self.logger.warn(f"Samples will contain {num_transitions} transitions in total and only {sum(weights)} are "
+                             "available. Because we sample with replacement, a significant number of transitions are "
+                             "likely to appear multiple times.")
+        p = np.array(weights) / sum(weights)
+        fragments: List[TrajectoryWithRew] = []
+        for _ in range(2 * num_pairs):  # two fragments per comparison; same draws as the reference (:645-650)
+            traj = self.rng.choice(trajectories, p=p)  # type: ignore[arg-type]
+            n = len(traj)
+            start = self.rng.integers(0, n - fragment_length, endpoint=True)
+            end = start + fragment_length
+            fragments.append(TrajectoryWithRew(obs=traj.obs[start:end + 1], acts=traj.acts[start:end],
+                                               infos=traj.infos[start:end] if traj.infos is not None else None,
+                                               rews=traj.rews[start:end], terminal=(end == n) and traj.terminal))
+        it = iter(fragments)
+        return list(zip(it, it))
+
+
+class PreferenceGatherer(abc.ABC):
+    def __init__(self, rng: Optional[np.random.Generator] = None,
+                 custom_logger: Optional[imit_logger.HierarchicalLogger] = None) -> None:
+        del rng
+        self.logger = custom_logger or imit_logger.configure()
+
+    @abc.abstractmethod
+    def __call__(self, fragment_pairs: Sequence[TrajectoryWithRewPair]) -> np.ndarray:
+        """Probability that fragment 1 is preferred, one float32 per pair."""
+
+
+class SyntheticGatherer(PreferenceGatherer):
+    """Preferences from the ground-truth rewards of the fragments (:821-906)."""
+
+    def __init__(self, temperature: float = 1, discount_factor: float = 1, sample: bool = True,
+                 rng: Optional[np.random.Generator] = None, threshold: float = 50,
+                 custom_logger: Optional[imit_logger.HierarchicalLogger] = None) -> None:
+        super().__init__(custom_logger=custom_logger)
+        self.temperature, self.discount_factor, self.sample = temperature, discount_factor, sample
+        self.rng, self.threshold = rng, threshold
+        if self.sample and self.rng is None:
+            raise ValueError("If `sample` is True, then `rng` must be provided.")
+
+    def __call__(self, fragment_pairs: Sequence[TrajectoryWithRewPair]) -> np.ndarray:
+        returns1, returns2 = self._reward_sums(fragment_pairs)
+        if self.temperature == 0:
+            return (np.sign(returns1 - returns2) + 1) / 2
+        returns1 /= self.temperature
+        returns2 /= self.temperature
+        returns_diff = np.clip(returns2 - returns1, -self.threshold, self.threshold)
+        model_probs = 1 / (1 + np.exp(returns_diff))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            xlogx = lambda q: np.where(q > 0, q * np.log(np.where(q > 0, q, 1.0)), 0.0)  # scipy.special.xlogy(q, q)
+            entropy = -(xlogx(model_probs) + xlogx(1 - model_probs)).mean()
+        self.logger.record("entropy", entropy)
+        if self.sample:
+            assert self.rng is not None
+            return self.rng.binomial(n=1, p=model_probs).astype(np.float32)
+        return model_probs
+
+    def _reward_sums(self, fragment_pairs) -> Tuple[np.ndarray, np.ndarray]:
+        r1, r2 = zip(*[(rollout.discounted_sum(f1.rews, self.discount_factor),
+                        rollout.discounted_sum(f2.rews, self.discount_factor)) for f1, f2 in fragment_pairs])
+        return np.array(r1, dtype=np.float32), np.array(r2, dtype=np.float32)
+
+
+class PreferenceDataset(data_th.Dataset):
+    """Fragment pairs + preference probabilities, optionally a FIFO of `max_size` (:909-997)."""
+
+    def __init__(self, max_size: Optional[int] = None) -> None:
+        self.fragments1: List[TrajectoryWithRew] = []
+        self.fragments2: List[TrajectoryWithRew] = []
+        self.max_size = max_size
+        self.preferences: np.ndarray = np.array([])
+
+    def push(self, fragments: Sequence[TrajectoryWithRewPair], preferences: np.ndarray) -> None:
+        fragments1, fragments2 = zip(*fragments)
+        if preferences.shape != (len(fragments),):
+            raise ValueError(f"Unexpected preferences shape {preferences.shape}, expected {(len(fragments),)}")
+        if preferences.dtype != np.float32:
+            raise ValueError("preferences should have dtype float32")
+        self.fragments1.extend(fragments1)
+        self.fragments2.extend(fragments2)
+        self.preferences = np.concatenate((self.preferences, preferences))
+        if self.max_size is not None:
+            extra = len(self.preferences) - self.max_size
+            if extra > 0:
+                self.fragments1, self.fragments2 = self.fragments1[extra:], self.fragments2[extra:]
+                self.preferences = self.preferences[extra:]
+
+    def __getitem__(self, key):
+        return (self.fragments1[key], self.fragments2[key]), self.preferences[key]
+
+    def __len__(self) -> int:
+        assert len(self.fragments1) == len(self.fragments2) == len(self.preferences)
+        return len(self.fragments1)
+
+    def save(self, path) -> None:
+        with open(path, "wb") as f:
+            pickle.dump(self, f)
+
+    @staticmethod
+    def load(path) -> "PreferenceDataset":
+        with open(path, "rb") as f:
+            return pickle.load(f)
+
+
+def preference_collate_fn(batch):
+    fragment_pairs, preferences = zip(*batch)
+    return list(fragment_pairs), np.array(preferences)
+
+
+# ------------------------------------------------------------------------------------------------
+# preference model and loss (device side)
+# ------------------------------------------------------------------------------------------------
+def get_base_model(reward_model: reward_nets.RewardNet) -> reward_nets.RewardNet:
+    base = reward_model
+    while hasattr(base, "base"):
+        base = base.base
+    return base
+
+
+def _stack_fragments(frags: Sequence[TrajectoryWithRew]) -> Mapping[str, np.ndarray]:
+    """Transition arrays of equal-length fragments, fragment-major: row f * L + t (what flatten_trajectories gives
+    for each fragment, concatenated)."""
+    L = len(frags[0])
+    obs = np.stack([f.obs for f in frags])           # [F, L + 1, ...]
+    acts = np.stack([f.acts for f in frags])         # [F, L, ...]
+    dones = np.zeros((len(frags), L), dtype=bool)
+    dones[:, -1] = [f.terminal for f in frags]
+    flat = lambda a: a.reshape((a.shape[0] * a.shape[1],) + a.shape[2:])
+    return dict(obs=flat(obs[:, :-1]), acts=flat(acts), next_obs=flat(obs[:, 1:]), dones=flat(dones))
+
+
+class PreferenceModel(nn.Module):
+    """Fragment rewards -> probability that the first fragment is preferred (:345-530)."""
+
+    def __init__(self, model: reward_nets.RewardNet, noise_prob: float = 0.0, discount_factor: float = 1.0,
+                 threshold: float = 50) -> None:
+        super().__init__()
+        self.model = model
+        self.noise_prob, self.discount_factor, self.threshold = noise_prob, discount_factor, threshold
+        base_model = get_base_model(model)
+        self.ensemble_model = None
+        if isinstance(base_model, reward_nets.RewardEnsemble):
+            is_std_wrapper = isinstance(model, reward_nets.AddSTDRewardWrapper) and model.base is base_model
+            if not (model is base_model or is_std_wrapper):
+                raise ValueError(f"RewardEnsemble can only be wrapped by AddSTDRewardWrapper but found {type(model).__name__}.")
+            self.ensemble_model = base_model
+            self.member_pref_models = [PreferenceModel(m, self.noise_prob, self.discount_factor, self.threshold)
+                                       for m in self.ensemble_model.members]
+
+    # -- rewards of a batch of transitions (keeps the graph for single networks) ----------------------------------
+    def rewards(self, transitions) -> th.Tensor:
+        tr = types.as_transition_arrays(transitions)
+        state, action, next_state, done = tr["obs"], tr["acts"], tr["next_obs"], tr["dones"]
+        if self.ensemble_model is not None:
+            rews_np = self.ensemble_model.predict_processed_all(state, action, next_state, done)
+            assert rews_np.shape == (len(state), self.ensemble_model.num_members)
+            return th.as_tensor(rews_np).to(self.ensemble_model.device)
+        rews = self.model(*self.model.preprocess(state, action, next_state, done))
+        assert rews.shape == (len(state),)
+        return rews
+
+    def probability(self, rews1: th.Tensor, rews2: th.Tensor) -> th.Tensor:
+        """Boltzmann-rational probability that fragment 1 is best; time is axis 0 (:487-530)."""
+        expected_dims = 2 if self.ensemble_model is not None else 1
+        assert rews1.ndim == rews2.ndim == expected_dims
+        return self._probability(rews1, rews2, time_axis=0)
+
+    def _probability(self, rews1: th.Tensor, rews2: th.Tensor, time_axis: int) -> th.Tensor:
+        diff = rews2 - rews1
+        if self.discount_factor == 1:
+            returns_diff = diff.sum(dim=time_axis)
+        else:
+            L = diff.shape[time_axis]
+            discounts = self.discount_factor ** th.arange(L, device=diff.device)
+            shape = [1] * diff.ndim
+            shape[time_axis] = L
+            returns_diff = (discounts.reshape(shape) * diff).sum(dim=time_axis)
+        returns_diff = th.clip(returns_diff, -self.threshold, self.threshold)  # also keeps the backward finite
+        model_probability = 1 / (1 + returns_diff.exp())
+        return self.noise_prob * 0.5 + (1 - self.noise_prob) * model_probability
+
+    def forward(self, fragment_pairs: Sequence[Tuple[types.Trajectory, types.Trajectory]]
+                ) -> Tuple[th.Tensor, Optional[th.Tensor]]:
+        """Probabilities for all pairs: shape (P,) (single network, differentiable) or (P, members)."""
+        P = len(fragment_pairs)
+        frags = [p[0] for p in fragment_pairs] + [p[1] for p in fragment_pairs]
+        lengths = {len(f) for f in frags}
+        gt_available = isinstance(fragment_pairs[0][0], TrajectoryWithRew) and isinstance(fragment_pairs[0][1], TrajectoryWithRew)
+        if len(lengths) == 1:
+            # one batch of 2 * P * L rows through the fused kernels; rows f * L + t, first fragments first
+            L = lengths.pop()
+            rews = self.rewards(_stack_fragments(frags))
+            rews = rews.reshape((2, P, L) + tuple(rews.shape[1:]))
+            probs = self._probability(rews[0], rews[1], time_axis=1)
+        else:  # ragged fragments: pair by pair like the reference
+            probs = th.stack([self.probability(self.rewards(rollout.flatten_trajectories([a])),
+                                               self.rewards(rollout.flatten_trajectories([b])))
+                              for a, b in fragment_pairs])
+        gt_probs = None
+        if gt_available:
+            if len({len(f) for f in frags}) == 1:
+                gr = th.as_tensor(np.stack([f.rews for f in frags])).reshape(2, P, -1)
+                gt_probs = self._probability(gr[0], gr[1], time_axis=1)
+            else:
+                gt_probs = th.stack([self._probability(th.from_numpy(a.rews), th.from_numpy(b.rews), 0)
+                                     for a, b in fragment_pairs])
+        return probs, gt_probs
+
+
+class LossAndMetrics(NamedTuple):
+    loss: th.Tensor
+    metrics: Mapping[str, th.Tensor]
+
+
+class RewardLoss(nn.Module, abc.ABC):
+    @abc.abstractmethod
+    def forward(self, fragment_pairs, preferences: np.ndarray, preference_model: PreferenceModel) -> LossAndMetrics:
+        """Loss of the preference model on a batch of comparisons."""
+
+
+class CrossEntropyRewardLoss(RewardLoss):
+    """Cross entropy between the model's and the target preference probabilities (:1043-1090)."""
+
+    def forward(self, fragment_pairs, preferences: np.ndarray, preference_model: PreferenceModel) -> LossAndMetrics:
+        probs, gt_probs = preference_model(fragment_pairs)
+        preferences_th = th.as_tensor(preferences, dtype=th.float32)
+        predictions = probs.detach().cpu() > 0.5
+        ground_truth = preferences_th > 0.5
+        metrics = {"accuracy": (predictions == ground_truth).float().mean()}
+        if gt_probs is not None:
+            metrics["gt_reward_loss"] = th.nn.functional.binary_cross_entropy(gt_probs.cpu(), preferences_th)
+        metrics = {k: v.detach().cpu() for k, v in metrics.items()}
+        loss = th.nn.functional.binary_cross_entropy(probs, preferences_th.to(probs.device))
+        return LossAndMetrics(loss=loss, metrics=metrics)
+
+
+# ------------------------------------------------------------------------------------------------
+# reward trainers
+# ------------------------------------------------------------------------------------------------
+class RewardTrainer(abc.ABC):
+    def __init__(self, preference_model: PreferenceModel,
+                 custom_logger: Optional[imit_logger.HierarchicalLogger] = None) -> None:
+        self._preference_model = preference_model
+        self._logger = custom_logger or imit_logger.configure()
+
+    @property
+    def logger(self) -> imit_logger.HierarchicalLogger:
+        return self._logger
+
+    @logger.setter
+    def logger(self, custom_logger: imit_logger.HierarchicalLogger) -> None:
+        self._logger = custom_logger
+
+    def train(self, dataset, epoch_multiplier: float = 1.0) -> None:
+        from ..util import networks
+
+        with networks.training(self._preference_model.model):
+            self._train(dataset, epoch_multiplier)
+
+    @abc.abstractmethod
+    def _train(self, dataset, epoch_multiplier: float) -> None:
+        """Train the reward model."""
+
+
+class BasicRewardTrainer(RewardTrainer):
+    """Minibatch gradient accumulation with AdamW over a `PreferenceDataset` (:1139-1323)."""
+
+    def __init__(self, preference_model: PreferenceModel, loss: RewardLoss, rng: np.random.Generator,
+                 batch_size: int = 32, minibatch_size: Optional[int] = None, epochs: int = 1, lr: float = 1e-3,
+                 custom_logger: Optional[imit_logger.HierarchicalLogger] = None, regularizer_factory=None) -> None:
+        super().__init__(preference_model, custom_logger)
+        if regularizer_factory is not None:
+            raise NotImplementedError("regularizers (imitation.regularization) are outside this path")
+        self.loss = loss
+        self.batch_size = batch_size
+        self.minibatch_size = minibatch_size or batch_size
+        if self.batch_size % self.minibatch_size != 0:
+            raise ValueError("Batch size must be a multiple of minibatch size.")
+        self.epochs = epochs
+        self.optim = th.optim.AdamW(self._preference_model.parameters(), lr=lr)
+        self.rng = rng
+        self.regularizer = None
+        self.last_epoch_stats: Dict[str, float] = {}
+
+    def _make_data_loader(self, dataset) -> data_th.DataLoader:
+        return data_th.DataLoader(dataset, batch_size=self.minibatch_size, shuffle=True,
+                                  collate_fn=preference_collate_fn)
+
+    @property
+    def requires_regularizer_update(self) -> bool:
+        return False
+
+    def _train(self, dataset, epoch_multiplier: float = 1.0) -> None:
+        dataloader = self._make_data_loader(dataset)
+        epochs = round(self.epochs * epoch_multiplier)
+        assert epochs > 0, "Must train for at least one epoch."
+        with self.logger.accumulate_means("reward"):
+            for epoch_num in range(epochs):
+                train_loss, accumulated_size, n_batches, acc = 0.0, 0, 0, 0.0
+                self.optim.zero_grad()
+                for fragment_pairs, preferences in dataloader:
+                    out = self.loss.forward(fragment_pairs, preferences, self._preference_model)
+                    self.logger.record(f"epoch-{epoch_num}/train/loss", out.loss.item())
+                    for name, value in out.metrics.items():
+                        self.logger.record(f"epoch-{epoch_num}/train/{name}", value.item())
+                    acc += float(out.metrics["accuracy"])
+                    n_batches += 1
+                    # averaged over the whole batch instead of the minibatch (an incomplete batch gets smaller gradients)
+                    loss = out.loss * (len(fragment_pairs) / self.batch_size)
+                    train_loss += loss.item()
+                    loss.backward()
+                    accumulated_size += len(fragment_pairs)
+                    if accumulated_size >= self.batch_size:
+                        self.optim.step()
+                        self.optim.zero_grad()
+                        accumulated_size = 0
+                if accumulated_size != 0:
+                    self.optim.step()  # an incomplete batch remains
+                self.last_epoch_stats = {"loss": train_loss, "accuracy": acc / max(n_batches, 1)}
+        for k, v in self.last_epoch_stats.items():
+            self.logger.record(f"reward/final/train/{k}", v)
+
+
+class EnsembleTrainer(BasicRewardTrainer):
+    """One `BasicRewardTrainer` per ensemble member, each on its own bootstrap sample (:1326-1438)."""
+
+    def __init__(self, preference_model: PreferenceModel, loss: RewardLoss, rng: np.random.Generator,
+                 batch_size: int = 32, minibatch_size: Optional[int] = None, epochs: int = 1, lr: float = 1e-3,
+                 custom_logger: Optional[imit_logger.HierarchicalLogger] = None, regularizer_factory=None) -> None:
+        if preference_model.ensemble_model is None:
+            raise TypeError("PreferenceModel of a RewardEnsemble expected by EnsembleTrainer.")
+        super().__init__(preference_model, loss=loss, batch_size=batch_size, minibatch_size=minibatch_size,
+                         epochs=epochs, lr=lr, custom_logger=custom_logger, rng=rng,
+                         regularizer_factory=regularizer_factory)
+        self.member_trainers = [
+            BasicRewardTrainer(mp, loss=loss, batch_size=batch_size, minibatch_size=minibatch_size, epochs=epochs, lr=lr,
+                               custom_logger=self.logger, regularizer_factory=regularizer_factory, rng=self.rng)
+            for mp in self._preference_model.member_pref_models]
+
+    def _train(self, dataset, epoch_multiplier: float = 1.0) -> None:
+        sampler = data_th.RandomSampler(dataset, replacement=True, num_samples=len(dataset),
+                                        generator=th.Generator().manual_seed(make_seeds(self.rng)))
+        stats = defaultdict(list)
+        for member_idx, trainer in enumerate(self.member_trainers):
+            bagging_dataset = data_th.Subset(dataset, list(sampler))
+            trainer.train(bagging_dataset, epoch_multiplier=epoch_multiplier)
+            del member_idx
+            for k, v in trainer.last_epoch_stats.items():
+                stats[k].append(v)
+        self.last_epoch_stats = {k: float(np.mean(v)) for k, v in stats.items()}
+        for k, v in stats.items():
+            self.logger.record(f"reward/final/train/{k}", float(np.mean(v)))
+            self.logger.record(f"reward/final/train/{k}_std", float(np.std(v)))
+
+
+def _make_reward_trainer(preference_model: PreferenceModel, loss: RewardLoss, rng: np.random.Generator,
+                         reward_trainer_kwargs: Optional[Mapping[str, Any]] = None) -> RewardTrainer:
+    kw = dict(reward_trainer_kwargs or {})
+    if preference_model.ensemble_model is not None:
+        return EnsembleTrainer(preference_model, loss, rng=rng, **kw)
+    return BasicRewardTrainer(preference_model, loss=loss, rng=rng, **kw)
+
+
+QUERY_SCHEDULES: Dict[str, Callable[[float], float]] = {
+    "constant": lambda t: 1.0,
+    "hyperbolic": lambda t: 1.0 / (1.0 + t),
+    "inverse_quadratic": lambda t: 1.0 / (1.0 + t ** 2),
+}
+
+
+class PreferenceComparisons:
+    """The outer loop (:1482-1700): sample trajectories -> fragments -> preferences -> train the reward model."""
+
+    def __init__(self, trajectory_generator: TrajectoryGenerator, reward_model: reward_nets.RewardNet,
+                 num_iterations: int, fragmenter: Optional[Fragmenter] = None,
+                 preference_gatherer: Optional[PreferenceGatherer] = None,
+                 reward_trainer: Optional[RewardTrainer] = None, comparison_queue_size: Optional[int] = None,
+                 fragment_length: int = 100, transition_oversampling: float = 1,
+                 initial_comparison_frac: float = 0.1, initial_epoch_multiplier: float = 200.0,
+                 custom_logger: Optional[imit_logger.HierarchicalLogger] = None,
+                 rng: Optional[np.random.Generator] = None,
+                 query_schedule: Union[str, Callable[[float], float]] = "hyperbolic") -> None:
+        self.logger = custom_logger or imit_logger.configure()
+        if rng is None and not (fragmenter is not None and preference_gatherer is not None and reward_trainer is not None):
+            raise ValueError("If you don't provide a random state, you must provide your own "
+                             "seeded fragmenter, preference gatherer, and reward_trainer. ")
+        self.rng = rng
+        self.model = reward_model
+        self.preference_model = PreferenceModel(reward_model)
+        self.reward_trainer = reward_trainer or _make_reward_trainer(self.preference_model, CrossEntropyRewardLoss(), rng)
+        self.trajectory_generator = trajectory_generator
+        self.fragmenter = fragmenter or RandomFragmenter(custom_logger=self.logger, rng=rng)
+        self.preference_gatherer = preference_gatherer or SyntheticGatherer(custom_logger=self.logger, rng=rng)
+        self.fragment_length = fragment_length
+        self.initial_comparison_frac = initial_comparison_frac
+        self.initial_epoch_multiplier = initial_epoch_multiplier
+        self.num_iterations = num_iterations
+        self.transition_oversampling = transition_oversampling
+        if callable(query_schedule):
+            self.query_schedule = query_schedule
+        elif query_schedule in QUERY_SCHEDULES:
+            self.query_schedule = QUERY_SCHEDULES[query_schedule]
+        else:
+            raise ValueError(f"Unknown query schedule: {query_schedule}")
+        self.dataset = PreferenceDataset(max_size=comparison_queue_size)
+        self._iteration = 0
+
+    def train(self, total_timesteps: int, total_comparisons: int,
+              callback: Optional[Callable[[int], None]] = None) -> Mapping[str, Any]:
+        initial_comparisons = int(total_comparisons * self.initial_comparison_frac)
+        total_comparisons -= initial_comparisons
+        vec = np.array([self.query_schedule(t) for t in np.linspace(0, 1, self.num_iterations)])
+        shares = (vec / vec.sum() * total_comparisons)
+        schedule = [initial_comparisons] + [int(x) for x in _round_keep_sum(shares)]
+        timesteps_per_iteration, extra = divmod(total_timesteps, self.num_iterations)
+        reward_loss = reward_accuracy = None
+        for i, num_pairs in enumerate(schedule):
+            num_steps = math.ceil(self.transition_oversampling * 2 * num_pairs * self.fragment_length)
+            trajectories = self.trajectory_generator.sample(num_steps)
+            fragments = self.fragmenter(trajectories, self.fragment_length, num_pairs)
+            preferences = self.preference_gatherer(fragments)
+            self.dataset.push(fragments, np.asarray(preferences, dtype=np.float32))
+            epoch_multiplier = self.initial_epoch_multiplier if i == 0 else 1.0
+            self.reward_trainer.train(self.dataset, epoch_multiplier=epoch_multiplier)
+            stats = getattr(self.reward_trainer, "last_epoch_stats", {})
+            reward_loss, reward_accuracy = stats.get("loss"), stats.get("accuracy")
+            num_steps = timesteps_per_iteration + (extra if i == self.num_iterations - 1 else 0)
+            self.trajectory_generator.train(steps=num_steps)
+            if callback:
+                callback(self._iteration)
+            self._iteration += 1
+        return {"reward_loss": reward_loss, "reward_accuracy": reward_accuracy}
+
+
+def _round_keep_sum(x: np.ndarray) -> np.ndarray:
+    """Round to integers keeping the total (util.oric, :util.py)."""
+    floor = np.floor(x)
+    k = int(round(x.sum() - floor.sum()))
+    order = np.argsort(-(x - floor), kind="stable")
+    floor[order[:k]] += 1
+    return floor.astype(int)

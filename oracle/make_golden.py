@@ -274,8 +274,75 @@ def train_stats_case():
     print("wrote train_stats")
 
 
+def preference_case():
+    """algorithms/preference_comparisons.py: RandomFragmenter, SyntheticGatherer, PreferenceModel,
+    CrossEntropyRewardLoss on seeded trajectories and a seeded BasicRewardNet (single network and 3-member ensemble)."""
+    from imitation.algorithms import preference_comparisons as ref_pc
+
+    Do, Da, L, P = 11, 3, 25, 12
+    rng = np.random.default_rng(21)
+    trajs = []
+    for i in range(6):
+        n = int(rng.integers(30, 60))
+        trajs.append(ref_types.TrajectoryWithRew(
+            obs=rng.standard_normal((n + 1, Do)).astype(np.float32), acts=rng.uniform(-1, 1, (n, Da)).astype(np.float32),
+            infos=None, terminal=bool(i % 2), rews=(0.3 * rng.standard_normal(n)).astype(np.float32)))
+    out = {"cfg": np.array([Do, Da, L, P])}
+    for i, t in enumerate(trajs):
+        out.update(_flat(f"traj{i}", dict(obs=t.obs, acts=t.acts, rews=t.rews, terminal=np.array(t.terminal))))
+    log = ref_logger.configure(os.path.join("/tmp", "imb_golden_log_pref"), format_strs=[])
+    frags = ref_pc.RandomFragmenter(rng=np.random.default_rng(3), warning_threshold=0, custom_logger=log)(trajs, L, P)
+    for i, (a, b) in enumerate(frags):
+        out.update(_flat(f"pair{i}/a", dict(obs=a.obs, acts=a.acts, rews=a.rews, terminal=np.array(a.terminal))))
+        out.update(_flat(f"pair{i}/b", dict(obs=b.obs, acts=b.acts, rews=b.rews, terminal=np.array(b.terminal))))
+    out["prefs_prob"] = ref_pc.SyntheticGatherer(sample=False, temperature=0.5, discount_factor=0.9,
+                                                 custom_logger=log)(frags)
+    out["prefs_sampled"] = ref_pc.SyntheticGatherer(sample=True, rng=np.random.default_rng(4), custom_logger=log)(frags)
+    out["prefs_t0"] = ref_pc.SyntheticGatherer(sample=False, temperature=0, custom_logger=log)(frags)
+    obs_space = spaces.Box(-np.inf, np.inf, (Do,), np.float32)
+    act_space = spaces.Box(-1.0, 1.0, (Da,), np.float32)
+    th.manual_seed(8)
+    net = ref_nets.BasicRewardNet(obs_space, act_space, hid_sizes=(32, 32))
+    out.update(_flat("net", _state(net)))
+    pm = ref_pc.PreferenceModel(net, noise_prob=0.1, discount_factor=0.95)
+    prefs = out["prefs_sampled"].astype(np.float32)
+    res = ref_pc.CrossEntropyRewardLoss()(frags, prefs, pm)
+    probs, gt_probs = pm(frags)
+    out["probs"], out["gt_probs"] = probs.detach().numpy(), gt_probs.numpy()
+    out["loss"] = res.loss.detach().numpy()
+    out["accuracy"], out["gt_reward_loss"] = res.metrics["accuracy"].numpy(), res.metrics["gt_reward_loss"].numpy()
+    net.zero_grad()
+    res.loss.backward()
+    out.update(_flat("grad", {k: p.grad.numpy().copy() for k, p in net.named_parameters()}))
+    # three-member ensemble: probabilities of all members (no gradient path, as in the reference)
+    th.manual_seed(9)
+    members = [ref_nets.BasicRewardNet(obs_space, act_space, hid_sizes=(32, 32)) for _ in range(3)]
+    ens = ref_nets.RewardEnsemble(obs_space, act_space, members)
+    for i, m in enumerate(members):
+        out.update(_flat(f"member{i}", _state(m)))
+    pme = ref_pc.PreferenceModel(ens, discount_factor=1.0)
+    # (the reference's PreferenceModel.forward cannot hold per-member probabilities -- its `probs` buffer is 1-D --
+    #  so the ensemble path is pinned through rewards() + probability(), the calls ActiveSelectionFragmenter makes)
+    pe = [pme.probability(pme.rewards(ref_rollout.flatten_trajectories([a])),
+                          pme.rewards(ref_rollout.flatten_trajectories([b]))) for a, b in frags]
+    out["ensemble_probs"] = th.stack(pe).detach().numpy()
+    # one BasicRewardTrainer epoch (AdamW, batch 8, minibatch 4) from the single network's initial weights
+    th.manual_seed(10)
+    ds = ref_pc.PreferenceDataset()
+    ds.push(frags, prefs)
+    trainer = ref_pc.BasicRewardTrainer(pm, ref_pc.CrossEntropyRewardLoss(), rng=np.random.default_rng(5), batch_size=8,
+                                        minibatch_size=4, epochs=2, lr=1e-3, custom_logger=log)
+    trainer.train(ds)
+    out.update(_flat("net_trained", _state(net)))
+    np.savez_compressed(os.path.join(OUT, "preference.npz"), **out)
+    print("wrote preference")
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "preference":
+        preference_case()
+        sys.exit(0)
     RN = ref_networks.RunningNorm
     disc_case("disc_gail_hc", "gail", 17, 6, False, dict(normalize_input_layer=RN), 64, 64, 4, 0)
     disc_case("disc_gail_hc_minibatch", "gail", 17, 6, False, dict(normalize_input_layer=RN), 64, 16, 3, 1)
@@ -292,3 +359,4 @@ if __name__ == "__main__":
     relabel_case()
     expert_loader_case()
     train_stats_case()
+    preference_case()
