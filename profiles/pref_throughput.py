@@ -51,8 +51,11 @@ rows = M * 2 * P * L
 print(f"fused path: {dt * 1e3:.1f} ms per pass over {P} pairs x {M} members ({rows / dt / 1e6:.1f} M transition rows/s, "
       f"{M * P / dt:.0f} pair-evaluations/s; includes the host-side stacking and H2D copy of every minibatch)")
 
-# CPU restatement, fragment by fragment like the reference (bounded sample: 64 pairs, one member)
-from oracle import nets_port, pref_port  # noqa: E402  (bench-style CPU leg)
+# CPU restatement, fragment by fragment like the reference (bounded sample: 64 pairs, one member) -- a bench-style
+# baseline leg, run only on request: the oracle is test infrastructure, nothing in the product path imports it
+if "--cpu-baseline" not in sys.argv:
+    sys.exit(0)
+from oracle import nets_port, pref_port  # noqa: E402
 
 th.set_num_threads(8)
 net = nets_port.BasicRewardNetPort(Do, Da, hid_sizes=(32, 32))
