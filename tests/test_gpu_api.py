@@ -506,3 +506,40 @@ def test_full_size_round_properties():
     assert s[7] == B and s[8] == B and 0.0 <= s[1] <= 1.0 and abs(s[5] - 0.5) < 1e-6 and np.isfinite(s).all()
     # feature RunningNorm of the policy: every PPO minibatch row counted once per epoch
     assert int(a.policy.flat_vectors()[2][0]) == rounds * 5 * E * T
+
+
+def test_load_reward_registry_round_trip(tmp_path):
+    """rewards/serialize.load_reward on `th.save(reward_net)` checkpoints (scripts/train_adversarial.py:25-35): wrapper
+    validation / stripping like the reference's registry, predictions through the re-aliased fused engines."""
+    from imitation_b200 import spaces
+    from imitation_b200.rewards import reward_nets, serialize
+    from imitation_b200.util import networks
+
+    Do, Da = 6, 2
+    obs_space, act_space = spaces.Box(-np.inf, np.inf, (Do,)), spaces.Box(-1.0, 1.0, (Da,))
+    th.manual_seed(3)
+    shaped = reward_nets.BasicShapedRewardNet(obs_space, act_space, normalize_input_layer=networks.RunningNorm).cuda()
+    net = reward_nets.NormalizedRewardNet(shaped, networks.RunningNorm)
+    rng = np.random.default_rng(0)
+    obs, nobs = rng.standard_normal((32, Do)).astype(np.float32), rng.standard_normal((32, Do)).astype(np.float32)
+    acts, done = rng.uniform(-1, 1, (32, Da)).astype(np.float32), rng.random(32) < 0.2
+    net.predict_processed(obs, acts, nobs, done)  # moves the output normaliser's statistics
+    p = tmp_path / "reward.pt"
+    th.save(net, p)
+    want_norm = net.predict_processed(obs, acts, nobs, done, update_stats=False)
+    want_raw = shaped.predict(obs, acts, nobs, done)
+    want_base = shaped.base.predict(obs, acts, nobs, done)
+    got = serialize.load_reward("RewardNet_normalized", str(p), None)(obs, acts, nobs, done)
+    np.testing.assert_array_equal(got, want_norm)
+    np.testing.assert_array_equal(serialize.load_reward("RewardNet_unnormalized", str(p), None)(obs, acts, nobs, done),
+                                  want_raw)
+    q = tmp_path / "shaped.pt"
+    th.save(shaped, q)
+    np.testing.assert_array_equal(serialize.load_reward("RewardNet_shaped", str(q), None)(obs, acts, nobs, done), want_raw)
+    np.testing.assert_array_equal(serialize.load_reward("RewardNet_unshaped", str(q), None)(obs, acts, nobs, done),
+                                  want_base)
+    assert serialize.load_reward("zero", "", None)(obs, acts, nobs, done).shape == (32,)
+    with pytest.raises(TypeError, match="Wrapper structure should match"):
+        serialize.load_reward("RewardNet_normalized", str(q), None)
+    with pytest.raises(KeyError):
+        serialize.load_reward("nonexistent", str(q), None)
