@@ -519,7 +519,7 @@ def test_load_reward_registry_round_trip(tmp_path):
     obs_space, act_space = spaces.Box(-np.inf, np.inf, (Do,)), spaces.Box(-1.0, 1.0, (Da,))
     th.manual_seed(3)
     shaped = reward_nets.BasicShapedRewardNet(obs_space, act_space, normalize_input_layer=networks.RunningNorm).cuda()
-    net = reward_nets.NormalizedRewardNet(shaped, networks.RunningNorm)
+    net = reward_nets.NormalizedRewardNet(shaped, networks.RunningNorm).cuda()
     rng = np.random.default_rng(0)
     obs, nobs = rng.standard_normal((32, Do)).astype(np.float32), rng.standard_normal((32, Do)).astype(np.float32)
     acts, done = rng.uniform(-1, 1, (32, Da)).astype(np.float32), rng.random(32) < 0.2
