@@ -18,7 +18,6 @@ row (the GAIL/AIRL generator is the on-device RL path); pass a `TrajectoryDatase
 import abc
 import math
 import pickle
-import re
 from collections import defaultdict
 from typing import Any, Callable, Dict, List, Mapping, NamedTuple, Optional, Sequence, Tuple, Union
 
