@@ -241,6 +241,11 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         self._expert_state = th.zeros(_lib.ST_WORDS, dtype=th.int64, device=self._device)
         self._expert_compat = (_TorchCompatExpertIndices(n, self.demo_batch_size)
                                if self.sampling == "host_compat" else None)
+        # captured graphs hold the OLD table / sampling-state pointers: drop them (they are re-captured on demand)
+        if getattr(self, "_disc_graphs", None):
+            self._disc_graphs = {}
+        if getattr(self, "_graph", None) is not None:
+            self._graph = None
 
     def _rows_to_table(self, tr: Mapping[str, np.ndarray]) -> th.Tensor:
         """host/device transition arrays -> AoS device table (RewardNet.preprocess semantics)."""
