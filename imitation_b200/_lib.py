@@ -17,6 +17,7 @@ IMB_MAX_HIDDEN = 64
 IMB_MAX_DIN = 64
 IMB_F_ZERO_GRAD = 1
 IMB_F_TRAIN_NORM = 2
+IMB_F_NO_TENSOR = 4   # force the fp32-FFMA discriminator kernel (A/B measurements)
 IMB_RF_DETERMINISTIC = 1  # imb_rollout flags
 
 # device-resident counter block (include/imb.h enum)

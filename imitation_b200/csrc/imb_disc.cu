@@ -541,6 +541,10 @@ __global__ void __launch_bounds__(R, 256 / R) k_disc_fwdbwd(const DiscLaunch L, 
   }
 }
 
+}  // namespace
+#include "imb_disc_tc.cuh"
+namespace {
+
 // ---- deterministic reduction of the per-CTA partials -----------------------------------------
 // warp per parameter (and per statistic): lanes stride over the G partial rows, shuffle-reduce.
 __global__ void __launch_bounds__(256) k_disc_reduce(int P, int G, const float* __restrict__ partial,
@@ -959,6 +963,28 @@ extern "C" int imb_disc_fwd_bwd(const imb_disc_desc* d, const float* params, con
   if (flags & IMB_F_ZERO_GRAD) {
     cudaError_t e = cudaMemsetAsync(ws + w.gacc, 0, sizeof(float) * d->n_params, st);
     if (e != cudaSuccess) IMB_FAIL(-2, "memset: %s", cudaGetErrorString(e));
+  }
+  // Tensor-core path (tcgen05 / TMEM, 3xTF32 split) whenever the network shape fits it
+  if (!(flags & IMB_F_NO_TENSOR) && tc_applicable(L)) {
+    const TcPlan T = tc_plan(L);
+    const size_t bytes = (size_t)T.total * 4 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(k_disc_fwdbwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IMB_SMEM_MAX);
+      if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    IMB_REQUIRE(bytes <= IMB_SMEM_MAX, "tensor-core disc kernel: %zu B of shared memory", bytes);
+    const int64_t ntiles = (n + 127) / 128;
+    int64_t Gt = imb_num_sms();
+    if (Gt > MAXG) Gt = MAXG;
+    if (Gt > ntiles) Gt = ntiles;
+    k_disc_fwdbwd_tc<<<(int)Gt, TC_THREADS, bytes, st>>>(L, T, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
+                                                      ws + w.partial, reinterpret_cast<int*>(ws + w.meta),
+                                                      part_stride(d->n_params));
+    IMB_CHECK_LAUNCH("k_disc_fwdbwd_tc");
+    g_last_grid = (int)Gt;
+    return 0;
   }
   // Preferred: 128-row tiles with TWO resident CTAs per SM (independent CTAs overlap each other's
   // barriers and epilogues); else one 256-row CTA; else one 128-row CTA.

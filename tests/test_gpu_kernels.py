@@ -307,6 +307,70 @@ def test_disc_fwd_bwd_large_against_torch_fp32(L):
     np.testing.assert_allclose(grad.cpu().numpy(), want.cpu().numpy(), rtol=1e-3, atol=1e-5 * max(scale, 1.0))
 
 
+@pytest.mark.parametrize("n", [100, 128, 1000, 16384, 1 << 18])
+@pytest.mark.parametrize("dims", [(17, 6), (4, 2), (20, 11)])
+def test_disc_tensor_core_path_matches_ffma_and_fp64(L, n, dims):
+    """The tcgen05 kernel (3xTF32 split, TMEM accumulators) against the fp32-FFMA kernel of round 1 and against
+    a float64 evaluation of the same network: logits within north_star's 1e-5 relative, gradients alike, every
+    statistic equal.  Sizes cover a partial tile, one tile, several tiles per CTA (persistent loop, weight-gradient
+    accumulator kept in TMEM across tiles) and K1 = 8 / 24 / 32 input columns."""
+    from imitation_b200 import _desc
+
+    Do, Da = dims
+    d = _desc.disc_desc(Do, Da)
+    din = Do + Da
+    g = th.Generator(device="cuda").manual_seed(n + Do)
+    P = (th.rand(d.n_params, device="cuda", generator=g) - 0.5) * 0.6
+    bw, ld = _desc.batch_rows(Do, Da), _desc.batch_ld(n)
+    batch = th.zeros(bw, ld, device="cuda")
+    batch[:, :n] = th.randn(bw, n, device="cuda", generator=g)
+    NS = th.zeros(2, device="cuda")
+    n_exp = n // 2
+    out = {}
+    for name, extra in (("tc", 0), ("ffma", L.IMB_F_NO_TENSOR)):
+        ws = th.zeros(L.disc_workspace_floats(d), device="cuda")
+        logits = th.zeros(n, device="cuda")
+        grad = th.zeros(d.n_params, device="cuda")
+        L.disc_fwd_bwd(d, P, NS, batch, ld, n, n_exp, 1.0 / n, None, logits, L.IMB_F_ZERO_GRAD | extra, ws)
+        L.disc_reduce(d, ws, grad)
+        th.cuda.synchronize()
+        stats = ws[_desc_stats_offset(L, d):_desc_stats_offset(L, d) + 5].cpu().numpy()
+        out[name] = (logits.cpu().numpy(), grad.cpu().numpy(), stats)
+    # float64 reference
+    Pd = P.double()
+    o = 0
+    W1 = Pd[o:o + 32 * din].view(32, din); o += 32 * din
+    b1 = Pd[o:o + 32]; o += 32
+    W2 = Pd[o:o + 1024].view(32, 32); o += 1024
+    b2 = Pd[o:o + 32]; o += 32
+    wf = Pd[o:o + 32]; o += 32
+    bf = Pd[o]
+    ps = [t.clone().requires_grad_(True) for t in (W1, b1, W2, b2, wf, bf)]
+    x = batch[:din, :n].T.double()
+    lg = th.relu(th.relu(x @ ps[0].T + ps[1]) @ ps[2].T + ps[3]) @ ps[4] + ps[5]
+    y = th.zeros(n, device="cuda", dtype=th.float64)
+    y[:n_exp] = 1
+    loss = th.nn.functional.binary_cross_entropy_with_logits(lg, y)
+    loss.backward()
+    want_g = th.cat([p.grad.ravel() for p in ps]).cpu().numpy()
+    want_l = lg.detach().cpu().numpy()
+    for name in ("tc", "ffma"):
+        lgt, grd, _ = out[name]
+        # north_star: logits within 1e-5 relative (fp32); the floor of 1e-6 absolute covers logits that cancel to ~0
+        np.testing.assert_allclose(lgt, want_l, rtol=1e-5, atol=1e-6, err_msg=f"{name} logits")
+        scale = float(np.abs(want_g).max())
+        np.testing.assert_allclose(grd, want_g, rtol=2e-4, atol=2e-6 * max(scale, 1.0), err_msg=f"{name} grads")
+    # the two kernels agree far inside the tolerance against fp64, and on every statistic
+    np.testing.assert_allclose(out["tc"][0], out["ffma"][0], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(out["tc"][2][2:], out["ffma"][2][2:], rtol=0, atol=0)       # counts: exact
+    np.testing.assert_allclose(out["tc"][2][:2], out["ffma"][2][:2], rtol=2e-6)             # loss / entropy sums
+
+
+def _desc_stats_offset(L, d):
+    """float offset of the reduced statistics inside the workspace (mirror of ws_layout in csrc/imb_disc.cu)."""
+    return (d.n_params + 31) // 32 * 32
+
+
 # ---------------------------------------------------------------------------------------------
 # NormalizedRewardNet scan
 # ---------------------------------------------------------------------------------------------
