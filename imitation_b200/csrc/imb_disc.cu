@@ -18,6 +18,8 @@
 //                  Weights (<34 KB) stay in shared memory; activations never touch HBM.
 //   k_disc_reduce  warp-per-parameter deterministic sum of the per-CTA partials.
 //   k_disc_adam    torch.optim.Adam step + the 9 train statistics.
+#include <stdlib.h>
+
 #include "imb_common.cuh"
 #include "imb_mlp.cuh"
 #include "imb_tile.cuh"
@@ -969,9 +971,12 @@ extern "C" int imb_disc_fwd_bwd(const imb_disc_desc* d, const float* params, con
     const TcPlan T = tc_plan(L);
     const size_t bytes = (size_t)T.total * 4 + 1024;
     static bool attr_set = false;
+    static int cw = 8;
     if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(k_disc_fwdbwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IMB_SMEM_MAX);
-      if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e));
+      if (const char* e = getenv("IMB_TC_CW")) cw = atoi(e) == 16 ? 16 : 8;  // (tuning knob: columns per epilogue thread)
+      cudaError_t e1 = cudaFuncSetAttribute(k_disc_fwdbwd_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IMB_SMEM_MAX);
+      cudaError_t e2 = cudaFuncSetAttribute(k_disc_fwdbwd_tc<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)IMB_SMEM_MAX);
+      if (e1 != cudaSuccess || e2 != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute(tc): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
       attr_set = true;
     }
     IMB_REQUIRE(bytes <= IMB_SMEM_MAX, "tensor-core disc kernel: %zu B of shared memory", bytes);
@@ -979,9 +984,14 @@ extern "C" int imb_disc_fwd_bwd(const imb_disc_desc* d, const float* params, con
     int64_t Gt = imb_num_sms();
     if (Gt > MAXG) Gt = MAXG;
     if (Gt > ntiles) Gt = ntiles;
-    k_disc_fwdbwd_tc<<<(int)Gt, TC_THREADS, bytes, st>>>(L, T, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
-                                                      ws + w.partial, reinterpret_cast<int*>(ws + w.meta),
-                                                      part_stride(d->n_params));
+    if (cw == 8)
+      k_disc_fwdbwd_tc<8><<<(int)Gt, TcCfg<8>::THREADS, bytes, st>>>(L, T, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
+                                                        ws + w.partial, reinterpret_cast<int*>(ws + w.meta),
+                                                        part_stride(d->n_params));
+    else
+      k_disc_fwdbwd_tc<16><<<(int)Gt, TcCfg<16>::THREADS, bytes, st>>>(L, T, params, batch, ld, n, n_expert, loss_scale, grad_out, logits_out,
+                                                         ws + w.partial, reinterpret_cast<int*>(ws + w.meta),
+                                                         part_stride(d->n_params));
     IMB_CHECK_LAUNCH("k_disc_fwdbwd_tc");
     g_last_grid = (int)Gt;
     return 0;

@@ -10,9 +10,10 @@ import torch as th
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from imitation_b200 import _desc, _lib as L  # noqa: E402
 
-NAMES = ["wait: tile staged (bulk copy)", "E0 load + normalise", "E0 split + wait: previous weight-gradient MMAs done",
-         "E0 stores + signal", "wait: M1 (z1)", "E1 ld + relu + split + stores + signal", "wait: M2 (z2)",
-         "E2 ld + head + BCE + dz2 + split + stores + signal", "wait: M3 (dz1')", "E3 ld + mask + split + stores + proxy fence + signal"]
+NAMES = ["wait: tile staged (bulk copy)", "E0 load + normalise + split + TMEM store + signal", "wait: M1 (z1)",
+         "E1 ld + relu + split + stores + signal", "wait: M2 (z2)", "E2 ld + head + BCE + dz2 + split + TMEM store + signal",
+         "wait: previous tile's weight-gradient MMAs drained", "E2 tail: dz2 atoms + x recompute + x atoms", "wait: M3 (dz1')",
+         "E3 ld + mask + split + stores + proxy fence + signal"]
 Do, Da = 17, 6
 d = _desc.disc_desc(Do, Da)
 P = (th.rand(d.n_params, device="cuda") - 0.5) * 0.6

@@ -8,7 +8,8 @@ KEEP = ("gpu__time_duration", "dram__bytes", "launch__", "sm__inst_executed", "s
         "sm__icc_request_hit_rate", "sm__warps_active", "smsp__issue_active", "issue_stalled", "sm__throughput",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared", "smsp__inst_executed_op_shared", "sm__pipe_fma",
         "sm__pipe_fmaheavy", "smsp__inst_executed_pipe_lsu", "sm__cycles_elapsed.max", "lts__t_bytes.sum",
-        "sm__sass_thread_inst_executed_op_ffma", "sm__inst_executed_pipe")
+        "sm__sass_thread_inst_executed_op_ffma", "sm__inst_executed_pipe", "tensor", "tmem", "l1tex__data_pipe_lsu_wavefronts_mem_shared",
+        "smsp__warp_issue_stalled", "sm__pipe_shared")
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 h, u = rows[0], rows[1]
