@@ -84,7 +84,7 @@ SYMBOLS = [
     "imb_ring_advance", "imb_sample_indices", "imb_gather_rows", "imb_rollout", "imb_rollout_row_width", "imb_gae",
     "imb_rollout_advance", "imb_env_reset", "imb_ppo_update", "imb_policy_logp", "imb_state_init",
     "imb_sync_buffer_doubles", "imb_sync_snapshot", "imb_sync_pack", "imb_sync_unpack",
-    "imb_disc_sample_gather", "imb_sample_advance2", "imb_disc_reduce_adam",
+    "imb_disc_sample_gather", "imb_sample_advance2", "imb_disc_reduce_adam", "imb_norm_batch_stats", "imb_norm_fold",
 ]
 
 
@@ -111,7 +111,8 @@ _KERNELS_PER_CALL = {
     "imb_disc_adam": 1, "imb_reward_forward": 1, "imb_reward_norm_scan": 1, "imb_table_store": 1,
     "imb_ring_advance": 1, "imb_sample_indices": 2, "imb_gather_rows": 1, "imb_rollout": 1, "imb_gae": 1,
     "imb_rollout_advance": 1, "imb_env_reset": 1, "imb_ppo_update": 1, "imb_policy_logp": 1,
-    "imb_disc_sample_gather": 1, "imb_sample_advance2": 1, "imb_disc_reduce_adam": 1,
+    "imb_disc_sample_gather": 1, "imb_sample_advance2": 1, "imb_disc_reduce_adam": 1, "imb_norm_batch_stats": 1,
+    "imb_norm_fold": 1,
 }
 
 
@@ -184,6 +185,19 @@ def disc_norm_update(d, batch, ld, n, norm_state, norm_count, ws):
                                       _p(norm_state, th.float32), _p(norm_count, th.int32), _p(ws, th.float32),
                                       _stream()), "imb_disc_norm_update",
            int(d.base.has_norm) + (2 if (d.shaped and d.potential.has_norm) else 0))
+
+
+def norm_batch_stats(d, batch, ld, n, row0, din, norm_state, norm_count, defer, defer_cap, ws):
+    """RunningNorm update of a foreign normaliser (the policy's feature extractor) from batch rows [row0, row0 + din);
+    `defer` = slot list for a later in-order `norm_fold` (None: fold immediately)."""
+    _check(lib().imb_norm_batch_stats(C.byref(d), _p(batch, th.float32), C.c_int64(ld), C.c_int64(n), C.c_int(row0),
+                                      C.c_int(din), _p(norm_state, th.float32), _p(norm_count, th.int32), _p(defer),
+                                      C.c_int(defer_cap), _p(ws, th.float32), _stream()), "imb_norm_batch_stats")
+
+
+def norm_fold(din, defer, norm_state, norm_count):
+    _check(lib().imb_norm_fold(C.c_int(din), _p(defer, th.float32), _p(norm_state, th.float32),
+                               _p(norm_count, th.int32), _stream()), "imb_norm_fold")
 
 
 def disc_fwd_bwd(d, params, norm_state, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, flags, ws):

@@ -83,18 +83,29 @@ class FusedAdamState:
     """Optimiser handle of the fused path (Adam moments are flat device vectors next to the
     parameters; the step itself happens inside `train_disc`)."""
 
-    def __init__(self, n_params: int, device, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, n_params: int, device, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, step_word: Optional[th.Tensor] = None):
         self.exp_avg = th.zeros(n_params, device=device)
         self.exp_avg_sq = th.zeros(n_params, device=device)
         self.hp = _lib.Adam(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps)
-        self.defaults = dict(lr=lr, betas=betas, eps=eps)
+        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps)
+        # the step count (bias correction) lives in the device counter block so that captured graphs advance it;
+        # `step_word` is the one-element int64 view of that word
+        self.step_word = step_word
 
     def state_dict(self):
-        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "defaults": self.defaults}
+        step = int(self.step_word.item()) if self.step_word is not None else 0
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(), "defaults": dict(self.defaults),
+                "step": step}
 
     def load_state_dict(self, sd):
         self.exp_avg.copy_(sd["exp_avg"])
         self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        d = sd.get("defaults")
+        if d:
+            self.defaults = dict(lr=d["lr"], betas=tuple(d["betas"]), eps=d["eps"])
+            self.hp = _lib.Adam(lr=d["lr"], beta1=d["betas"][0], beta2=d["betas"][1], eps=d["eps"])
+        if self.step_word is not None and "step" in sd:  # warm moments with a cold bias correction would overshoot
+            self.step_word.fill_(int(sd["step"]))
 
     def zero_grad(self):
         pass
@@ -142,7 +153,8 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
                        and set(self._disc_opt_kwargs) <= {"lr", "betas", "eps"})
         if fusable_opt:
             eng = self._fused_net.engine()
-            self._disc_opt = FusedAdamState(eng.desc.n_params, self._device, **self._disc_opt_kwargs)
+            self._disc_opt = FusedAdamState(eng.desc.n_params, self._device, **self._disc_opt_kwargs,
+                                            step_word=self.venv.state[_lib.ST_DISC_STEP:_lib.ST_DISC_STEP + 1])
         else:
             self._disc_opt = disc_opt_cls(self._reward_net.parameters(), **self._disc_opt_kwargs)
         self._fused = fusable_opt
@@ -197,6 +209,16 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         self._ev_disc = None
         self._disc_graphs = {}
         self._stage = {}
+        # the reference evaluates `policy.evaluate_actions` on every discriminator minibatch (GAIL
+        # discards the result, common.py:606-615) with the policy still in the train mode SB3's PPO.train left it in,
+        # so a NormalizeFeaturesExtractor's RunningNorm also sees the expert|generator observations.  Reproduced: the
+        # batch moments are computed beside the discriminator update and folded into the policy's statistics, in
+        # order, once the PPO update (which updates the same statistics) has finished.
+        self.reproduce_evaluate_actions_side_effect = True
+        self._pn_cap = 256
+        self._pn_defer = None    # [4 + cap * (2 d_obs + 1)] slot list of deferred batch moments
+        self._pn_pending = 0     # host mirror of the number of slots in use
+        self._ev_fold = None
 
     # -- helpers --------------------------------------------------------------------------------------------------
     @staticmethod
@@ -286,6 +308,7 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         """Order the current stream after every discriminator update enqueued so far (callers of `train_disc_async`
         that go on to touch the reward network on the current stream, e.g. the multi-GPU round sync)."""
         self._join_disc()
+        self._fold_policy_norm()
 
     def _join_disc(self) -> None:
         """Make the current stream wait for the discriminator updates enqueued so far (the next rollout relabels its
@@ -355,6 +378,8 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
 
     def _train_disc_async_on_stream(self, expert_samples, gen_samples, stats_out) -> th.Tensor:
         e_host, g_host = expert_samples is not None, gen_samples is not None
+        if (not self._capturing and self._pn_pending + self.demo_batch_size // self.demo_minibatch_size > self._pn_cap):
+            self.join()  # (hundreds of updates without a train_gen in between: make room in the slot list)
         if e_host:
             self._stage_host(self._check_samples(expert_samples, "expert"), "expert")
         if g_host:
@@ -392,6 +417,8 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
                 _lib.LAUNCHES["count"] += ent[1]
         if not self._capturing:
             self._disc_step += 1
+            if self._side_effect_active() and self._overlap():
+                self._pn_pending += self.demo_batch_size // self.demo_minibatch_size
         return out
 
     def _disc_update_body(self, e_host: bool, g_host: bool, train_mode: bool, out: th.Tensor) -> None:
@@ -427,6 +454,7 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
                 gt = g_table if g_idx is not None else g_table[start:start + mb]
                 _lib.gather_rows(et, e_cap if e_idx is not None else mb, self._tw, ei, mb, self._batch, self._ld, 0)
                 _lib.gather_rows(gt, g_cap if g_idx is not None else mb, self._tw, gi, mb, self._batch, self._ld, mb)
+            self._policy_norm_side_effect(eng, n)
             if self._needs_logp:
                 pp, pn, _ = self.policy.flat_vectors()
                 _lib.policy_logp(self.policy.desc, pp, pn, self._batch, self._ld, n, self._bw - 1)
@@ -441,6 +469,43 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
                                       self.venv.state, out)
         if fused_sampling:
             _lib.sample_advance2(B, self._expert_n, self._expert_state, self.venv.state)
+
+    # -- SURVEY App. A.14 --------------------------------------------------------------------------------------------------
+    def _side_effect_active(self) -> bool:
+        pol = self.gen_algo.policy
+        return bool(self.reproduce_evaluate_actions_side_effect and getattr(pol, "normalize_features", False)
+                    and self._fused and getattr(pol, "training", True))
+
+    def _policy_norm_side_effect(self, eng, n: int) -> None:
+        """RunningNorm.update_stats of the policy's feature extractor on the observations of the current discriminator
+        minibatch (batch rows [0, d_obs)).  Serial path (AIRL): immediately, before log pi is evaluated -- exactly where
+        `evaluate_actions` does it.  Two-stream path (GAIL): moments now, fold after the PPO update (`_fold_policy_norm`)."""
+        if not self._side_effect_active():
+            return
+        pol = self.gen_algo.policy
+        _, pn, pc = pol.flat_vectors()
+        if not self._overlap():
+            _lib.norm_batch_stats(eng.desc, self._batch, self._ld, n, 0, pol.d_obs, pn, pc, None, 0, eng.ws)
+            return
+        if self._pn_defer is None:
+            self._pn_defer = th.zeros(4 + self._pn_cap * (2 * pol.d_obs + 1), device=self._device)
+        _lib.norm_batch_stats(eng.desc, self._batch, self._ld, n, 0, pol.d_obs, pn, pc, self._pn_defer, self._pn_cap,
+                              eng.ws)
+
+    def _fold_policy_norm(self) -> None:
+        """Apply the deferred moments on the CURRENT stream (ordered after the PPO update by stream order and after the
+        discriminator stream by `_join_disc`)."""
+        if self._pn_defer is None or (self._pn_pending == 0 and not self._capturing):
+            return
+        pol = self.gen_algo.policy
+        _, pn, pc = pol.flat_vectors()
+        _lib.norm_fold(pol.d_obs, self._pn_defer, pn, pc)
+        self._pn_pending = 0
+        if not self._capturing and self._disc_stream is not None:  # later updates append to the emptied slot list
+            if self._ev_fold is None:
+                self._ev_fold = th.cuda.Event()
+            self._ev_fold.record()
+            self._disc_stream.wait_event(self._ev_fold)
 
     # -- whole round as one CUDA graph (no host work between kernels) ---------------------------------------------
     def _enqueue_round(self) -> None:
@@ -467,6 +532,8 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
             done = th.cuda.Event()
             done.record(side)
             th.cuda.current_stream().wait_event(done)
+            if self._side_effect_active() and self._pn_defer is not None:
+                self._fold_policy_norm()
 
     def capture_round(self) -> None:
         """Capture [rollout -> GAE -> PPO update -> n_disc x discriminator update] into a CUDA graph.
@@ -496,8 +563,7 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         self._graph.replay()
         _lib.LAUNCHES["count"] += self._graph_launches
         self.gen_algo.after_rollout_host(t0)
-        self.venv_buffering._ep_lens = []
-        self.venv_buffering.n_transitions = 0
+        self.venv_buffering.discard()
         self._global_step += 1
         self._disc_step += self.n_disc_updates_per_round
         return self._round_stats
@@ -576,13 +642,13 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         if total_timesteps is None:
             total_timesteps = self.gen_train_timesteps
         self._join_disc()  # the rollouts are relabelled with the reward network the previous updates produced
+        self._fold_policy_norm()
         with self.logger.accumulate_means("gen"):
             self.gen_algo.learn(total_timesteps=total_timesteps, reset_num_timesteps=False,
                                 callback=self.gen_callback, **(learn_kwargs or {}))
             self._global_step += 1
         ep_lens = list(self.venv_buffering._ep_lens)
-        self.venv_buffering._ep_lens = []
-        self.venv_buffering.n_transitions = 0  # samples were consumed by the fused ring store
+        self.venv_buffering.discard()  # the samples were consumed by the fused ring store
         self._check_fixed_horizon(ep_lens)
 
     def train(self, total_timesteps: int, callback: Optional[Callable[[int], None]] = None) -> None:
@@ -595,6 +661,8 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
             for _ in range(self.n_disc_updates_per_round):
                 with networks.training(self.reward_train):
                     self.train_disc()
+            if self._pn_pending:
+                self.join()
             if callback:
                 callback(r)
             self.logger.dump(self._global_step)

@@ -27,7 +27,8 @@ class DevicePPO:
                  device="cuda", sampling: str = "device", **unused):
         self.device = th.device(device)
         self.n_steps, self.batch_size, self.n_epochs = int(n_steps), int(batch_size), int(n_epochs)
-        self.seed = 0 if seed is None else int(seed)
+        self._user_seed = None if seed is None else int(seed)  # SB3: the global RNGs are seeded only when a seed is given
+        self.seed = 0 if seed is None else int(seed)        # the Philox streams of the kernels always need a key
         self.sampling = sampling
         self.hp = _lib.PpoHparams(gamma=gamma, gae_lambda=gae_lambda, clip_range=clip_range, ent_coef=ent_coef,
                                   vf_coef=vf_coef, max_grad_norm=max_grad_norm, lr=learning_rate, adam_eps=1e-5,
@@ -46,8 +47,8 @@ class DevicePPO:
             kw = dict(policy_kwargs or {})
             if cls is policies.ActorCriticPolicy:
                 kw.setdefault("net_arch", (64, 64))
-            if self.seed is not None:
-                th.manual_seed(self.seed)
+            if self._user_seed is not None:
+                th.manual_seed(self._user_seed)
             self.policy = cls(self._base_env.observation_space, self._base_env.action_space, **kw).to(self.device)
         n = self.policy.desc.n_params
         self.exp_avg = th.zeros(n, device=self.device)
@@ -157,6 +158,8 @@ class DevicePPO:
         """One collect_rollouts + train, replayed from a CUDA graph once it is warm (the kernels read every
         per-call scalar from the device counter block, so the captured launch sequence is exact)."""
         plain = self.noise is None and self.perm is None and self.loss_log is None
+        if self._buffering is not None:
+            self._buffering.before_rollout()
         if not (self.use_cuda_graph and plain) or self._eager_iters < 1 or self._tbl is None:
             self.collect_rollouts()
             if not self._capturing:

@@ -420,7 +420,7 @@ class BasicRewardTrainer(RewardTrainer):
         assert epochs > 0, "Must train for at least one epoch."
         with self.logger.accumulate_means("reward"):
             for epoch_num in range(epochs):
-                train_loss, accumulated_size, n_batches, acc = 0.0, 0, 0, 0.0
+                train_loss, accumulated_size, n_batches, acc, loss_sum = 0.0, 0, 0, 0.0, 0.0
                 self.optim.zero_grad()
                 for fragment_pairs, preferences in dataloader:
                     out = self.loss.forward(fragment_pairs, preferences, self._preference_model)
@@ -428,6 +428,7 @@ class BasicRewardTrainer(RewardTrainer):
                     for name, value in out.metrics.items():
                         self.logger.record(f"epoch-{epoch_num}/train/{name}", value.item())
                     acc += float(out.metrics["accuracy"])
+                    loss_sum += out.loss.item()
                     n_batches += 1
                     # averaged over the whole batch instead of the minibatch (an incomplete batch gets smaller gradients)
                     loss = out.loss * (len(fragment_pairs) / self.batch_size)
@@ -440,7 +441,9 @@ class BasicRewardTrainer(RewardTrainer):
                         accumulated_size = 0
                 if accumulated_size != 0:
                     self.optim.step()  # an incomplete batch remains
-                self.last_epoch_stats = {"loss": train_loss, "accuracy": acc / max(n_batches, 1)}
+                # `reward/final/train/loss` of the reference = mean over the last epoch's minibatches of the UNSCALED
+                # minibatch loss (logger.record("loss", ...) under accumulate_means, preference_comparisons.py:1296-1323)
+                self.last_epoch_stats = {"loss": loss_sum / max(n_batches, 1), "accuracy": acc / max(n_batches, 1)}
         for k, v in self.last_epoch_stats.items():
             self.logger.record(f"reward/final/train/{k}", v)
 

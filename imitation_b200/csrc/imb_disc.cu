@@ -80,7 +80,8 @@ struct NormLaunch {
 __global__ void __launch_bounds__(256) k_norm_stats(NormLaunch L, const float* __restrict__ batch, int64_t ld,
                                                     int64_t n, int chunk_rows, float* __restrict__ run_mean_var,
                                                     int32_t* __restrict__ count, float* __restrict__ snap_out,
-                                                    float* __restrict__ part, unsigned int* __restrict__ ticket) {
+                                                    float* __restrict__ part, unsigned int* __restrict__ ticket,
+                                                    float* __restrict__ defer = nullptr, int defer_cap = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const int64_t r0 = (int64_t)blockIdx.x * chunk_rows;
   const int64_t r1 = min(n, r0 + (int64_t)chunk_rows);
@@ -115,7 +116,15 @@ __global__ void __launch_bounds__(256) k_norm_stats(NormLaunch L, const float* _
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  const int32_t old_count = *count;
+  // deferred mode: the batch moments go to the next free slot of `defer` ([0] = slot counter, slots of 2 * din + 1
+  // floats: mean | biased variance | n) instead of into the running statistics; k_norm_fold applies them later, in order
+  float* slot = nullptr;
+  if (defer) {
+    int k = (int)defer[0];
+    if (k >= defer_cap) k = defer_cap - 1;  // (host folds long before this; never overrun)
+    slot = defer + 4 + (int64_t)k * (2 * L.din + 1);
+  }
+  const int32_t old_count = defer ? 0 : *count;
   // warp per feature: every lane Chan-merges its chunks (lane, lane + 32, ...) in index order, then the 32 lane
   // results are merged by a fixed butterfly (deterministic; a single thread walking all chunks cost more than
   // the statistics themselves once the chunks became small enough to fill the GPU)
@@ -146,7 +155,10 @@ __global__ void __launch_bounds__(256) k_norm_stats(NormLaunch L, const float* _
       }
       na = nt;
     }
-    if (lane == 0) {
+    if (lane == 0 && slot) {
+      slot[k] = ma;
+      slot[L.din + k] = m2a / na;
+    } else if (lane == 0) {
       const float b_mean = ma, b_var = m2a / na, b_n = na;
       float mean = run_mean_var[k], var = run_mean_var[L.din + k];
       const float cnt = (float)old_count;
@@ -167,8 +179,47 @@ __global__ void __launch_bounds__(256) k_norm_stats(NormLaunch L, const float* _
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    *count = old_count + (int32_t)n;
+    if (slot) {
+      slot[2 * L.din] = (float)n;
+      defer[0] += 1.0f;
+    } else {
+      *count = old_count + (int32_t)n;
+    }
     *ticket = 0u;  // re-arm for the next launch
+  }
+}
+
+// fold the deferred batch moments into the running statistics, slot by slot, with RunningNorm.update_stats'
+// arithmetic (util/networks.py:121-134) -- the same expressions as the in-kernel fold of k_norm_stats
+__global__ void k_norm_fold(int din, float* __restrict__ defer, float* __restrict__ run_mean_var,
+                            int32_t* __restrict__ count) {
+  const int K = (int)defer[0];
+  const int k = threadIdx.x;
+  int32_t cnt_i = *count;
+  if (k < din) {
+    float mean = run_mean_var[k], var = run_mean_var[din + k];
+    int32_t c = cnt_i;
+    for (int sidx = 0; sidx < K; ++sidx) {
+      const float* slot = defer + 4 + (int64_t)sidx * (2 * din + 1);
+      const float b_mean = slot[k], b_var = slot[din + k], b_n = slot[2 * din];
+      const float cnt = (float)c;
+      const float tot = cnt + b_n;
+      const float delta = b_mean - mean;
+      mean += delta * b_n / tot;
+      var *= cnt;
+      var += b_var * b_n;
+      var += delta * delta * cnt * b_n / tot;
+      var /= tot;
+      c += (int32_t)b_n;
+    }
+    run_mean_var[k] = mean;
+    run_mean_var[din + k] = var;
+  }
+  __syncthreads();
+  if (k == 0) {
+    for (int sidx = 0; sidx < K; ++sidx) cnt_i += (int32_t)defer[4 + (int64_t)sidx * (2 * din + 1) + 2 * din];
+    *count = cnt_i;
+    defer[0] = 0.f;
   }
 }
 
@@ -890,6 +941,32 @@ extern "C" int imb_disc_norm_update(const imb_disc_desc* d, const float* batch, 
     for (int k = 0; k < d->potential.din; ++k) rows[k] = L.stage_row[L.pass[2].in_slot[k]];
     if (int rc = norm_launch(d->potential, rows, batch, ld, n, norm_state, norm_count, nullptr, ws, w, st)) return rc;
   }
+  return 0;
+}
+
+extern "C" int imb_norm_batch_stats(const imb_disc_desc* d, const float* batch, int64_t ld, int64_t n, int row0, int din,
+                                    float* norm_state, int32_t* norm_count, float* defer, int defer_cap, float* ws,
+                                    void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IMB_REQUIRE(n >= 1 && din >= 1 && din <= IMB_MAX_DIN, "norm batch stats: bad sizes");
+  IMB_REQUIRE(defer == nullptr || defer_cap >= 1, "norm batch stats: defer_cap");
+  const WsLayout w = ws_layout(d->n_params);
+  NormLaunch NL;
+  NL.din = din;
+  for (int k = 0; k < din; ++k) NL.row[k] = (short)(row0 + k);
+  const int chunk_rows = n <= (int64_t)128 * 2048 ? 128 : NORM_CHUNK;
+  const int chunks = (int)((n + chunk_rows - 1) / chunk_rows);
+  IMB_REQUIRE(chunks >= 1 && chunks <= MAXCHUNKS, "norm update: n=%lld out of range", (long long)n);
+  k_norm_stats<<<chunks, 256, 0, st>>>(NL, batch, ld, n, chunk_rows, norm_state, norm_count, nullptr, ws + w.normpart,
+                                       reinterpret_cast<unsigned int*>(ws + w.ticket), defer, defer_cap);
+  IMB_CHECK_LAUNCH("k_norm_stats(batch)");
+  return 0;
+}
+
+extern "C" int imb_norm_fold(int din, float* defer, float* norm_state, int32_t* norm_count, void* stream) {
+  IMB_REQUIRE(din >= 1 && din <= IMB_MAX_DIN, "norm fold: din");
+  k_norm_fold<<<1, 64, 0, (cudaStream_t)stream>>>(din, defer, norm_state, norm_count);
+  IMB_CHECK_LAUNCH("k_norm_fold");
   return 0;
 }
 

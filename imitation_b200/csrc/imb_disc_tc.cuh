@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(TcCfg<CW>::THREADS, 1)
                      int* __restrict__ meta, int64_t pstride) {
   constexpr int TC_EPI_WARPS = TcCfg<CW>::EPI_WARPS, TC_EPI_THREADS = TcCfg<CW>::EPI_THREADS,
                 TC_THREADS = TcCfg<CW>::THREADS, NH = TcCfg<CW>::NH, NP = CW / 4;
-  extern __shared__ __align__(1024) float smem[];
+  // (the swizzled operand atoms need a 1024-byte aligned base; another kernel of this translation unit declares the
+  //  dynamic shared array with a smaller alignment, so align by hand -- the launch adds 1 KB of slack)
+  extern __shared__ float tc_smem_raw[];
+  float* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u) / 4;
   __shared__ __align__(8) TcBars bars;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

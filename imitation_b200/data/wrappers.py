@@ -30,6 +30,10 @@ class BufferingWrapper:
         self._env_rews: Optional[th.Tensor] = None  # [E][T] ground-truth env rewards of the last rollout
         self._last: Optional[Tuple[int, int, int]] = None  # (T, t0, H) of the last rollout
         self._ep_lens: List[int] = []
+        # earlier rollouts that have not been popped yet (the reference buffers every step until pop): per-env step
+        # arrays [E][T_k][tw] and rewards [E][T_k], oldest first
+        self._hist: List[Tuple[np.ndarray, np.ndarray, int]] = []
+        self._unsaved = False  # the device buffers hold a rollout that is not in `_hist` yet
 
     # -- plumbing used by DevicePPO / AdversarialTrainer ------------------------------------------------------
     @property
@@ -49,17 +53,25 @@ class BufferingWrapper:
         E = self.num_envs
         tw = _desc.table_width(self.venv.d_obs, self.venv.d_act)
         if self._flat is None or self._flat.shape[0] != E * n_steps:
+            self.before_rollout()
             self._flat = th.zeros(E * n_steps, tw, device=self.venv.device)
-        if self.n_transitions:
-            raise NotImplementedError("collecting a second rollout before pop_trajectories()/pop_transitions() is "
-                                      "not supported by the device BufferingWrapper")
         return self._flat, self._ring
+
+    def before_rollout(self) -> None:
+        """Called before every rollout (eager or graph replay): a rollout that is still waiting to be popped is copied
+        off the device buffers the next one overwrites (several PPO rollouts per `train_gen`, common.py:408-419)."""
+        if self._unsaved and self.n_transitions and self._flat is not None:
+            T, t0, H = self._last
+            self._hist.append((self._unflatten(self._flat.cpu().numpy(), T, t0, H),
+                               self._env_rews.cpu().numpy().reshape(self.num_envs, T).copy(), t0))
+        self._unsaved = False
 
     def after_rollout(self, n_steps: int, t0: int, env_rews: th.Tensor) -> None:
         H = self.venv.horizon
         self._last = (n_steps, t0, H)
         self._env_rews = env_rews
         self.n_transitions = (self.n_transitions or 0) + self.num_envs * n_steps
+        self._unsaved = True
         self._ep_lens += [H] * (self.num_envs * ((t0 + n_steps) // H))
         if self._ring is not None:
             self._ring.note_stored(self.num_envs * n_steps)
@@ -72,38 +84,67 @@ class BufferingWrapper:
         self.n_transitions = 0
         return self.venv.reset(**kwargs)
 
-    def _segments(self):
-        T, t0, H = self._last
+    @staticmethod
+    def _segments_of(T: int, t0: int, H: int):
         bounds = [0] + [b for b in range(H - t0, T, H)] + [T]
         return [(bounds[i], bounds[i + 1]) for i in range(len(bounds) - 1) if bounds[i + 1] > bounds[i]]
 
-    def _flat_rews(self) -> np.ndarray:
-        T, t0, H = self._last
+    def _segments(self):
+        return self._segments_of(*self._last)
+
+    def _unflatten(self, flat: np.ndarray, T: int, t0: int, H: int) -> np.ndarray:
+        """reference-ordered rows [segment][env][step] -> per-env step arrays [E][T][tw]"""
         E = self.num_envs
-        r = self._env_rews.cpu().numpy().reshape(E, T)
-        return np.concatenate([r[:, a:b].reshape(-1) for a, b in self._segments()])
+        out = np.empty((E, T, flat.shape[1]), flat.dtype)
+        off = 0
+        for a, b in self._segments_of(T, t0, H):
+            out[:, a:b] = flat[off:off + E * (b - a)].reshape(E, b - a, -1)
+            off += E * (b - a)
+        return out
+
+    def _collect(self):
+        """All buffered steps since the last pop as ([E][T][tw] rows, [E][T] env rewards, T, t0): the rollouts the
+        reference's wrapper would have accumulated, joined in time."""
+        T, t0, H = self._last
+        rows = [h[0] for h in self._hist] + [self._unflatten(self._flat.cpu().numpy(), T, t0, H)]
+        rews = [h[1] for h in self._hist] + [self._env_rews.cpu().numpy().reshape(self.num_envs, T)]
+        t0_all = self._hist[0][2] if self._hist else t0
+        rows, rews = np.concatenate(rows, 1), np.concatenate(rews, 1)
+        return rows, rews, rows.shape[1], t0_all
 
     def pop_transitions(self) -> types.TransitionsWithRew:
         if not self.n_transitions:
             raise RuntimeError("Called pop_transitions on an empty BufferingWrapper")
         v = self.venv
-        out = buffer_mod.rows_to_transitions(self._flat.cpu().numpy(), v.d_obs, v.d_act, v.observation_space.shape,
+        H = self.venv.horizon
+        rows, rews, T, t0 = self._collect()
+        segs = self._segments_of(T, t0, H)
+        flat = np.concatenate([rows[:, a:b].reshape(-1, rows.shape[2]) for a, b in segs])
+        frews = np.concatenate([rews[:, a:b].reshape(-1) for a, b in segs])
+        out = buffer_mod.rows_to_transitions(flat, v.d_obs, v.d_act, v.observation_space.shape,
                                              v.action_space.shape, v.observation_space.dtype, v.action_space.dtype,
-                                             v.discrete, rews=self._flat_rews().astype(np.float32))
+                                             v.discrete, rews=frews.astype(np.float32))
         assert len(out.obs) == self.n_transitions
+        self._popped = (T, t0, H)
+        self.discard()
+        return out
+
+    def discard(self) -> None:
+        """Forget the buffered steps (AdversarialTrainer.train_gen: they already went into the replay ring)."""
         self.n_transitions = 0
         self._ep_lens = []
-        return out
+        self._hist = []
+        self._unsaved = False
 
     def pop_trajectories(self) -> Tuple[Sequence[types.TrajectoryWithRew], Sequence[int]]:
         if not self.n_transitions:
             return [], []
         ep_lens = list(self._ep_lens)
         tr = self.pop_transitions()
-        T, t0, H = self._last
+        T, t0, H = self._popped
         E = self.num_envs
         trajs, off = [], 0
-        segs = self._segments()
+        segs = self._segments_of(T, t0, H)
         for si, (a, b) in enumerate(segs):
             L = b - a
             terminal = (t0 + b) % H == 0

@@ -110,6 +110,19 @@ int64_t imb_disc_workspace_floats(const imb_disc_desc* d);
 int imb_disc_norm_update(const imb_disc_desc* d, const float* batch, int64_t ld, int64_t n,
                          float* norm_state, int32_t* norm_count, float* ws, void* stream);
 
+/* RunningNorm.update_stats (util/networks.py:111-134) over `din` consecutive feature rows [row0, row0 + din) of a
+ * feature-major batch, for a normaliser that is NOT the discriminator's own: the generator policy's
+ * NormalizeFeaturesExtractor, which the reference updates as a side effect of `policy.evaluate_actions` on every
+ * discriminator minibatch (algorithms/adversarial/common.py:606-615 with the policy left in train mode by SB3's
+ * PPO.train).  defer == NULL: fold into (norm_state = [mean | var], norm_count) immediately.  defer != NULL: append the
+ * batch moments to the slot list `defer` ([0] = number of slots in use, [4 + k * (2 din + 1) ...] = mean | var | n) so that
+ * the update can be computed on a stream that runs beside the PPO update and applied afterwards, in order, by
+ * imb_norm_fold.  `d` / `ws`: any discriminator descriptor + its workspace (chunk partials live there). */
+int imb_norm_batch_stats(const imb_disc_desc* d, const float* batch, int64_t ld, int64_t n, int row0, int din,
+                                 float* norm_state, int32_t* norm_count, float* defer, int defer_cap, float* ws,
+                                 void* stream);
+int imb_norm_fold(int din, float* defer, float* norm_state, int32_t* norm_count, void* stream);
+
 /* Fused forward + BCE-with-logits + backward over one minibatch of n = 2*mb rows (expert rows
  * first: label 1, generator rows second: label 0), gradients ACCUMULATED into ws (scaled by
  * loss_scale = 1/(2*B), common.py:360-369).  Replaces RewardNet.forward + F.binary_cross_

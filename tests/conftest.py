@@ -20,3 +20,15 @@ def _torch_threads():
 
     torch.set_num_threads(min(4, os.cpu_count() or 1))
     yield
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests skip (instead of failing inside the first kernel launch) on a box without a CUDA device."""
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)

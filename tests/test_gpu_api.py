@@ -330,6 +330,31 @@ def test_buffering_wrapper_pop_matches_oracle_order():
         tr.venv_buffering.pop_transitions()
 
 
+def test_several_rollouts_per_learn_are_buffered_like_the_reference():
+    """`learn(total_timesteps)` larger than one rollout (common.py:408-419 allows any `gen_train_timesteps`): the wrapper
+    keeps every step until the pop, so three rollouts of 4 steps pop exactly what one rollout of 12 steps pops (the
+    generator's learning rate is 0 so the policy -- and with it the trajectories -- are the same on both sides; the second
+    and third rollout of the split run are CUDA-graph replays)."""
+    kw = dict(Do=5, Da=2, E=6, H=7, B=16, net_kwargs={}, seed=2, learning_rate=0.0)
+    a, _ = _mk(T=4, **kw)
+    b, _ = _mk(T=12, **kw)
+    a.gen_algo.learn(3 * 6 * 4)
+    b.gen_algo.learn(6 * 12)
+    assert a.venv_buffering.n_transitions == b.venv_buffering.n_transitions == 72
+    ta, la = a.venv_buffering.pop_trajectories()
+    tb, lb = b.venv_buffering.pop_trajectories()
+    assert la == lb and len(ta) == len(tb)
+    for x, y in zip(ta, tb):
+        np.testing.assert_array_equal(x.obs, y.obs)
+        np.testing.assert_array_equal(x.acts, y.acts)
+        np.testing.assert_array_equal(x.rews, y.rews)
+        assert x.terminal == y.terminal
+    # and through the trainer: two rollouts per round, both end up in the replay ring
+    c, _ = _mk(T=4, **kw)
+    c.train_gen(2 * 6 * 4)
+    assert c._gen_replay_buffer.size() == min(48, c._gen_replay_buffer.capacity) and c.venv_buffering.n_transitions == 0
+
+
 # ---- whole round: graph replay == eager; device sampling twins -------------------------------------------------------
 def test_graph_round_equals_eager_round():
     a, _ = _mk(E=64, T=4, H=50, B=128, cap=96, n_disc=3, norm_features=True, seed=5)
