@@ -85,6 +85,7 @@ SYMBOLS = [
     "imb_rollout_advance", "imb_env_reset", "imb_ppo_update", "imb_policy_logp", "imb_state_init",
     "imb_sync_buffer_doubles", "imb_sync_snapshot", "imb_sync_pack", "imb_sync_unpack",
     "imb_disc_sample_gather", "imb_sample_advance2", "imb_disc_reduce_adam", "imb_norm_batch_stats", "imb_norm_fold",
+    "imb_disc_set_rows",
 ]
 
 
@@ -112,7 +113,7 @@ _KERNELS_PER_CALL = {
     "imb_ring_advance": 1, "imb_sample_indices": 2, "imb_gather_rows": 1, "imb_rollout": 1, "imb_gae": 1,
     "imb_rollout_advance": 1, "imb_env_reset": 1, "imb_ppo_update": 1, "imb_policy_logp": 1,
     "imb_disc_sample_gather": 1, "imb_sample_advance2": 1, "imb_disc_reduce_adam": 1, "imb_norm_batch_stats": 1,
-    "imb_norm_fold": 1,
+    "imb_norm_fold": 1, "imb_disc_set_rows": 1,
 }
 
 
@@ -195,9 +196,14 @@ def norm_batch_stats(d, batch, ld, n, row0, din, norm_state, norm_count, defer, 
                                       C.c_int(defer_cap), _p(ws, th.float32), _stream()), "imb_norm_batch_stats")
 
 
-def norm_fold(din, defer, norm_state, norm_count):
+def norm_fold(din, defer, norm_state, norm_count, n_slots=0):
     _check(lib().imb_norm_fold(C.c_int(din), _p(defer, th.float32), _p(norm_state, th.float32),
-                               _p(norm_count, th.int32), _stream()), "imb_norm_fold")
+                               _p(norm_count, th.int32), C.c_int(n_slots), _stream()), "imb_norm_fold")
+
+
+def disc_set_rows(d, ws, n_rows_total, n_expert_total):
+    _check(lib().imb_disc_set_rows(C.byref(d), _p(ws, th.float32), C.c_int64(n_rows_total), C.c_int64(n_expert_total),
+                                   _stream()), "imb_disc_set_rows")
 
 
 def disc_fwd_bwd(d, params, norm_state, batch, ld, n, n_expert, loss_scale, grad_out, logits_out, flags, ws):

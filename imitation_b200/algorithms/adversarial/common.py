@@ -219,6 +219,13 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         self._pn_defer = None    # [4 + cap * (2 d_obs + 1)] slot list of deferred batch moments
         self._pn_pending = 0     # host mirror of the number of slots in use
         self._ev_fold = None
+        # multi-GPU (set_distributed): the discriminator is the GLOBAL-batch discriminator -- every optimiser step
+        # all-reduces [gradients | statistic sums] and all-gathers the RunningNorm batch moments, so the replicas apply
+        # bit-identical updates (reference loss = mean over the global 2 * minibatch rows, common.py:360-368)
+        self._dist_group = None
+        self._dist_world = 1
+        self._dn_local = None    # my batch moments (one slot)
+        self._dn_all = None      # the gathered slot list
 
     # -- helpers --------------------------------------------------------------------------------------------------
     @staticmethod
@@ -459,16 +466,65 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
                 pp, pn, _ = self.policy.flat_vectors()
                 _lib.policy_logp(self.policy.desc, pp, pn, self._batch, self._ld, n, self._bw - 1)
             tn = train_mode and eng.has_norm
-            if tn:
+            W = self._dist_world
+            if tn and W > 1:
+                self._global_norm_update(eng, n)
+            elif tn:
                 eng.norm_update(self._batch, self._ld, n)
-            eng.fwd_bwd(self._batch, self._ld, n, mb, 1.0 / (2 * B), None, self._logits, i == 0, tn)
+            eng.fwd_bwd(self._batch, self._ld, n, mb, 1.0 / (2 * B * W), None, self._logits, i == 0, tn)
             if i + 1 < len(starts):
                 eng.reduce(None)
+            elif W > 1:  # global-batch step: sum [gradients | statistic sums] over the ranks, identical Adam everywhere
+                import torch.distributed as dist
+
+                eng.reduce(None)
+                k = (eng.desc.n_params + 31) // 32 * 32 + 5
+                dist.all_reduce(eng.ws[:k], op=dist.ReduceOp.SUM, group=self._dist_group)
+                _lib.disc_set_rows(eng.desc, eng.ws, n * W, mb * W)
+                _lib.disc_adam(eng.desc, opt.hp, eng.params, opt.exp_avg, opt.exp_avg_sq, None, 1.0, eng.ws,
+                               self.venv.state, out)
             else:  # last minibatch: reduction, optimiser step and the statistics in one launch
                 _lib.disc_reduce_adam(eng.desc, opt.hp, eng.params, opt.exp_avg, opt.exp_avg_sq, 1.0, eng.ws,
                                       self.venv.state, out)
         if fused_sampling:
             _lib.sample_advance2(B, self._expert_n, self._expert_state, self.venv.state)
+
+    def _global_norm_update(self, eng, n: int) -> None:
+        """RunningNorm.update_stats with the GLOBAL minibatch: local moments -> all-gather -> the W batches are folded in
+        rank order on every rank (identical arithmetic, identical result)."""
+        import torch.distributed as dist
+
+        d = eng.desc
+        slot = 2 * d.base.din + 1
+        _lib.norm_batch_stats(d, self._batch, self._ld, n, 0, d.base.din, eng.norm_state, eng.norm_count,
+                              self._dn_local, 1, eng.ws)
+        dist.all_gather_into_tensor(self._dn_all[4:], self._dn_local[4:4 + slot], group=self._dist_group)
+        _lib.norm_fold(d.base.din, self._dn_all, eng.norm_state, eng.norm_count, self._dist_world)
+
+    # -- multi-GPU -----------------------------------------------------------------------------------------------------------
+    def set_distributed(self, group=None) -> None:
+        """One process per GPU (`torch.distributed` initialised): shard = this trainer's env slice, ring and sampling
+        streams; discriminator steps become global-batch steps (see __init__).  The generator side is synchronised by
+        `imitation_b200.distributed.trainer_round_sync(self)` once per round."""
+        import torch.distributed as dist
+
+        if not self._fused:
+            raise NotImplementedError("distributed training needs the fused Adam path")
+        d = self._fused_net.engine().desc
+        if d.shaped or d.use_next_state or d.use_done:
+            raise NotImplementedError("distributed discriminator steps: BasicRewardNet(state, action) only")
+        self._dist_group = group
+        self._dist_world = dist.get_world_size(group)
+        slot = 2 * d.base.din + 1
+        self._dn_local = th.zeros(4 + slot, device=self._device)
+        self._dn_all = th.zeros(4 + self._dist_world * slot, device=self._device)
+        self._disc_graphs = {}
+        self._graph = None
+        # the replicas start from rank 0's discriminator (parameters, Adam state, RunningNorm statistics, step counter)
+        eng, opt = self._fused_net.engine(), self._disc_opt
+        for t in (eng.params, opt.exp_avg, opt.exp_avg_sq, eng.norm_state, eng.norm_count,
+                  self.venv.state[_lib.ST_DISC_STEP:_lib.ST_DISC_STEP + 1]):
+            dist.broadcast(t, 0, group=group)
 
     # -- SURVEY App. A.14 --------------------------------------------------------------------------------------------------
     def _side_effect_active(self) -> bool:

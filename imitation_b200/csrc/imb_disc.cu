@@ -192,8 +192,8 @@ __global__ void __launch_bounds__(256) k_norm_stats(NormLaunch L, const float* _
 // fold the deferred batch moments into the running statistics, slot by slot, with RunningNorm.update_stats'
 // arithmetic (util/networks.py:121-134) -- the same expressions as the in-kernel fold of k_norm_stats
 __global__ void k_norm_fold(int din, float* __restrict__ defer, float* __restrict__ run_mean_var,
-                            int32_t* __restrict__ count) {
-  const int K = (int)defer[0];
+                            int32_t* __restrict__ count, int k_fixed) {
+  const int K = k_fixed > 0 ? k_fixed : (int)defer[0];
   const int k = threadIdx.x;
   int32_t cnt_i = *count;
   if (k < din) {
@@ -219,7 +219,7 @@ __global__ void k_norm_fold(int din, float* __restrict__ defer, float* __restric
   if (k == 0) {
     for (int sidx = 0; sidx < K; ++sidx) cnt_i += (int32_t)defer[4 + (int64_t)sidx * (2 * din + 1) + 2 * din];
     *count = cnt_i;
-    defer[0] = 0.f;
+    if (k_fixed <= 0) defer[0] = 0.f;
   }
 }
 
@@ -963,10 +963,23 @@ extern "C" int imb_norm_batch_stats(const imb_disc_desc* d, const float* batch, 
   return 0;
 }
 
-extern "C" int imb_norm_fold(int din, float* defer, float* norm_state, int32_t* norm_count, void* stream) {
+extern "C" int imb_norm_fold(int din, float* defer, float* norm_state, int32_t* norm_count, int n_slots, void* stream) {
   IMB_REQUIRE(din >= 1 && din <= IMB_MAX_DIN, "norm fold: din");
-  k_norm_fold<<<1, 64, 0, (cudaStream_t)stream>>>(din, defer, norm_state, norm_count);
+  k_norm_fold<<<1, 64, 0, (cudaStream_t)stream>>>(din, defer, norm_state, norm_count, n_slots);
   IMB_CHECK_LAUNCH("k_norm_fold");
+  return 0;
+}
+
+// multi-GPU: the statistics of the last minibatch were summed over the ranks -> the row counts k_disc_adam divides by
+// are the global ones
+__global__ void k_set_rows(int* meta, int64_t n, int64_t n_expert) {
+  meta[1] = (int)n;
+  meta[2] = (int)n_expert;
+}
+extern "C" int imb_disc_set_rows(const imb_disc_desc* d, float* ws, int64_t n, int64_t n_expert, void* stream) {
+  const WsLayout w = ws_layout(d->n_params);
+  k_set_rows<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<int*>(ws + w.meta), n, n_expert);
+  IMB_CHECK_LAUNCH("k_set_rows");
   return 0;
 }
 

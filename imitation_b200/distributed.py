@@ -139,7 +139,12 @@ def trainer_round_sync(trainer, group=None) -> RoundSync:
     pp, pn, pc = gen.policy.flat_vectors()
     eng = trainer._fused_net.engine()
     opt = trainer._disc_opt
-    averaged = [pp, gen.exp_avg, gen.exp_avg_sq, eng.params, opt.exp_avg, opt.exp_avg_sq]
+    # a trainer in distributed mode (`set_distributed`) keeps its discriminator replicas identical by itself: every
+    # optimiser step is a global-batch step (gradient all-reduce).  Only the generator is synchronised per round then.
+    disc_is_global = getattr(trainer, "_dist_world", 1) > 1
+    averaged = [pp, gen.exp_avg, gen.exp_avg_sq]
+    if not disc_is_global:
+        averaged += [eng.params, opt.exp_avg, opt.exp_avg_sq]
     norms: List[NormStat] = []
     if gen.policy.normalize_features:
         k = gen.policy.d_obs
@@ -147,6 +152,8 @@ def trainer_round_sync(trainer, group=None) -> RoundSync:
     off = 0
     for i, n in enumerate([m for m in eng._norms() if m is not None]):
         k = n.running_mean.numel()
-        norms.append(NormStat(eng.norm_state[off:off + k], eng.norm_state[off + k:off + 2 * k], eng.norm_count[i:i + 1]))
+        if not disc_is_global:
+            norms.append(NormStat(eng.norm_state[off:off + k], eng.norm_state[off + k:off + 2 * k],
+                                  eng.norm_count[i:i + 1]))
         off += 2 * k
     return RoundSync(averaged, norms, group)

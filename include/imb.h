@@ -121,7 +121,13 @@ int imb_disc_norm_update(const imb_disc_desc* d, const float* batch, int64_t ld,
 int imb_norm_batch_stats(const imb_disc_desc* d, const float* batch, int64_t ld, int64_t n, int row0, int din,
                                  float* norm_state, int32_t* norm_count, float* defer, int defer_cap, float* ws,
                                  void* stream);
-int imb_norm_fold(int din, float* defer, float* norm_state, int32_t* norm_count, void* stream);
+int imb_norm_fold(int din, float* defer, float* norm_state, int32_t* norm_count, int n_slots /* <= 0: the list's own
+                  counter, which is then reset; > 0: exactly that many slots (an all-gathered list), no reset */,
+                  void* stream);
+/* multi-GPU discriminator step: after the [gradient | statistic sums] block at the start of the workspace
+ * (n_params rounded up to 32 floats, then 5 sums) has been all-reduced over the ranks, record the GLOBAL row counts that
+ * imb_disc_adam's statistics divide by (common.py:52-77 over the global 2 * minibatch rows). */
+int imb_disc_set_rows(const imb_disc_desc* d, float* ws, int64_t n_rows_total, int64_t n_expert_total, void* stream);
 
 /* Fused forward + BCE-with-logits + backward over one minibatch of n = 2*mb rows (expert rows
  * first: label 1, generator rows second: label 0), gradients ACCUMULATED into ws (scaled by

@@ -338,25 +338,37 @@ def preference_case():
     print("wrote preference")
 
 
+def all_cases():
+    """Every golden file of tests/golden/, (name, thunk) in generation order (shared with
+    tests/test_oracle_vs_reference.py, which regenerates ALL of them from the reference)."""
+    RN = ref_networks.RunningNorm
+    return [
+        ("disc_gail_hc", lambda: disc_case("disc_gail_hc", "gail", 17, 6, False, dict(normalize_input_layer=RN), 64, 64, 4, 0)),
+        ("disc_gail_hc_minibatch", lambda: disc_case("disc_gail_hc_minibatch", "gail", 17, 6, False,
+                                                     dict(normalize_input_layer=RN), 64, 16, 3, 1)),
+        ("disc_gail_nonorm", lambda: disc_case("disc_gail_nonorm", "gail", 11, 3, False, dict(hid_sizes=(32,)), 32, 32, 3, 2)),
+        ("disc_gail_cartpole", lambda: disc_case("disc_gail_cartpole", "gail", 4, 2, True, dict(hid_sizes=(64, 64)), 32, 32, 3, 3)),
+        ("disc_gail_allinputs", lambda: disc_case("disc_gail_allinputs", "gail", 5, 2, False,
+                                                  dict(use_next_state=True, use_done=True, normalize_input_layer=RN), 16, 8, 3, 4)),
+        ("disc_airl_hc", lambda: disc_case("disc_airl_hc", "airl", 17, 6, False, dict(normalize_input_layer=RN), 64, 32, 4, 5,
+                                           shaped=True)),
+        ("disc_airl_nonorm", lambda: disc_case("disc_airl_nonorm", "airl", 6, 2, False,
+                                               dict(reward_hid_sizes=(32, 32), potential_hid_sizes=(32,)), 16, 16, 3, 6,
+                                               shaped=True)),
+        ("running_norm", running_norm_case),
+        ("replay_buffer", buffer_case),
+        ("rollout_order", rollout_case),
+        ("reward_relabel", relabel_case),
+        ("expert_loader", expert_loader_case),
+        ("train_stats", train_stats_case),
+        ("preference", preference_case),
+    ]
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "preference":
         preference_case()
         sys.exit(0)
-    RN = ref_networks.RunningNorm
-    disc_case("disc_gail_hc", "gail", 17, 6, False, dict(normalize_input_layer=RN), 64, 64, 4, 0)
-    disc_case("disc_gail_hc_minibatch", "gail", 17, 6, False, dict(normalize_input_layer=RN), 64, 16, 3, 1)
-    disc_case("disc_gail_nonorm", "gail", 11, 3, False, dict(hid_sizes=(32,)), 32, 32, 3, 2)
-    disc_case("disc_gail_cartpole", "gail", 4, 2, True, dict(hid_sizes=(64, 64)), 32, 32, 3, 3)
-    disc_case("disc_gail_allinputs", "gail", 5, 2, False,
-              dict(use_next_state=True, use_done=True, normalize_input_layer=RN), 16, 8, 3, 4)
-    disc_case("disc_airl_hc", "airl", 17, 6, False, dict(normalize_input_layer=RN), 64, 32, 4, 5, shaped=True)
-    disc_case("disc_airl_nonorm", "airl", 6, 2, False, dict(reward_hid_sizes=(32, 32), potential_hid_sizes=(32,)),
-              16, 16, 3, 6, shaped=True)
-    running_norm_case()
-    buffer_case()
-    rollout_case()
-    relabel_case()
-    expert_loader_case()
-    train_stats_case()
-    preference_case()
+    for _name, _thunk in all_cases():
+        _thunk()

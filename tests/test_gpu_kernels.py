@@ -13,6 +13,7 @@ from tests import golden_util as G
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-5
+LOGIT_RTOL, LOGIT_ATOL = 1e-5, 1e-6   # north_star: logits within 1e-5 relative (fp32)
 
 
 @pytest.fixture(scope="module")
@@ -251,13 +252,17 @@ def test_disc_update_matches_reference_golden(L, name):
         L.gather_rows(tq, nq, tw, None, nq, bq, ldq, 0)
         bq[bw - 1, :nq] = dev(z[f"step{s}/query_logp"])
         out = th.zeros(nq, device="cuda")
+        # north_star: discriminator logits within 1e-5 relative.  The forward is evaluated with the REFERENCE's parameters
+        # and statistics of this step (our own have drifted by up to the 1e-5 / 2e-6 asserted above, which would be
+        # measured instead of the kernel); LOGIT_ATOL covers logits that cancel to ~0 (|logit| <~ 0.1 in these cases).
+        Pq, NSq = dev(wp), (dev(wn) if len(wn) else NS)
+        L.reward_forward(d, Pq, NSq, bq, ldq, nq, 1, out)
+        np.testing.assert_allclose(out.cpu().numpy(), z[f"step{s}/query_logits"], rtol=LOGIT_RTOL, atol=LOGIT_ATOL)
+        L.reward_forward(d, Pq, NSq, bq, ldq, nq, 2 if algo == "gail" else 0, out)
+        np.testing.assert_allclose(out.cpu().numpy(), z[f"step{s}/reward_train"], rtol=LOGIT_RTOL, atol=LOGIT_ATOL)
+        # and with our own parameters: the drift stays inside the parameter tolerance propagated through the net
         L.reward_forward(d, P, NS, bq, ldq, nq, 1, out)
         np.testing.assert_allclose(out.cpu().numpy(), z[f"step{s}/query_logits"], rtol=1e-4, atol=2e-5)
-        L.reward_forward(d, P, NS, bq, ldq, nq, 2 if algo == "gail" else 0, out)
-        if not (algo == "airl"):
-            np.testing.assert_allclose(out.cpu().numpy(), z[f"step{s}/reward_train"], rtol=1e-4, atol=2e-5)
-        else:
-            np.testing.assert_allclose(out.cpu().numpy(), z[f"step{s}/reward_train"], rtol=1e-4, atol=2e-5)
     assert int(st[L.ST_DISC_STEP]) == steps
 
 
@@ -302,7 +307,7 @@ def test_disc_fwd_bwd_large_against_torch_fp32(L):
     lg, loss = _torch_disc_reference(Do, Da, 32, batch[:Do, :n].T, batch[Do:Do + Da, :n].T, ps, n // 2)
     loss.backward()
     want = th.cat([p.grad.ravel() for p in ps])
-    np.testing.assert_allclose(logits.cpu().numpy(), lg.detach().cpu().numpy(), rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(logits.cpu().numpy(), lg.detach().cpu().numpy(), rtol=LOGIT_RTOL, atol=2e-6)
     scale = float(want.abs().max())
     np.testing.assert_allclose(grad.cpu().numpy(), want.cpu().numpy(), rtol=1e-3, atol=1e-5 * max(scale, 1.0))
 
