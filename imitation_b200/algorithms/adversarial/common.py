@@ -646,8 +646,7 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
             if self._fused:
                 stats_t = self.train_disc_async(expert_samples=expert_samples, gen_samples=gen_samples,
                                                 check_ring=False)
-                with self._disc_ctx():  # (read back on the stream that produced them: does not wait for the PPO update)
-                    vals = stats_t[:9].cpu().numpy()  # the one D2H read the Mapping[str, float] return needs
+                vals = self._read_stats(stats_t)  # the one D2H read the Mapping[str, float] return needs
                 train_stats = {k: float(v) for k, v in zip(STAT_KEYS, vals)}
             else:
                 train_stats = self._train_disc_generic(expert_samples, gen_samples)
@@ -656,6 +655,18 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
                 self.logger.record(k, v)
             self.logger.dump(self._disc_step)
         return train_stats
+
+    def _read_stats(self, stats_t: th.Tensor) -> np.ndarray:
+        """Nine floats device -> pinned host on the stream that produced them (does not wait for the PPO update on the
+        other stream); waits on an event instead of a device-wide synchronisation."""
+        if getattr(self, "_stats_host", None) is None:
+            self._stats_host = th.empty(9, dtype=th.float32).pin_memory()
+            self._ev_stats = th.cuda.Event()
+        with self._disc_ctx():
+            self._stats_host.copy_(stats_t[:9], non_blocking=True)
+            self._ev_stats.record()
+        self._ev_stats.synchronize()
+        return self._stats_host.numpy().copy()
 
     def _train_disc_generic(self, expert_samples, gen_samples) -> Mapping[str, float]:
         """Any torch optimiser: logits through the fused autograd Function, BCE/optimiser in torch."""

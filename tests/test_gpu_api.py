@@ -577,3 +577,40 @@ def test_load_reward_registry_round_trip(tmp_path):
         serialize.load_reward("RewardNet_normalized", str(q), None)
     with pytest.raises(KeyError):
         serialize.load_reward("nonexistent", str(q), None)
+
+
+@pytest.mark.parametrize("name,discrete", [("demo_cartpole_legacy", True), ("demo_pendulum_legacy", False)])
+def test_ingested_demonstrations_land_bit_exactly_in_the_device_expert_table(name, discrete):
+    """legacy `.npz` demonstrations (fixtures cut from the reference's own expert rollouts) ->
+    serialize.load -> trajectories handed to GAIL(demonstrations=...) -> flatten -> ONE upload into the AoS device table
+    [obs | act (one-hot for Discrete) | next_obs | done]; every row equals the host-side flattening bit for bit."""
+    import os
+
+    from imitation_b200.algorithms import ppo
+    from imitation_b200.algorithms.adversarial import gail
+    from imitation_b200.data import serialize, types
+    from imitation_b200.envs import synth
+    from imitation_b200.rewards import reward_nets
+
+    trajs = serialize.load(os.path.join(G.GOLDEN, name + ".npz"))
+    flat = types.flatten_trajectories(trajs)
+    Do = flat.obs.shape[1]
+    Da = int(flat.acts.max()) + 1 if discrete else flat.acts.shape[1]
+    venv = synth.DeviceVecEnv(Do, Da, 8, discrete=discrete, horizon=50, seed=0)
+    gen = ppo.DevicePPO("FeedForward32Policy", venv, n_steps=4, batch_size=16, n_epochs=1, seed=0)
+    net = reward_nets.BasicRewardNet(venv.observation_space, venv.action_space)
+    tr = gail.GAIL(demonstrations=trajs, demo_batch_size=32, venv=venv, gen_algo=gen, reward_net=net)
+    tbl = tr._expert_table.cpu().numpy()
+    n = len(flat.obs)
+    assert tbl.shape == (n, 2 * Do + Da + 1) and tr._expert_n == n
+    np.testing.assert_array_equal(tbl[:, :Do], flat.obs.astype(np.float32))
+    if discrete:
+        np.testing.assert_array_equal(tbl[:, Do:Do + Da], np.eye(Da, dtype=np.float32)[flat.acts])
+    else:
+        np.testing.assert_array_equal(tbl[:, Do:Do + Da], flat.acts.astype(np.float32))
+    np.testing.assert_array_equal(tbl[:, Do + Da:2 * Do + Da], flat.next_obs.astype(np.float32))
+    np.testing.assert_array_equal(tbl[:, -1] > 0.5, flat.dones)
+    # and the discriminator trains on them
+    tr.train_gen()
+    stats = tr.train_disc()
+    assert stats["n_expert"] == 32 and np.isfinite(stats["disc_loss"])

@@ -162,31 +162,56 @@ def test_demo_ingest_npz_round_trip(tmp_path):
     np.testing.assert_array_equal(flat.next_obs[:5], trajs[0].obs[1:])
 
 
-@pytest.mark.refsrc
-def test_demo_ingest_reads_reference_npz_fixture():
-    """The reference's own legacy-format fixture (tests/testdata/npz_format_rollout.npz) loads with the same split
-    the reference applies (container-only: /root/reference is not on the GPU box)."""
-    import os
+def _manual_split(raw):
+    """the reference's decoding of the legacy layout (data/serialize.py:50-65), spelled out"""
+    idx = np.asarray(raw["indices"])
+    return (np.split(raw["obs"], idx + np.arange(len(idx)) + 1), np.split(raw["acts"], idx),
+            np.split(raw["rews"], idx) if "rews" in raw.files else None)
 
-    from imitation_b200.data import serialize
 
-    path = "/root/reference/tests/testdata/npz_format_rollout.npz"
-    if not os.path.exists(path):
-        pytest.skip("reference checkout not present")
-    with open(path, "rb") as f:
-        if f.read(7) == b"version":
-            pytest.skip("fixture is a git-lfs pointer in this checkout")
+def _check_fixture(path):
     import warnings
+
+    from imitation_b200.data import serialize, types
 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         trajs = serialize.load_with_rewards(path)
     raw = np.load(path, allow_pickle=True)
-    idx = raw["indices"]
-    want_obs = np.split(raw["obs"], idx + np.arange(len(idx)) + 1)
-    want_acts = np.split(raw["acts"], idx)
+    want_obs, want_acts, want_rews = _manual_split(raw)
     assert len(trajs) == len(want_acts) == len(raw["terminal"])
-    for t, o, a in zip(trajs, want_obs, want_acts):
+    for t, o, a, r, term in zip(trajs, want_obs, want_acts, want_rews, raw["terminal"]):
         np.testing.assert_array_equal(t.obs, o)
         np.testing.assert_array_equal(t.acts, a)
-        assert len(t.obs) == len(t.acts) + 1
+        np.testing.assert_array_equal(t.rews, r)
+        assert len(t.obs) == len(t.acts) + 1 and t.terminal == bool(term)
+    # flatten_trajectories (data/rollout.py:563-621): obs[:-1] / obs[1:], dones only at the end of terminal trajectories
+    flat = types.flatten_trajectories(trajs)
+    np.testing.assert_array_equal(flat.obs, np.concatenate([o[:-1] for o in want_obs]))
+    np.testing.assert_array_equal(flat.next_obs, np.concatenate([o[1:] for o in want_obs]))
+    np.testing.assert_array_equal(flat.acts, np.concatenate(want_acts))
+    dones = np.concatenate([np.r_[np.zeros(len(a) - 1, bool), bool(t)] for a, t in zip(want_acts, raw["terminal"])])
+    np.testing.assert_array_equal(flat.dones, dones)
+    return trajs
+
+
+@pytest.mark.parametrize("name", ["demo_cartpole_legacy", "demo_pendulum_legacy"])
+def test_demo_ingest_reads_legacy_npz_fixture(name):
+    """Fixtures cut from the reference's own expert rollouts (oracle/make_demo_fixture.py) in the legacy layout."""
+    import os
+
+    trajs = _check_fixture(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    assert len(trajs) in (3, 4)
+
+
+@pytest.mark.refsrc
+@pytest.mark.parametrize("rel", ["cartpole_0/rollouts/final.npz", "pendulum_0/rollouts/final.npz"])
+def test_demo_ingest_reads_reference_rollouts(rel):
+    """The reference's full on-disk demonstrations (27 k CartPole / 11 k Pendulum transitions; container only)."""
+    import os
+
+    path = os.path.join("/root/reference/tests/testdata/expert_models", rel)
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    trajs = _check_fixture(path)
+    assert len(trajs) > 50

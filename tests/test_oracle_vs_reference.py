@@ -22,7 +22,7 @@ def test_goldens_reproduce_from_reference(tmp_path):
 
     mg.OUT = str(tmp_path)
     cases = mg.all_cases()
-    committed = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    committed = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("demo_"))
     assert sorted(n for n, _ in cases) == committed, "a golden file without a generator (or the reverse)"
     for name, thunk in cases:
         thunk()
@@ -36,6 +36,23 @@ def test_goldens_reproduce_from_reference(tmp_path):
                 assert [str(x) for x in np.ravel(new[k])] == [str(x) for x in np.ravel(old[k])], f"{name}:{k}"
             else:
                 np.testing.assert_array_equal(new[k], old[k], err_msg=f"{name}:{k}")
+
+
+def test_demo_fixtures_are_cut_from_the_reference_rollouts(tmp_path):
+    """tests/golden/demo_*.npz = leading trajectories of the reference's own expert rollouts (oracle/make_demo_fixture.py)."""
+    from oracle import make_demo_fixture as mdf
+
+    for src, name, k in (("cartpole_0/rollouts/final.npz", "demo_cartpole_legacy", 4),
+                         ("pendulum_0/rollouts/final.npz", "demo_pendulum_legacy", 3)):
+        out = os.path.join(str(tmp_path), name + ".npz")
+        mdf.cut(os.path.join(mdf.REF, src), out, k)
+        new, old = np.load(out, allow_pickle=True), np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=True)
+        assert set(new.files) == set(old.files)
+        for key in old.files:
+            if old[key].dtype.kind == "O":
+                assert [str(x) for x in new[key]] == [str(x) for x in old[key]]
+            else:
+                np.testing.assert_array_equal(new[key], old[key], err_msg=f"{name}:{key}")
 
 
 def test_reference_modules_used_are_the_real_ones():
