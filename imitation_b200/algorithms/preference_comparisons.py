@@ -26,6 +26,7 @@ import torch as th
 from torch import nn
 from torch.utils import data as data_th
 
+from .. import _desc, _lib, spaces
 from ..data import rollout, types
 from ..data.types import TrajectoryWithRew
 from ..rewards import reward_nets
@@ -253,6 +254,74 @@ def _stack_fragments(frags: Sequence[TrajectoryWithRew]) -> Mapping[str, np.ndar
     return dict(obs=flat(obs[:, :-1]), acts=flat(acts), next_obs=flat(obs[:, 1:]), dones=flat(dones))
 
 
+class FragmentPool:
+    """Device-resident transitions of every fragment a preference model has seen: fragment slot k owns rows
+    [k * L, (k + 1) * L) of an AoS table [obs | act (one-hot for Discrete) | next_obs | done] (the layout of the expert / ring
+    tables, imb_table_store) plus its ground-truth rewards.  A fragment is stacked on the host and uploaded ONCE, on first
+    use; afterwards a minibatch of 2 P fragments is an index vector and one imb_gather_rows launch into the feature-major
+    batch the reward kernels read -- the reference re-walks every fragment on the host on every use
+    (preference_comparisons.py:441-454)."""
+
+    def __init__(self, d_obs: int, d_act: int, discrete: bool, device):
+        self.d_obs, self.d_act, self.discrete, self.device = d_obs, d_act, discrete, th.device(device)
+        self.tw = _desc.table_width(d_obs, d_act)
+        self.L: Optional[int] = None
+        self.table: Optional[th.Tensor] = None
+        self.rews: Optional[th.Tensor] = None
+        self._slots: Dict[int, Tuple[object, int]] = {}
+        self._state = th.zeros(_lib.ST_WORDS, dtype=th.int64, device=self.device)
+
+    def _grow(self, n_slots: int) -> None:
+        rows = n_slots * self.L
+        if self.table is None:
+            cap = max(rows, 256 * self.L)
+            self.table = th.zeros(cap, self.tw, device=self.device)
+            self.rews = th.zeros(cap, device=self.device)
+        elif rows > self.table.shape[0]:
+            cap = max(rows, 2 * self.table.shape[0])
+            t = th.zeros(cap, self.tw, device=self.device)
+            t[:self.table.shape[0]] = self.table
+            r = th.zeros(cap, device=self.device)
+            r[:self.rews.shape[0]] = self.rews
+            self.table, self.rews = t, r
+
+    def slots(self, frags: Sequence[TrajectoryWithRew]) -> th.Tensor:
+        """Slot index of every fragment (uploading the ones not seen before), as a device int64 vector."""
+        if self.L is None:
+            self.L = len(frags[0])
+        out, new = [], []
+        for f in frags:
+            ent = self._slots.get(id(f))
+            if ent is None or ent[0] is not f:
+                ent = (f, len(self._slots))
+                self._slots[id(f)] = ent  # (keeps the fragment alive: its id cannot be reused while it is pooled)
+                new.append(f)
+            out.append(ent[1])
+        if new:
+            k0 = self._slots[id(new[0])][1]
+            self._grow(len(self._slots))
+            tr = _stack_fragments(new)
+            n = len(tr["obs"])
+            dev = self.device
+            f32 = lambda x: th.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(dev).reshape(n, -1)
+            dones = th.as_tensor(np.ascontiguousarray(tr["dones"]).astype(np.uint8)).to(dev)
+            dst = self.table[k0 * self.L:]
+            if self.discrete:
+                acts = th.as_tensor(np.ascontiguousarray(tr["acts"]).astype(np.int64)).to(dev).reshape(n)
+                _lib.table_store(dst, n, self.d_obs, self.d_act, f32(tr["obs"]), None, acts, f32(tr["next_obs"]), dones, n,
+                                 False, self._state)
+            else:
+                _lib.table_store(dst, n, self.d_obs, self.d_act, f32(tr["obs"]), f32(tr["acts"]), None, f32(tr["next_obs"]),
+                                 dones, n, False, self._state)
+            if isinstance(new[0], TrajectoryWithRew):
+                self.rews[k0 * self.L:k0 * self.L + n] = th.as_tensor(
+                    np.concatenate([f.rews for f in new]).astype(np.float32)).to(dev)
+        return th.as_tensor(np.asarray(out, dtype=np.int64)).to(self.device)
+
+    def row_index(self, slots: th.Tensor) -> th.Tensor:
+        return (slots[:, None] * self.L + th.arange(self.L, device=self.device)[None, :]).reshape(-1)
+
+
 class PreferenceModel(nn.Module):
     """Fragment rewards -> probability that the first fragment is preferred (:345-530)."""
 
@@ -270,6 +339,31 @@ class PreferenceModel(nn.Module):
             self.ensemble_model = base_model
             self.member_pref_models = [PreferenceModel(m, self.noise_prob, self.discount_factor, self.threshold)
                                        for m in self.ensemble_model.members]
+        # device-resident fragment pool (shared by the members of an ensemble): used when the model is a fused net,
+        # possibly inside pass-through wrappers, and the fragments have equal lengths
+        self.use_fragment_pool = True
+        self._pool: Optional[FragmentPool] = None
+        if self.ensemble_model is not None:
+            for m in self.member_pref_models:
+                m._pool_owner = self
+
+    _pool_owner = None
+
+    def _fused_target(self):
+        """The fused network whose forward() equals self.model's forward() (wrappers that only change predict_processed
+        are transparent for the forward pass, reward_nets.py:314-322), or None."""
+        m = self.model
+        while isinstance(m, reward_nets.PredictProcessedWrapper):
+            m = m.base
+        return m if hasattr(m, "forward_batch") and hasattr(m, "_engine") else None
+
+    def _get_pool(self, net) -> FragmentPool:
+        owner = self._pool_owner or self
+        if owner._pool is None:
+            d = net.engine().desc
+            discrete = spaces.is_discrete(net.action_space)
+            owner._pool = FragmentPool(d.d_obs, d.d_act, discrete, net.engine().device())
+        return owner._pool
 
     # -- rewards of a batch of transitions (keeps the graph for single networks) ----------------------------------
     def rewards(self, transitions) -> th.Tensor:
@@ -310,7 +404,26 @@ class PreferenceModel(nn.Module):
         frags = [p[0] for p in fragment_pairs] + [p[1] for p in fragment_pairs]
         lengths = {len(f) for f in frags}
         gt_available = isinstance(fragment_pairs[0][0], TrajectoryWithRew) and isinstance(fragment_pairs[0][1], TrajectoryWithRew)
-        if len(lengths) == 1:
+        net = self._fused_target() if (self.use_fragment_pool and self.ensemble_model is None) else None
+        pooled = None
+        if len(lengths) == 1 and net is not None and net.engine().device().type == "cuda":
+            # device-resident fragments: one index vector + one gather launch feed the fused kernels
+            L = lengths.pop()
+            pool = self._get_pool(net)
+            if pool.L in (None, L):
+                slots = pool.slots(frags)
+                idx = pool.row_index(slots)
+                e = net.engine()
+                n = 2 * P * L
+                batch, ld = e.new_batch(n)
+                _lib.gather_rows(pool.table, pool.table.shape[0], pool.tw, idx, n, batch, ld, 0)
+                rews = net.forward_batch(batch, ld, n).reshape(2, P, L)
+                probs = self._probability(rews[0], rews[1], time_axis=1)
+                pooled = (pool, idx)
+            lengths = {L}
+        if pooled is not None:
+            pass
+        elif len(lengths) == 1:
             # one batch of 2 * P * L rows through the fused kernels; rows f * L + t, first fragments first
             L = lengths.pop()
             rews = self.rewards(_stack_fragments(frags))
@@ -321,7 +434,10 @@ class PreferenceModel(nn.Module):
                                                self.rewards(rollout.flatten_trajectories([b])))
                               for a, b in fragment_pairs])
         gt_probs = None
-        if gt_available:
+        if gt_available and pooled is not None:
+            gr = pooled[0].rews[pooled[1]].reshape(2, P, -1)
+            gt_probs = self._probability(gr[0], gr[1], time_axis=1).cpu()  # (a host tensor, like the reference's)
+        elif gt_available:
             if len({len(f) for f in frags}) == 1:
                 gr = th.as_tensor(np.stack([f.rews for f in frags])).reshape(2, P, -1)
                 gt_probs = self._probability(gr[0], gr[1], time_axis=1)

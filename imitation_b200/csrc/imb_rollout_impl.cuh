@@ -267,7 +267,25 @@ __global__ void __launch_bounds__(RT, 1) k_rollout(const RolloutArgs A, const Di
   const int64_t e0 = (int64_t)blockIdx.x * RR;
   const int64_t e = e0 + rt;
   const bool live = rowthread && e < E;
-  if (rowthread) {
+  // The tile's environment state is SoA [d_obs][E] in HBM: one contiguous RR-float run per feature.  Full, 16-byte
+  // aligned tiles are staged by the TMA unit (one cp.async.bulk per feature row, completion on an mbarrier: SASS
+  // UBLKCP); ragged tail tiles take the plain coalesced loads.
+  __shared__ __align__(8) uint64_t obs_bar;
+  const bool bulk_tile = (e0 + RR <= E) && ((E & 3) == 0);
+  if (tid == 0) {
+    mbar_init(&obs_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (bulk_tile) {
+    if (tid == 0) {
+      mbar_expect_tx(&obs_bar, (uint32_t)(Do * RR * 4));
+      for (int k = 0; k < Do; ++k) bulk_g2s(OBSU + k * RRS, env_obs + (int64_t)k * E + e0, (uint32_t)(RR * 4), &obs_bar);
+    }
+    if (rowthread)
+      for (int a = 0; a < Da; ++a) OBSU[(Do + a) * RRS + tid] = 0.f;
+    mbar_wait(&obs_bar, 0);
+  } else if (rowthread) {
     for (int k = 0; k < Do; ++k) OBSU[k * RRS + tid] = live ? env_obs[(int64_t)k * E + e] : 0.f;  // coalesced
     for (int a = 0; a < Da; ++a) OBSU[(Do + a) * RRS + tid] = 0.f;
   }
@@ -500,8 +518,21 @@ __global__ void __launch_bounds__(RT, 1) k_rollout(const RolloutArgs A, const Di
   }
   // ---- tail: state back to HBM, V(last obs) for GAE ------------------------------------------------------
   const float vlast = value_of_obs(OBSU);
-  if (live) {
+  if (bulk_tile) {  // state tile back to HBM through the TMA unit as well (shared -> global bulk copies)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      for (int k = 0; k < Do; ++k)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(env_obs + (int64_t)k * E + e0),
+                     "r"(smem_u32(OBSU + k * RRS)), "r"((uint32_t)(RR * 4))
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+  } else if (live) {
     for (int k = 0; k < Do; ++k) env_obs[(int64_t)k * E + e] = OBSU[k * RRS + tid];
+  }
+  if (live) {
     aux[e] = vlast;
     aux[E + e] = done ? 1.f : 0.f;
   }

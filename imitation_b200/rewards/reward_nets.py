@@ -367,6 +367,12 @@ class _FusedNetMixin:
     def _fused_forward(self, state, action, next_state, done) -> th.Tensor:
         e = self.engine()
         batch, ld, n = e.pack(state, action, next_state, done)
+        return self.forward_batch(batch, ld, n)
+
+    def forward_batch(self, batch: th.Tensor, ld: int, n: int) -> th.Tensor:
+        """forward() on an already feature-major device batch (rows gathered from a device table: the preference
+        comparisons' fragment pool, imb_gather_rows); differentiable like forward()."""
+        e = self.engine()
         if n == 0:
             return th.zeros(0, device=batch.device)
         train_norm = bool(self.training and e.has_norm)

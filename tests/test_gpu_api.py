@@ -538,8 +538,13 @@ def test_full_size_round_properties():
     # statistics of the last update: both halves have demo_batch_size rows, accuracies are proportions
     s = stats[-1, :9].cpu().numpy()
     assert s[7] == B and s[8] == B and 0.0 <= s[1] <= 1.0 and abs(s[5] - 0.5) < 1e-6 and np.isfinite(s).all()
-    # feature RunningNorm of the policy: every PPO minibatch row counted once per epoch
-    assert int(a.policy.flat_vectors()[2][0]) == rounds * 5 * E * T
+    # feature RunningNorm of the policy: every PPO minibatch row counted once per epoch, plus the
+    # expert|generator rows of every discriminator minibatch; eager rounds and captured rounds agree
+    a.join()
+    th.cuda.synchronize()
+    assert int(a.policy.flat_vectors()[2][0]) == rounds * 5 * E * T + rounds * nd * 2 * B
+    assert int(b.policy.flat_vectors()[2][0]) == int(a.policy.flat_vectors()[2][0])
+    th.testing.assert_close(a.policy.flat_vectors()[1], b.policy.flat_vectors()[1], rtol=0, atol=0)
 
 
 def test_load_reward_registry_round_trip(tmp_path):
