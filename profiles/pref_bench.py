@@ -110,7 +110,7 @@ def main(args):
     launches = _lib.LAUNCHES["count"] - l0
     v = world * K * P * M / (ms / 1e3)
     rows = K * M * 2 * P * L
-    h2d = M * 2 * P * L * (2 * Do + Da + 1) * 4
+    h2d = M * 8 * 2 * 256 * 8  # per epoch: 40 minibatches x 512 slot indices (int64); the pool uploads happened in warm-up
     if rank == 0:
         print(json.dumps({"metric": "preference reward-model training, fragment-pair evaluations/sec", "value": v,
                           "unit": "pair-evaluations/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
@@ -118,15 +118,18 @@ def main(args):
                           "config": config,
                           "e2e": {"value": v, "unit": "pair-evaluations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                                   "path": "CrossEntropyRewardLoss(fragment_pairs: host TrajectoryWithRew, preferences, "
-                                          "PreferenceModel) -> loss.backward() -> AdamW.step(); the host fragments are stacked "
-                                          "and copied H2D inside every call, so value == e2e for this row"},
+                                          "PreferenceModel) -> loss.backward() -> AdamW.step(); every call starts from host "
+                                          "fragment objects and ends with a host float, so value == e2e for this row (the "
+                                          "fragments' transitions are uploaded on their first use and gathered on the device "
+                                          "afterwards; the warm-up epochs contain those uploads)"},
                           "gpu_launches": launches,
                           "roofline": {"kernel": "k_disc_fwdbwd / k_reward_fwd over 2 * 256 * 100 = 51 200 transition rows per "
                                                  "minibatch", "bound": "hbm",
                                        "achieved": rows * (4 * (Do + Da) + 4) / (ms / 1e3) / 1e9, "peak": None, "unit": "GB/s",
                                        "frac": None, "traffic": None,
-                                       "note": "host-bound: the per-minibatch stacking of 512 host fragments dominates "
-                                               "(profiles/r02_summary.md); transition rows/s = "
+                                       "note": "fragments are device-resident after their first use (FragmentPool); what remains per "
+                                               "minibatch is host work: the slot lookup of 512 fragment objects, the Boltzmann / "
+                                               "BCE torch ops and the eager AdamW step; transition rows/s = "
                                                f"{rows / (ms / 1e3) / 1e6:.1f} M"},
                           "cpu_baseline": None}))
 

@@ -376,6 +376,54 @@ def _desc_stats_offset(L, d):
     return (d.n_params + 31) // 32 * 32
 
 
+def test_norm_batch_stats_and_fold_match_running_norm(L):
+    """imb_norm_batch_stats / imb_norm_fold (the policy feature-norm side effect of SURVEY App. A.14 and the multi-GPU
+    RunningNorm merge) against RunningNorm.update_stats (util/networks.py:111-134) restated in torch: immediate mode, deferred
+    slots folded in order, and an explicit slot count (the all-gathered list of the multi-GPU step)."""
+    from imitation_b200 import _desc
+    from oracle import nets_port
+
+    Do, Da = 7, 3
+    d = _desc.disc_desc(Do, Da, normalize_input=True)
+    ws = th.zeros(L.disc_workspace_floats(d), device="cuda")
+    g = th.Generator(device="cuda").manual_seed(3)
+    port = nets_port.RunningNormPort(Do)
+    port.train()
+    ns = th.cat([th.zeros(Do), th.ones(Do)]).cuda()
+    nc = th.zeros(1, dtype=th.int32, device="cuda")
+    cap = 8
+    defer = th.zeros(4 + cap * (2 * Do + 1), device="cuda")
+    batches = []
+    for i, n in enumerate((100, 257, 64, 1000)):
+        ld = _desc.batch_ld(n)
+        b = th.zeros(_desc.batch_rows(Do, Da), ld, device="cuda")
+        b[:, :n] = th.randn(b.shape[0], n, device="cuda", generator=g) * (1 + i) + i
+        batches.append((b, ld, n))
+    # immediate
+    b, ld, n = batches[0]
+    L.norm_batch_stats(d, b, ld, n, 0, Do, ns, nc, None, 0, ws)
+    port.update_stats(b[:Do, :n].t().cpu())
+    np.testing.assert_allclose(ns.cpu().numpy(), th.cat([port.running_mean, port.running_var]).numpy(), rtol=1e-5, atol=1e-6)
+    assert int(nc) == int(port.count) == 100
+    # deferred: two batches into slots, nothing changes until the fold, then both are applied in order
+    before = ns.clone()
+    for b, ld, n in batches[1:3]:
+        L.norm_batch_stats(d, b, ld, n, 0, Do, ns, nc, defer, cap, ws)
+        port.update_stats(b[:Do, :n].t().cpu())
+    th.cuda.synchronize()
+    assert th.equal(ns, before) and int(nc) == 100 and float(defer[0]) == 2.0
+    L.norm_fold(Do, defer, ns, nc)
+    np.testing.assert_allclose(ns.cpu().numpy(), th.cat([port.running_mean, port.running_var]).numpy(), rtol=1e-5, atol=1e-6)
+    assert int(nc) == int(port.count) == 421 and float(defer[0]) == 0.0
+    # explicit slot count: the list keeps its counter
+    b, ld, n = batches[3]
+    L.norm_batch_stats(d, b, ld, n, 0, Do, ns, nc, defer, cap, ws)
+    L.norm_fold(Do, defer, ns, nc, 1)
+    port.update_stats(b[:Do, :n].t().cpu())
+    np.testing.assert_allclose(ns.cpu().numpy(), th.cat([port.running_mean, port.running_var]).numpy(), rtol=1e-5, atol=1e-6)
+    assert int(nc) == int(port.count) == 1421 and float(defer[0]) == 1.0
+
+
 # ---------------------------------------------------------------------------------------------
 # NormalizedRewardNet scan
 # ---------------------------------------------------------------------------------------------
