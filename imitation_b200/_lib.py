@@ -85,7 +85,7 @@ SYMBOLS = [
     "imb_rollout_advance", "imb_env_reset", "imb_ppo_update", "imb_policy_logp", "imb_state_init",
     "imb_sync_buffer_doubles", "imb_sync_snapshot", "imb_sync_pack", "imb_sync_unpack",
     "imb_disc_sample_gather", "imb_sample_advance2", "imb_disc_reduce_adam", "imb_norm_batch_stats", "imb_norm_fold",
-    "imb_disc_set_rows",
+    "imb_disc_set_rows", "imb_stats_publish",
 ]
 
 
@@ -113,7 +113,7 @@ _KERNELS_PER_CALL = {
     "imb_ring_advance": 1, "imb_sample_indices": 2, "imb_gather_rows": 1, "imb_rollout": 1, "imb_gae": 1,
     "imb_rollout_advance": 1, "imb_env_reset": 1, "imb_ppo_update": 1, "imb_policy_logp": 1,
     "imb_disc_sample_gather": 1, "imb_sample_advance2": 1, "imb_disc_reduce_adam": 1, "imb_norm_batch_stats": 1,
-    "imb_norm_fold": 1, "imb_disc_set_rows": 1,
+    "imb_norm_fold": 1, "imb_disc_set_rows": 1, "imb_stats_publish": 1,
 }
 
 
@@ -185,7 +185,7 @@ def disc_norm_update(d, batch, ld, n, norm_state, norm_count, ws):
     _check(lib().imb_disc_norm_update(C.byref(d), _p(batch, th.float32), C.c_int64(ld), C.c_int64(n),
                                       _p(norm_state, th.float32), _p(norm_count, th.int32), _p(ws, th.float32),
                                       _stream()), "imb_disc_norm_update",
-           int(d.base.has_norm) + (2 if (d.shaped and d.potential.has_norm) else 0))
+           1 if (d.shaped and d.potential.has_norm) else int(d.base.has_norm))  # shaped: one multi-job launch
 
 
 def norm_batch_stats(d, batch, ld, n, row0, din, norm_state, norm_count, defer, defer_cap, ws):
@@ -199,6 +199,14 @@ def norm_batch_stats(d, batch, ld, n, row0, din, norm_state, norm_count, defer, 
 def norm_fold(din, defer, norm_state, norm_count, n_slots=0):
     _check(lib().imb_norm_fold(C.c_int(din), _p(defer, th.float32), _p(norm_state, th.float32),
                                _p(norm_count, th.int32), C.c_int(n_slots), _stream()), "imb_norm_fold")
+
+
+def stats_publish(stats_dev, n, host_pinned, state, state_idx):
+    """host_pinned: a pinned (page-locked, hence device-mapped under unified addressing) float32 CPU tensor of 16 elements."""
+    if host_pinned.is_cuda or not host_pinned.is_pinned() or host_pinned.numel() < 16:
+        raise ImbError("stats_publish needs a pinned CPU tensor of >= 16 floats")
+    _check(lib().imb_stats_publish(_p(stats_dev, th.float32), C.c_int(n), C.c_void_p(host_pinned.data_ptr()),
+                                   _p(state, th.int64), C.c_int(state_idx), _stream()), "imb_stats_publish")
 
 
 def disc_set_rows(d, ws, n_rows_total, n_expert_total):

@@ -224,6 +224,9 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         # bit-identical updates (reference loss = mean over the global 2 * minibatch rows, common.py:360-368)
         self._dist_group = None
         self._dist_world = 1
+        self._stats_pub = None   # pinned host mirror of the nine statistics + sequence word (imb_stats_publish)
+        self._stats_pub_i = None
+        self._pub_seq = None
         self._dn_local = None    # my batch moments (one slot)
         self._dn_all = None      # the gathered slot list
 
@@ -352,6 +355,10 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
             self._stage[which] = st
         for k in ("obs", "next_obs", "acts", "dones"):
             src = samples[k]
+            dst = st[k]
+            if type(src) is th.Tensor and src.dtype == dst.dtype and src.shape == dst.shape and not src.requires_grad:
+                dst.copy_(src, non_blocking=True)  # (the common case of the hot loop: a ready host / device tensor)
+                continue
             if isinstance(src, np.ndarray):
                 src = th.from_numpy(np.ascontiguousarray(src) if src.flags.writeable else src.copy())
             dst = st[k]
@@ -426,6 +433,8 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
             self._disc_step += 1
             if self._side_effect_active() and self._overlap():
                 self._pn_pending += self.demo_batch_size // self.demo_minibatch_size
+            if out is self._stats and self._pub_seq is not None:
+                self._pub_seq += 1  # (one Adam step per update; wraps like the int32 mirror does -- never in practice)
         return out
 
     def _disc_update_body(self, e_host: bool, g_host: bool, train_mode: bool, out: th.Tensor) -> None:
@@ -488,6 +497,13 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
                                       self.venv.state, out)
         if fused_sampling:
             _lib.sample_advance2(B, self._expert_n, self._expert_state, self.venv.state)
+        if out is self._stats:  # the synchronous API reads these nine floats: publish them to host-mapped memory
+            if self._stats_pub is None:
+                self._stats_pub = th.zeros(16, dtype=th.float32).pin_memory()
+                self._stats_pub_i = self._stats_pub.numpy().view(np.int32)
+                self._stats_pub_i[15] = -1
+                self._pub_seq = None
+            _lib.stats_publish(out, 9, self._stats_pub, self.venv.state, _lib.ST_DISC_STEP)
 
     def _global_norm_update(self, eng, n: int) -> None:
         """RunningNorm.update_stats with the GLOBAL minibatch: local moments -> all-gather -> the W batches are folded in
@@ -622,6 +638,7 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
         self.venv_buffering.discard()
         self._global_step += 1
         self._disc_step += self.n_disc_updates_per_round
+        self._pub_seq = None  # (the replayed updates advanced the device's step count without publishing)
         return self._round_stats
 
     def _check_samples(self, samples: Mapping, who: str) -> Mapping:
@@ -659,6 +676,26 @@ class AdversarialTrainer(base.DemonstrationAlgorithm):
     def _read_stats(self, stats_t: th.Tensor) -> np.ndarray:
         """Nine floats device -> pinned host on the stream that produced them (does not wait for the PPO update on the
         other stream); waits on an event instead of a device-wide synchronisation."""
+        if stats_t is self._stats and self._stats_pub is not None:
+            # the update's last kernel wrote the statistics and then the Adam step count into host-mapped memory: poll
+            # the word until it shows the step this update produces (`_pub_seq` = step expected after every update
+            # issued so far, advanced on the host by `_train_disc_async_on_stream`)
+            seq = self._stats_pub_i
+            if self._pub_seq is not None:
+                import time as _time
+
+                t0 = None
+                while int(seq[15]) != self._pub_seq:
+                    if t0 is None:
+                        t0 = _time.perf_counter()
+                    elif _time.perf_counter() - t0 > 0.5:
+                        break  # (e.g. the step counter was restored from a checkpoint: resynchronise below)
+                else:
+                    return self._stats_pub.numpy()[:9].copy()
+            # first read or resynchronisation: wait for the stream, then learn the device's step count from the mirror
+            (self._disc_stream if (self._disc_stream is not None and self._overlap()) else th.cuda.current_stream()).synchronize()
+            self._pub_seq = int(seq[15])
+            return self._stats_pub.numpy()[:9].copy()
         if getattr(self, "_stats_host", None) is None:
             self._stats_host = th.empty(9, dtype=th.float32).pin_memory()
             self._ev_stats = th.cuda.Event()

@@ -223,6 +223,112 @@ __global__ void k_norm_fold(int din, float* __restrict__ defer, float* __restric
   }
 }
 
+// Several RunningNorm updates in ONE launch (AIRL: the base net's normaliser and the potential's, the latter updated twice:
+// first with next_obs, then with obs -- reward_nets.py:708-710).  blockIdx.y = job; every CTA computes the (mean, M2) of its
+// chunk of its job's rows; the last CTA of the whole grid Chan-merges each job's chunks and folds the jobs into their
+// running statistics IN JOB ORDER (two jobs may share a normaliser; `snap` receives the statistics right after a job's fold).
+struct NormJobs {
+  int njobs;
+  NormLaunch job[3];
+  float* rmv[3];       // running [mean | var] of the job's normaliser
+  int32_t* cnt[3];
+  float* snap[3];      // optional copy of the statistics after this job's fold
+};
+__global__ void __launch_bounds__(256) k_norm_stats_multi(NormJobs J, const float* __restrict__ batch, int64_t ld, int64_t n,
+                                                          int chunk_rows, float* __restrict__ part,
+                                                          unsigned int* __restrict__ ticket) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int jb = blockIdx.y, nchunks = gridDim.x;
+  const NormLaunch& L = J.job[jb];
+  const int64_t r0 = (int64_t)blockIdx.x * chunk_rows;
+  const int64_t r1 = min(n, r0 + (int64_t)chunk_rows);
+  const int cn = (int)(r1 - r0);
+  const int PS = 2 * IMB_MAX_DIN + 4;
+  float* my = part + ((int64_t)jb * nchunks + blockIdx.x) * PS;
+  for (int k = warp; k < L.din; k += nw) {
+    const float* src = batch + (int64_t)L.row[k] * ld + r0;
+    float s = 0.f;
+    for (int i = lane; i < cn; i += 32) s += src[i];
+    s = warp_sum(s);
+    const float mean = s / (float)cn;
+    float m2 = 0.f;
+    for (int i = lane; i < cn; i += 32) {
+      float dlt = src[i] - mean;
+      m2 = fmaf(dlt, dlt, m2);
+    }
+    m2 = warp_sum(m2);
+    if (lane == 0) {
+      my[k] = mean;
+      my[IMB_MAX_DIN + k] = m2;
+    }
+  }
+  if (threadIdx.x == 0) my[2 * IMB_MAX_DIN] = (float)cn;
+  __threadfence();
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x * gridDim.y - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int job = 0; job < J.njobs; ++job) {  // folds in job order (a later job may read what an earlier one wrote)
+    const NormLaunch& Lj = J.job[job];
+    const int32_t old_count = *J.cnt[job];
+    float* run_mean_var = J.rmv[job];
+    for (int k = warp; k < Lj.din; k += nw) {
+      float na = 0.f, ma = 0.f, m2a = 0.f;
+      for (int c = lane; c < nchunks; c += 32) {
+        const float* p = part + ((int64_t)job * nchunks + c) * PS;
+        const float nb = __ldcg(p + 2 * IMB_MAX_DIN), mb = __ldcg(p + k), m2b = __ldcg(p + IMB_MAX_DIN + k);
+        const float nt = na + nb;
+        const float dlt = mb - ma;
+        ma = ma + dlt * (nb / nt);
+        m2a = m2a + m2b + dlt * dlt * (na * nb / nt);
+        na = nt;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float nb = __shfl_xor_sync(0xffffffffu, na, o), mb = __shfl_xor_sync(0xffffffffu, ma, o),
+                    m2b = __shfl_xor_sync(0xffffffffu, m2a, o);
+        const bool lowme = (lane & o) == 0;
+        const float n1 = lowme ? na : nb, m1 = lowme ? ma : mb, q1 = lowme ? m2a : m2b;
+        const float n2 = lowme ? nb : na, m2v = lowme ? mb : ma, q2 = lowme ? m2b : m2a;
+        const float nt = n1 + n2;
+        if (nt > 0.f) {
+          const float dlt = m2v - m1;
+          ma = m1 + dlt * (n2 / nt);
+          m2a = q1 + q2 + dlt * dlt * (n1 * n2 / nt);
+        }
+        na = nt;
+      }
+      if (lane == 0) {
+        const float b_mean = ma, b_var = m2a / na, b_n = na;
+        float mean = run_mean_var[k], var = run_mean_var[Lj.din + k];
+        const float cnt = (float)old_count;
+        const float tot = cnt + b_n;
+        const float delta = b_mean - mean;
+        mean += delta * b_n / tot;
+        var *= cnt;
+        var += b_var * b_n;
+        var += delta * delta * cnt * b_n / tot;
+        var /= tot;
+        run_mean_var[k] = mean;
+        run_mean_var[Lj.din + k] = var;
+        if (J.snap[job]) {
+          J.snap[job][k] = mean;
+          J.snap[job][Lj.din + k] = var;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *J.cnt[job] = old_count + (int32_t)n;
+    __syncthreads();  // the next job may fold into the same normaliser: count and statistics are in place
+  }
+  if (threadIdx.x == 0) *ticket = 0u;  // re-arm for the next launch
+}
+
 // ---- the fused forward / BCE / backward kernel (tiled-GEMM form, see imb_tile.cuh) ------------------
 // Dynamic shared memory (floats):
 //   [image per pass][AW: 4 slices x P][stage: nstage x RS][XN: KP x RS][H1, H2, DZ1: JP x RS each]
@@ -752,6 +858,17 @@ __global__ void __launch_bounds__(256) k_disc_reduce_adam(int P, int G, const fl
 }
 
 __global__ void k_state_add(int64_t* state, int idx, int64_t v) { state[idx] += v; }
+
+// statistics -> host-mapped pinned memory, followed by a sequence word (system-scope fence in between): the host polls
+// the word instead of issuing a D2H copy and synchronising on an event (one PCIe posted write burst per update)
+__global__ void k_stats_publish(const float* __restrict__ stats_dev, int n, float* host, const int64_t* __restrict__ state,
+                                int state_idx) {
+  const int lane = threadIdx.x;
+  if (lane < n) host[lane] = stats_dev[lane];
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) reinterpret_cast<volatile int*>(host)[15] = (int)state[state_idx];
+}
 __global__ void k_set_meta(int* meta, int G, int64_t n, int64_t n_expert, float loss_scale) {
   meta[0] = G;
   meta[1] = (int)n;
@@ -929,6 +1046,33 @@ extern "C" int imb_disc_norm_update(const imb_disc_desc* d, const float* batch, 
   DiscLaunch L;
   if (int rc = build_launch(d, norm_state, nullptr, L)) return rc;
   short rows[IMB_MAX_DIN];
+  // shaped nets: all updates of one training forward in ONE launch (base normaliser; potential normaliser with next_obs,
+  // then with obs -- reference order, both on the same RunningNorm) when the chunk table has room for the jobs
+  if (d->shaped && d->potential.has_norm) {
+    const int chunk_rows = n <= (int64_t)128 * 2048 ? 128 : NORM_CHUNK;
+    const int chunks = (int)((n + chunk_rows - 1) / chunk_rows);
+    NormJobs J;
+    memset(&J, 0, sizeof(J));
+    int nj = 0;
+    auto add = [&](const imb_mlp& m, int pass, float* snap) {
+      J.job[nj].din = m.din;
+      for (int k = 0; k < m.din; ++k) J.job[nj].row[k] = L.stage_row[L.pass[pass].in_slot[k]];
+      J.rmv[nj] = norm_state + m.norm_off;
+      J.cnt[nj] = norm_count + m.count_idx;
+      J.snap[nj] = snap;
+      ++nj;
+    };
+    if (d->base.has_norm) add(d->base, 0, nullptr);
+    add(d->potential, 1, ws + w.snap);
+    add(d->potential, 2, nullptr);
+    J.njobs = nj;
+    if ((int64_t)chunks * nj <= MAXCHUNKS) {
+      k_norm_stats_multi<<<dim3(chunks, nj), 256, 0, st>>>(J, batch, ld, n, chunk_rows, ws + w.normpart,
+                                                           reinterpret_cast<unsigned int*>(ws + w.ticket));
+      IMB_CHECK_LAUNCH("k_norm_stats_multi");
+      return 0;
+    }
+  }
   if (d->base.has_norm) {
     for (int k = 0; k < d->base.din; ++k) rows[k] = L.stage_row[L.pass[0].in_slot[k]];
     if (int rc = norm_launch(d->base, rows, batch, ld, n, norm_state, norm_count, nullptr, ws, w, st)) return rc;
@@ -980,6 +1124,14 @@ extern "C" int imb_disc_set_rows(const imb_disc_desc* d, float* ws, int64_t n, i
   const WsLayout w = ws_layout(d->n_params);
   k_set_rows<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<int*>(ws + w.meta), n, n_expert);
   IMB_CHECK_LAUNCH("k_set_rows");
+  return 0;
+}
+
+extern "C" int imb_stats_publish(const float* stats_dev, int n, float* host_mapped, const int64_t* state, int state_idx,
+                                 void* stream) {
+  IMB_REQUIRE(n >= 1 && n <= 15 && state_idx >= 0 && state_idx < IMB_ST_WORDS, "stats publish: bad sizes");
+  k_stats_publish<<<1, 32, 0, (cudaStream_t)stream>>>(stats_dev, n, host_mapped, state, state_idx);
+  IMB_CHECK_LAUNCH("k_stats_publish");
   return 0;
 }
 

@@ -77,6 +77,7 @@ class ActorCriticPolicy(nn.Module):
         st = self.__dict__.copy()
         st["_flat"] = None
         st.pop("_plist_cache", None)
+        st.pop("_flat_cache", None)
         st.pop("_norm_state", None)
         st.pop("_norm_count", None)
         return st
@@ -99,6 +100,15 @@ class ActorCriticPolicy(nn.Module):
         from ..rewards.reward_nets import FusedEngine
 
         plist = self._plist()
+        # fast path: no parameter / buffer was re-pointed since the last full check
+        sig = [p.data_ptr() for p in plist]
+        if self.normalize_features:
+            n = self.features_extractor.normalize
+            sig += [n.running_mean.data_ptr(), n.running_var.data_ptr(), n.count.data_ptr()]
+        sig = tuple(sig)
+        cached = self.__dict__.get("_flat_cache")
+        if cached is not None and cached[0] == sig:
+            return cached[1]
         dev = plist[0].device
         if dev.type != "cuda":
             raise _lib.ImbError("imitation_b200 policies run on CUDA only (no CPU fallback)")
@@ -126,6 +136,11 @@ class ActorCriticPolicy(nn.Module):
                 object.__setattr__(self, "_norm_state", th.zeros(2, device=dev))
                 object.__setattr__(self, "_norm_count", th.zeros(1, dtype=th.int32, device=dev))
             ns, nc = self._norm_state, self._norm_count
+        sig = [p.data_ptr() for p in plist]
+        if self.normalize_features:
+            n = self.features_extractor.normalize
+            sig += [n.running_mean.data_ptr(), n.running_var.data_ptr(), n.count.data_ptr()]
+        self.__dict__["_flat_cache"] = (tuple(sig), (flat, ns, nc))
         return flat, ns, nc
 
     # -- SB3-compatible API (torch ops; not on the hot path) ------------------------------------------------

@@ -80,6 +80,10 @@ class FusedEngine:
         nothing moved; after `.to(device)` it re-flattens.  A sub-network (e.g. the base of a
         shaped net) accepts the enclosing net's flat vector because its slice is contiguous."""
         plist = self._param_list()
+        # fast path (this runs on every kernel call of the API): nothing was re-pointed since the last full check
+        sig = self._signature(plist)
+        if sig == getattr(self, "_sig", None) and self.params is not None:
+            return
         dev = plist[0].device
         if dev.type != "cuda":
             raise _lib.ImbError("imitation_b200 reward nets run on CUDA only (no CPU fallback): call .to('cuda')")
@@ -115,6 +119,16 @@ class FusedEngine:
             self.norm_count = th.zeros(2, dtype=th.int32, device=dev)
         if self.ws is None or self.ws.device != dev:
             self.ws = th.zeros(_lib.disc_workspace_floats(self.desc), device=dev)
+        self._sig = self._signature(plist)
+
+    def _signature(self, plist) -> tuple:
+        """Addresses of every tensor the kernels alias (parameters, RunningNorm buffers): unchanged addresses = the flat
+        vectors established by the last full `sync()` are still what the modules point at."""
+        sig = [p.data_ptr() for p in plist]
+        for n in self._norms():
+            if n is not None:
+                sig += [n.running_mean.data_ptr(), n.running_var.data_ptr(), n.count.data_ptr()]
+        return tuple(sig)
 
     @property
     def has_norm(self) -> bool:

@@ -124,6 +124,10 @@ int imb_norm_batch_stats(const imb_disc_desc* d, const float* batch, int64_t ld,
 int imb_norm_fold(int din, float* defer, float* norm_state, int32_t* norm_count, int n_slots /* <= 0: the list's own
                   counter, which is then reset; > 0: exactly that many slots (an all-gathered list), no reset */,
                   void* stream);
+/* `train_disc` returns Mapping[str, float] (common.py:79-92): copy the n <= 15 statistics into HOST-MAPPED pinned memory
+ * (16 floats) and then store the current value of state[state_idx] (the Adam step) as int32 into word 15; the host polls that
+ * word -- no D2H memcpy, no event synchronisation on the critical path of the synchronous API. */
+int imb_stats_publish(const float* stats_dev, int n, float* host_mapped, const int64_t* state, int state_idx, void* stream);
 /* multi-GPU discriminator step: after the [gradient | statistic sums] block at the start of the workspace
  * (n_params rounded up to 32 floats, then 5 sums) has been all-reduced over the ranks, record the GLOBAL row counts that
  * imb_disc_adam's statistics divide by (common.py:52-77 over the global 2 * minibatch rows). */
