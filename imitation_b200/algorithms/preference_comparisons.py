@@ -27,6 +27,7 @@ from torch import nn
 from torch.utils import data as data_th
 
 from .. import _desc, _lib, spaces
+from . import base
 from ..data import rollout, types
 from ..data.types import TrajectoryWithRew
 from ..rewards import reward_nets
@@ -85,6 +86,74 @@ class TrajectoryDataset(TrajectoryGenerator):
         trajectories = list(self._trajectories)
         self.rng.shuffle(trajectories)  # type: ignore[arg-type]
         return _get_trajectories(trajectories, steps)
+
+
+class AgentTrainer(TrajectoryGenerator):
+    """Train the device generator on a learned reward and hand its trajectories (with the ENVIRONMENT's rewards) to the
+    preference pipeline (:127-316).  `algorithm` is a `DevicePPO` over a `DeviceVecEnv`; the learned reward is fused into
+    the rollout kernel through `RewardVecEnvWrapper`, the `BufferingWrapper` records the ground-truth rewards."""
+
+    def __init__(self, algorithm, reward_fn, venv, rng: np.random.Generator, exploration_frac: float = 0.0,
+                 switch_prob: float = 0.5, random_prob: float = 0.5,
+                 custom_logger: Optional[imit_logger.HierarchicalLogger] = None) -> None:
+        from ..data import wrappers
+        from ..rewards import reward_wrapper
+
+        self.algorithm = algorithm
+        super().__init__(custom_logger)
+        if exploration_frac > 0:
+            raise NotImplementedError("exploratory rollouts (ExplorationWrapper: host-side policy switching per step) have "
+                                      "no device path; use exploration_frac=0")
+        if isinstance(reward_fn, reward_nets.RewardNet):
+            reward_fn = reward_fn.predict_processed
+        self.reward_fn = reward_fn
+        self.exploration_frac = exploration_frac
+        self.rng = rng
+        self.buffering_wrapper = wrappers.BufferingWrapper(venv)
+        self.venv = self.reward_venv_wrapper = reward_wrapper.RewardVecEnvWrapper(self.buffering_wrapper,
+                                                                                  reward_fn=self.reward_fn)
+        self.log_callback = self.reward_venv_wrapper.make_log_callback()
+        self.algorithm.set_env(self.venv)
+        self.algorithm.set_logger(self.logger)
+
+    def train(self, steps: int, **kwargs) -> None:
+        n_transitions = self.buffering_wrapper.n_transitions
+        if n_transitions:
+            raise RuntimeError(f"There are {n_transitions} transitions left in the buffer. "
+                               "Call AgentTrainer.sample() first to clear them.")
+        self.algorithm.learn(total_timesteps=steps, reset_num_timesteps=False, callback=self.log_callback, **kwargs)
+
+    def sample(self, steps: int) -> Sequence[TrajectoryWithRew]:
+        agent_trajs, _ = self.buffering_wrapper.pop_finished_trajectories()
+        agent_trajs = agent_trajs[::-1]  # the latest trajectories come from the most relevant version of the agent
+        avail_steps = sum(len(t) for t in agent_trajs)
+        if avail_steps < steps:
+            self.logger.log(f"Requested {steps} transitions but only {avail_steps} in buffer. "
+                            f"Sampling {steps - avail_steps} additional transitions.")
+            # roll the (stochastic) policy without training until enough episodes have finished; the wrapper records them
+            per = self.buffering_wrapper.num_envs * self.algorithm.n_steps
+            H = self.buffering_wrapper.venv.horizon
+            guard = 0
+            more: List[TrajectoryWithRew] = []
+            while sum(len(t) for t in more) < steps - avail_steps:
+                self.buffering_wrapper.before_rollout()
+                self.algorithm.collect_rollouts()
+                new, _ = self.buffering_wrapper.pop_finished_trajectories()
+                more += list(new)
+                guard += per
+                if guard > 4 * (steps + H * self.buffering_wrapper.num_envs) + per:
+                    raise RuntimeError("could not collect enough finished trajectories")
+            agent_trajs = list(agent_trajs) + more
+        return list(_get_trajectories(agent_trajs, steps))
+
+    @property
+    def logger(self) -> imit_logger.HierarchicalLogger:
+        return self._logger
+
+    @logger.setter
+    def logger(self, value: imit_logger.HierarchicalLogger) -> None:
+        self._logger = value
+        self.algorithm.set_logger(value)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -611,8 +680,9 @@ QUERY_SCHEDULES: Dict[str, Callable[[float], float]] = {
 }
 
 
-class PreferenceComparisons:
-    """The outer loop (:1482-1700): sample trajectories -> fragments -> preferences -> train the reward model."""
+class PreferenceComparisons(base.BaseImitationAlgorithm):
+    """The outer loop (:1482-1760): sample trajectories -> fragments -> preferences -> train the reward model -> train the
+    agent; fixed-horizon check on the sampled trajectories and one logger dump per iteration like the reference."""
 
     def __init__(self, trajectory_generator: TrajectoryGenerator, reward_model: reward_nets.RewardNet,
                  num_iterations: int, fragmenter: Optional[Fragmenter] = None,
@@ -622,8 +692,9 @@ class PreferenceComparisons:
                  initial_comparison_frac: float = 0.1, initial_epoch_multiplier: float = 200.0,
                  custom_logger: Optional[imit_logger.HierarchicalLogger] = None,
                  rng: Optional[np.random.Generator] = None,
-                 query_schedule: Union[str, Callable[[float], float]] = "hyperbolic") -> None:
-        self.logger = custom_logger or imit_logger.configure()
+                 query_schedule: Union[str, Callable[[float], float]] = "hyperbolic",
+                 allow_variable_horizon: bool = False) -> None:
+        super().__init__(custom_logger=custom_logger, allow_variable_horizon=allow_variable_horizon)
         if rng is None and not (fragmenter is not None and preference_gatherer is not None and reward_trainer is not None):
             raise ValueError("If you don't provide a random state, you must provide your own "
                              "seeded fragmenter, preference gatherer, and reward_trainer. ")
@@ -631,7 +702,9 @@ class PreferenceComparisons:
         self.model = reward_model
         self.preference_model = PreferenceModel(reward_model)
         self.reward_trainer = reward_trainer or _make_reward_trainer(self.preference_model, CrossEntropyRewardLoss(), rng)
+        self.reward_trainer.logger = self.logger
         self.trajectory_generator = trajectory_generator
+        self.trajectory_generator.logger = self.logger
         self.fragmenter = fragmenter or RandomFragmenter(custom_logger=self.logger, rng=rng)
         self.preference_gatherer = preference_gatherer or SyntheticGatherer(custom_logger=self.logger, rng=rng)
         self.fragment_length = fragment_length
@@ -659,16 +732,22 @@ class PreferenceComparisons:
         reward_loss = reward_accuracy = None
         for i, num_pairs in enumerate(schedule):
             num_steps = math.ceil(self.transition_oversampling * 2 * num_pairs * self.fragment_length)
+            self.logger.log(f"Collecting {2 * num_pairs} fragments ({num_steps} transitions)")
             trajectories = self.trajectory_generator.sample(num_steps)
+            # (assumes no fragment misses initial timesteps, allows fragments that miss terminal ones)
+            self._check_fixed_horizon(len(traj) for traj in trajectories if traj.terminal)
             fragments = self.fragmenter(trajectories, self.fragment_length, num_pairs)
-            preferences = self.preference_gatherer(fragments)
+            with self.logger.accumulate_means("preferences"):
+                preferences = self.preference_gatherer(fragments)
             self.dataset.push(fragments, np.asarray(preferences, dtype=np.float32))
             epoch_multiplier = self.initial_epoch_multiplier if i == 0 else 1.0
             self.reward_trainer.train(self.dataset, epoch_multiplier=epoch_multiplier)
             stats = getattr(self.reward_trainer, "last_epoch_stats", {})
             reward_loss, reward_accuracy = stats.get("loss"), stats.get("accuracy")
             num_steps = timesteps_per_iteration + (extra if i == self.num_iterations - 1 else 0)
-            self.trajectory_generator.train(steps=num_steps)
+            with self.logger.accumulate_means("agent"):
+                self.trajectory_generator.train(steps=num_steps)
+            self.logger.dump(self._iteration)
             if callback:
                 callback(self._iteration)
             self._iteration += 1

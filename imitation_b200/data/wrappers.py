@@ -105,10 +105,14 @@ class BufferingWrapper:
     def _collect(self):
         """All buffered steps since the last pop as ([E][T][tw] rows, [E][T] env rewards, T, t0): the rollouts the
         reference's wrapper would have accumulated, joined in time."""
-        T, t0, H = self._last
-        rows = [h[0] for h in self._hist] + [self._unflatten(self._flat.cpu().numpy(), T, t0, H)]
-        rews = [h[1] for h in self._hist] + [self._env_rews.cpu().numpy().reshape(self.num_envs, T)]
-        t0_all = self._hist[0][2] if self._hist else t0
+        rows, rews = [h[0] for h in self._hist], [h[1] for h in self._hist]
+        t0_all = self._hist[0][2] if self._hist else None
+        if self._unsaved:  # the device buffers hold a rollout that is not in the history yet
+            T, t0, H = self._last
+            rows.append(self._unflatten(self._flat.cpu().numpy(), T, t0, H))
+            rews.append(self._env_rews.cpu().numpy().reshape(self.num_envs, T))
+            if t0_all is None:
+                t0_all = t0
         rows, rews = np.concatenate(rows, 1), np.concatenate(rews, 1)
         return rows, rews, rows.shape[1], t0_all
 
@@ -124,7 +128,7 @@ class BufferingWrapper:
         out = buffer_mod.rows_to_transitions(flat, v.d_obs, v.d_act, v.observation_space.shape,
                                              v.action_space.shape, v.observation_space.dtype, v.action_space.dtype,
                                              v.discrete, rews=frews.astype(np.float32))
-        assert len(out.obs) == self.n_transitions
+        assert len(out.obs) >= self.n_transitions
         self._popped = (T, t0, H)
         self.discard()
         return out
@@ -157,5 +161,31 @@ class BufferingWrapper:
         return trajs, ep_lens
 
     def pop_finished_trajectories(self):
-        trajs, lens = self.pop_trajectories()
-        return [t for t in trajs if t.terminal], lens
+        """Finished trajectories (in completion order) and their lengths; the steps of episodes that are still running
+        stay buffered and are joined with later rollouts (data/wrappers.py:113-130)."""
+        if not self.n_transitions:
+            return [], []
+        v, H, E = self.venv, self.venv.horizon, self.num_envs
+        rows, rews, T, t0 = self._collect()
+        segs = self._segments_of(T, t0, H)
+        keep_from = T
+        if (t0 + segs[-1][1]) % H != 0:  # the last segment is an unfinished episode
+            keep_from = segs[-1][0]
+            segs = segs[:-1]
+        trajs, lens = [], []
+        for a, b in segs:
+            flat = rows[:, a:b].reshape(-1, rows.shape[2])
+            tr = buffer_mod.rows_to_transitions(flat, v.d_obs, v.d_act, v.observation_space.shape, v.action_space.shape,
+                                                v.observation_space.dtype, v.action_space.dtype, v.discrete,
+                                                rews=rews[:, a:b].reshape(-1).astype(np.float32))
+            L = b - a
+            for e in range(E):
+                sl = slice(e * L, (e + 1) * L)
+                trajs.append(types.TrajectoryWithRew(obs=np.concatenate([tr.obs[sl], tr.next_obs[sl][-1:]]),
+                                                     acts=tr.acts[sl], infos=None, terminal=True, rews=tr.rews[sl]))
+                lens.append(L)
+        self.discard()
+        if keep_from < T:
+            # (like the reference, `n_transitions` restarts at 0 while the running episodes' steps stay in the accumulator)
+            self._hist = [(rows[:, keep_from:].copy(), rews[:, keep_from:].copy(), (t0 + keep_from) % H)]
+        return trajs, lens

@@ -146,3 +146,47 @@ def test_reward_trainer_matches_reference_after_two_epochs():
     out = algo.train(total_timesteps=0, total_comparisons=20)
     assert out["reward_accuracy"] is not None and 0.0 <= out["reward_accuracy"] <= 1.0 and np.isfinite(out["reward_loss"])
     assert len(algo.dataset) == 20
+
+
+@pytest.mark.gpu
+def test_agent_trainer_on_device_generator():
+    """AgentTrainer (:127-316) over DevicePPO + DeviceVecEnv: `train` runs the generator on the learned reward (fused into
+    the rollout kernel), `sample` returns finished trajectories carrying the ENVIRONMENT's rewards (checked against the env's
+    closed form), unfinished episodes stay buffered across pops, and PreferenceComparisons runs an iteration on top."""
+    from imitation_b200 import _desc
+    from imitation_b200.algorithms import ppo
+    from imitation_b200.algorithms import preference_comparisons as pc
+    from imitation_b200.envs import synth
+    from imitation_b200.rewards import reward_nets
+
+    Do, Da, E, T, H = 5, 2, 4, 4, 6
+    th.manual_seed(0)
+    venv = synth.DeviceVecEnv(Do, Da, E, horizon=H, seed=3)
+    net = reward_nets.BasicRewardNet(venv.observation_space, venv.action_space).cuda()
+    algo = ppo.DevicePPO("FeedForward32Policy", venv, n_steps=T, batch_size=8, n_epochs=1, seed=0)
+    rng = np.random.default_rng(0)
+    agent = pc.AgentTrainer(algo, net, venv, rng)
+    agent.train(steps=3 * E * T)  # 12 env steps per env = two finished episodes of 6
+    trajs = agent.sample(2 * E * H)
+    assert len(trajs) == 2 * E and all(t.terminal and len(t) == H for t in trajs)
+    with pytest.raises(RuntimeError, match="transitions left in the buffer"):
+        algo.collect_rollouts()
+        agent.buffering_wrapper.after_rollout  # noqa: B018  (the rollout above left transitions behind)
+        agent.train(steps=E * T)
+    agent.buffering_wrapper.discard()
+    # environment rewards: w . obs' - 0.1 |clip(a)|^2 of the synthetic env
+    ep = _desc.synth_env_params(Do, Da, 3)
+    w = ep[Do * Do + Do * Da + Do:Do * Do + Do * Da + 2 * Do]
+    for t in trajs:
+        want = t.obs[1:] @ w - 0.1 * (np.clip(t.acts, -1, 1) ** 2).sum(1)
+        np.testing.assert_allclose(t.rews, want, rtol=1e-4, atol=1e-5)
+    # asking for more than is buffered rolls the policy further (no training) until enough episodes finished
+    more = agent.sample(3 * E * H)
+    assert sum(len(t) for t in more) >= 3 * E * H and all(t.terminal for t in more)
+    # the whole pipeline on top
+    agent.buffering_wrapper.discard()
+    frag = pc.RandomFragmenter(warning_threshold=0, rng=rng)
+    pcs = pc.PreferenceComparisons(agent, net, num_iterations=1, fragmenter=frag, fragment_length=3,
+                                   transition_oversampling=1, initial_comparison_frac=0.5, initial_epoch_multiplier=1.0, rng=rng)
+    res = pcs.train(total_timesteps=2 * E * H, total_comparisons=8)
+    assert np.isfinite(res["reward_loss"]) and 0.0 <= res["reward_accuracy"] <= 1.0
