@@ -142,7 +142,7 @@ def test_reward_trainer_matches_reference_after_two_epochs():
     algo = pc.PreferenceComparisons(gen, ens, num_iterations=2, fragment_length=5, rng=rng,
                                     initial_epoch_multiplier=4.0,
                                     reward_trainer=pc.EnsembleTrainer(pc.PreferenceModel(ens), pc.CrossEntropyRewardLoss(),
-                                                                     rng=rng, batch_size=16, epochs=3, lr=3e-3))
+                                                                     rng=rng, batch_size=16, epochs=3, lr=3e-3), allow_variable_horizon=True)
     out = algo.train(total_timesteps=0, total_comparisons=20)
     assert out["reward_accuracy"] is not None and 0.0 <= out["reward_accuracy"] <= 1.0 and np.isfinite(out["reward_loss"])
     assert len(algo.dataset) == 20
