@@ -153,13 +153,14 @@ __device__ __forceinline__ float sum8(const float (&d)[8]) {
 
 // PPO.train for one rollout: n_epochs x ceil(N / batch) optimiser steps, ONE cluster of CL CTAs.
 // Data flow of one optimiser step (64-row minibatch, CTA c owns rows 8c..8c+7, every CTA holds all parameters):
-//   * the minibatch rows are staged row-major in shared memory by 64 bulk-async (TMA) row copies issued one
-//     step ahead by two warps (indices drawn on the fly), completion on an mbarrier;
+//   * the minibatch rows are staged row-major in shared memory by asynchronous 16-byte row copies issued TWO
+//     steps ahead by warps 4-7 (indices drawn on the fly, three buffers), completion on an mbarrier;
 //   * minibatch statistics (feature RunningNorm update, advantage normalisation) over all 64 rows are computed
-//     redundantly and identically by every CTA -- in the shadow of the previous step's cluster barrier;
-//   * forward + loss + backward to dL/dz run WARP-AUTONOMOUSLY: warp = (tower, 2 own rows), lane = hidden
-//     unit; only __syncwarp() between layers (the two towers interact through the summed loss only), so
-//     the ~8 dependent stages of the chain cost no CTA barrier;
+//     redundantly and identically by every CTA -- one step ahead, by warps 4-7, BESIDE the chain of warps 0-3;
+//   * forward + loss + backward to dL/dz run WARP-AUTONOMOUSLY on warps 0-3: warp = (tower, 4 own rows), lane =
+//     hidden unit; only __syncwarp() between layers (the two towers interact through the summed loss only), so
+//     the ~8 dependent stages of the chain cost no CTA barrier, and every weight read from shared memory
+//     feeds four FMAs (with 2 rows per warp on all 8 warps the chain was bound by shared-memory wavefronts);
 //   * weight gradients over the CTA's 8 rows: thread = (tower, unit, input subset), staged in local shared
 //     memory in the parameter layout, pushed to the slice owners through distributed shared memory with
 //     16-byte stores; owners sum the CL partials in fixed order, exchange the squared slice norms, run
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   extern __shared__ __align__(128) float smem[];
   __shared__ float red[32];
   __shared__ float bc[8];
-  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ __align__(8) uint64_t mbar[3];  // one per staged-minibatch buffer (step s lives in buffer s % 3)
   __shared__ __align__(8) uint64_t xbar[3];  // [0]: partial gradients of the owned slice arrived; [1]: all new parameter slices; [2]: all slice norms
   __shared__ float SSQ[CL];                  // squared gradient norms of the 8 slices (each written by its owner)
   const imb_policy_desc& pd = A.pol;
@@ -205,9 +206,10 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   float* LOSS = smem + o; o += 32;              // [CL][3] partial loss sums (read by CTA 0)
   const int DAP = (Da + 3) / 4 * 4;
   const int rsz = al(PR * RS2);
-  float* ROWS = smem + o; o += 2 * rsz;         // double-buffered minibatch, row-major [64][RS2]
+  float* ROWS = smem + o; o += 3 * rsz;         // triple-buffered minibatch, row-major [64][RS2]
   // own-row tiles, feature-major [feature][RL]
-  float* XNo = smem + o; o += al(KP * RL);
+  const int xsz = al(KP * RL);
+  float* XNo = smem + o; o += 2 * xsz;          // normalised observations, double-buffered by step parity
   float* TH1 = smem + o; o += 2 * HP * RL;
   float* TLAT = smem + o; o += 2 * HP * RL;
   float* TDZ2 = smem + o; o += 2 * HP * RL;
@@ -224,12 +226,10 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   // (selects, not PL.x[net]: a dynamically indexed member would put the whole struct in local memory)
   const int o_w1 = net ? PL.w1[1] : PL.w1[0], o_b1 = net ? PL.b1[1] : PL.b1[0];
   const int o_w2 = net ? PL.w2[1] : PL.w2[0], o_b2 = net ? PL.b2[1] : PL.b2[0];
-  const float* W1 = Pm + o_w1;
-  const float* W2 = Pm + o_w2;
 
   for (int i = tid; i < CL * S; i += PT) Pm[i] = Ms[i] = Vs[i] = GP[i] = RECV[i] = 0.f;
-  for (int i = tid; i < 2 * rsz; i += PT) ROWS[i] = 0.f;
-  for (int i = tid; i < al(KP * RL) + 8 * HP * RL + 3 * DAP * RL + 32; i += PT) XNo[i] = 0.f;  // XNo .. DVAL contiguous
+  for (int i = tid; i < 3 * rsz; i += PT) ROWS[i] = 0.f;
+  for (int i = tid; i < 2 * xsz + 8 * HP * RL + 3 * DAP * RL + 32; i += PT) XNo[i] = 0.f;  // XNo .. DVAL contiguous
   if (tid < 64) {
     rstat[tid] = (pd.has_norm && tid < Do) ? g_norm[tid] : 0.f;
     rstat[64 + tid] = (pd.has_norm && tid < Do) ? g_norm[Do + tid] : 1.f;
@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   if (tid == 0) {
     mbar_init(&mbar[0], 128);
     mbar_init(&mbar[1], 128);
+    mbar_init(&mbar[2], 128);
     mbar_init(&xbar[0], 1);
     mbar_init(&xbar[1], 1);
     mbar_init(&xbar[2], 1);
@@ -265,13 +266,12 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   constexpr int NWQ = 128 / HP;
   const int gj = tt % HP, wq = tt / HP;
   const bool jlive = gj < h;
-  const int g8 = tid >> 3, gl = tid & 7;   // 8-lane statistic groups
 
-  // Asynchronous row gather of one minibatch (epoch ep, first row start) into buffer `buf` by the value tower's
-  // threads (their chain is the shorter one): two threads per row draw the row index and copy half of the
-  // 16-byte aligned rollout row each with 16-byte cp.async (LDGSTS); completion is tracked by the buffer's
-  // mbarrier (one deferred arrival per thread).  (One bulk-async copy per row and lane was tried first: the
-  // 32 per-lane UBLKCP issues serialise, ~2500 cycles per warp.)
+  // Asynchronous row gather of one minibatch (epoch ep, first row start) into buffer `buf` by warps 4-7: two
+  // threads per row draw the row index and copy half of the 16-byte aligned rollout row each with 16-byte
+  // cp.async (LDGSTS); completion is tracked by the buffer's mbarrier (one deferred arrival per thread).  (One
+  // bulk-async copy per row and lane was tried first: the 32 per-lane UBLKCP issues serialise, ~2500 cycles per
+  // warp.)  Rows are fetched TWO optimiser steps ahead (three buffers), so their latency is never waited for.
   auto issue_gather = [&](int ep, int start, int buf) {
     const int t = tid - 128;
     if (t < 0) return;
@@ -292,18 +292,21 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     }
     cp_async_mbar_arrive(&mbar[buf]);
   };
-  // Statistics of one minibatch (step gs2, staged in buffer gs2 & 1): feature RunningNorm update + advantage
+  // Statistics of one minibatch (step gs2, staged in buffer gs2 % 3): feature RunningNorm update + advantage
   // normalisation over all 64 rows, one 8-lane group per statistic, identically in every CTA; the group of
-  // feature k also writes this CTA's own rows of it, normalised, into XNo[k][RL] (lane = row).  All lanes run the
-  // same code (full-mask shuffles); idle groups chew on the advantage column and discard the result.  The
-  // staged row stride RS2 = 4 (mod 8) makes the 32 lanes of a warp (4 features x 8 rows) hit 32 banks.
-  auto minibatch_stats = [&](int64_t gs2, int nbx) {
-    const int buf = (int)(gs2 & 1);
+  // feature k also writes this CTA's own rows of it, normalised, into XNo[gs2 & 1][k][RL] (lane = row).  Run by
+  // `ngrp` 8-lane groups (whole warps; group index gidx); all lanes run the same code (full-mask shuffles); idle
+  // groups chew on the advantage column and discard the result.  The staged row stride RS2 = 4 (mod 8) makes
+  // the 32 lanes of a warp (4 features x 8 rows) hit 32 banks.
+  auto minibatch_stats = [&](int64_t gs2, int nbx, int gidx, int ngrp) {
+    const int buf = (int)(gs2 % 3);
     float* R = ROWS + buf * rsz;
+    float* XN = XNo + (int)(gs2 & 1) * xsz;
+    const int gl = tid & 7;
     const float inv_nbx = 1.0f / (float)nbx;
-    mbar_wait(&mbar[buf], (uint32_t)((gs2 >> 1) & 1));  // all 64 row copies have landed
-    for (int task0 = 0; task0 <= Do; task0 += PT / 8) {
-      const int task = task0 + g8;
+    mbar_wait(&mbar[buf], (uint32_t)((gs2 / 3) & 1));  // all 64 row copies have landed
+    for (int task0 = 0; task0 <= Do; task0 += ngrp) {
+      const int task = task0 + gidx;
       const bool is_feat = task < Do, is_adv = task == Do;
       float* x = R + (is_feat ? task : col_adv);
       float v[8], s = 0.f;
@@ -338,7 +341,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
             rstat[64 + task] = var;
           }
         }
-        XNo[task * RL + gl] = (row0 + gl < nbx) ? (x[(row0 + gl) * RS2] - mean) * istd : 0.f;
+        XN[task * RL + gl] = (row0 + gl < nbx) ? (x[(row0 + gl) * RS2] - mean) * istd : 0.f;
       } else if (is_adv) {
         float am = 0.f, ais = 1.f;
         if (A.hp.normalize_advantage && nbx > 1) {
@@ -350,11 +353,12 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
           if (gl + 8 * i < nbx) x[(gl + 8 * i) * RS2] = (v[i] - am) * ais;
       }
     }
-    if (pd.has_norm) run_count += nbx;
   };
   __syncthreads();
   issue_gather(0, 0, 0);
-  minibatch_stats(0, min(mb, Ni));
+  if (n_steps > 1) issue_gather(mb >= Ni ? 1 : 0, mb >= Ni ? 0 : mb, 1);
+  minibatch_stats(0, min(mb, Ni), tid >> 3, PT / 8);
+  if (pd.has_norm) run_count += min(mb, Ni);  // (every thread keeps the count; the statistics' owners use it)
   // The gradient exchange is synchronised by the data itself: every 16-byte DSMEM store (st.async) completes
   // bytes on an mbarrier of the RECEIVING CTA, which waits until the expected byte count of the phase has
   // landed -- no cluster-wide barrier inside the step loop.  Each barrier is re-armed (one arrival + expected
@@ -378,7 +382,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   int ep_now = 0, start = 0;  // epoch and first row of the current step
   for (int64_t gs = 0; gs < n_steps; ++gs) {
     const int cur = (int)(gs & 1);
-    const float* Rc = ROWS + cur * rsz;
+    const float* Rc = ROWS + (int)(gs % 3) * rsz;
+    const float* XNc = XNo + cur * xsz;
     const int nb = min(mb, Ni - start);
     const float inv_nb = 1.0f / (float)nb;
     int ep_next = ep_now, start_next = start + mb;
@@ -398,23 +403,44 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
 #ifdef IMB_PPO_TIMING
     const long long wclk0 = clock64();
 #endif
-    if (gs + 1 < n_steps) issue_gather(ep_next, start_next, cur ^ 1);  // warps 6, 7: prefetch of the next minibatch
-    PPO_WCLK(1);
-
-    // ---- 1. warp-autonomous chain: forward, loss terms, backward to dL/dz for (tower, rows r0, r0 + 1) ---------
     float l_pg = 0.f, l_v = 0.f, l_ent = 0.f;
-    {
-      const int j = lane, jc = lane < h ? lane : 0, r0 = 2 * (warp & 3);
+    if (warp >= 4) {
+      // ---- 1b. warps 4-7, beside the chain: the NEXT step's minibatch statistics and own-row tile (they do not
+      //          depend on the parameters), then the row prefetch for the step after it ------------------------------
+      if (gs + 1 < n_steps) minibatch_stats(gs + 1, min(mb, Ni - start_next), (tid - 128) >> 3, (PT - 128) / 8);
+      PPO_WCLK(1);
+      if (gs + 2 < n_steps) {
+        int ep2 = ep_next, start2 = start_next + mb;
+        if (start2 >= Ni) {
+          start2 = 0;
+          ++ep2;
+        }
+        issue_gather(ep2, start2, (int)((gs + 2) % 3));
+      }
+      PPO_WCLK(3);
+    } else {
+      // ---- 1a. warp-autonomous chain on warps 0-3: forward, loss terms, backward to dL/dz for (tower, 4 own rows).
+      //          Four rows per warp: every weight fetched from shared memory feeds four FMAs (the chain was bound
+      //          by shared-memory wavefronts with two rows per warp and all eight warps fetching) ---------------------
+      const int cnet = warp >> 1;                // 0: policy tower (warps 0, 1), 1: value tower (warps 2, 3)
+      const int j = lane, jc = lane < h ? lane : 0, r0 = 4 * (warp & 1);
       const bool jl = lane < h;
-      const int rr = lane >> 4, la = lane & 15;  // per-row parts: half-warp rr handles row r0 + rr
+      const int rr = lane >> 3, la = lane & 7;   // per-row parts: lane octet rr handles row r0 + rr
       const int gr = row0 + r0 + rr;
       const bool live = gr < nb;
       const float* row = Rc + gr * RS2;
+      float* cH1 = TH1 + cnet * HP * RL;
+      float* cLAT = TLAT + cnet * HP * RL;
+      float* cDZ2 = TDZ2 + cnet * HP * RL;
+      float* cDZ1 = TDZ1 + cnet * HP * RL;
+      const float* cW1 = Pm + (cnet ? PL.w1[1] : PL.w1[0]);
+      const float* cW2 = Pm + (cnet ? PL.w2[1] : PL.w2[0]);
+      const int c_b1 = cnet ? PL.b1[1] : PL.b1[0], c_b2 = cnet ? PL.b2[1] : PL.b2[0];
       // policy warps: everything the loss needs that does not depend on the forward pass is fetched now, so its
       // latency (shared-memory loads, the exponential) hides behind the layers
-      const bool gfast = net == 0 && !pd.discrete && Da <= 16;  // one action per lane of the half-warp
+      const bool gfast = cnet == 0 && !pd.discrete && Da <= 8;  // one action per lane of the octet
       float pre_adv = 0.f, pre_lpo = 0.f, pre_act = 0.f, pre_ls = 0.f, pre_ivar = 0.f;
-      if (net == 0) {
+      if (cnet == 0) {
         pre_adv = row[col_adv];
         pre_lpo = row[col_logp];
         if (gfast && la < Da) {
@@ -424,89 +450,93 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
         }
       }
       // layer 1
-      float a0 = 0.f, a1 = 0.f;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       {
-        const float* wp = W1 + jc * ldo;
+        const float* wp = cW1 + jc * ldo;
 #pragma unroll 8
         for (int k = 0; k < Do; ++k) {
           const float w = wp[k];
-          const float2 x = *reinterpret_cast<const float2*>(XNo + k * RL + r0);
+          const float4 x = ld4(XNc + k * RL + r0);
           a0 = fmaf(x.x, w, a0);
           a1 = fmaf(x.y, w, a1);
+          a2 = fmaf(x.z, w, a2);
+          a3 = fmaf(x.w, w, a3);
         }
       }
-      float b = Pm[o_b1 + jc];
+      float b = Pm[c_b1 + jc];
       const float h10 = jl ? PPO_TANH(a0 + b) : 0.f, h11 = jl ? PPO_TANH(a1 + b) : 0.f;
-      *reinterpret_cast<float2*>(H1 + j * RL + r0) = make_float2(h10, h11);
+      const float h12 = jl ? PPO_TANH(a2 + b) : 0.f, h13 = jl ? PPO_TANH(a3 + b) : 0.f;
+      st4(cH1 + j * RL + r0, make_float4(h10, h11, h12, h13));
       __syncwarp();
       PPO_WCLK(3);
       // layer 2
-      a0 = a1 = 0.f;
+      a0 = a1 = a2 = a3 = 0.f;
       {
-        const float* wp = W2 + jc * ldh;
+        const float* wp = cW2 + jc * ldh;
 #pragma unroll 8
         for (int i = 0; i < h; ++i) {
           const float w = wp[i];
-          const float2 x = *reinterpret_cast<const float2*>(H1 + i * RL + r0);
+          const float4 x = ld4(cH1 + i * RL + r0);
           a0 = fmaf(x.x, w, a0);
           a1 = fmaf(x.y, w, a1);
+          a2 = fmaf(x.z, w, a2);
+          a3 = fmaf(x.w, w, a3);
         }
       }
-      b = Pm[o_b2 + jc];
+      b = Pm[c_b2 + jc];
       const float lat0 = jl ? PPO_TANH(a0 + b) : 0.f, lat1 = jl ? PPO_TANH(a1 + b) : 0.f;
-      *reinterpret_cast<float2*>(LAT + j * RL + r0) = make_float2(lat0, lat1);
+      const float lat2 = jl ? PPO_TANH(a2 + b) : 0.f, lat3 = jl ? PPO_TANH(a3 + b) : 0.f;
+      st4(cLAT + j * RL + r0, make_float4(lat0, lat1, lat2, lat3));
       PPO_WCLK(4);
-      // heads + loss terms; dl0/dl1 = dL/dlatent of this unit for the two rows
-      // (reductions over the units: lanes < 16 end up with row r0's sum, lanes >= 16 with row r0 + 1's)
-      float dl0 = 0.f, dl1 = 0.f;
-      auto half_reduce = [&](float keep, float send) {
-        keep += __shfl_xor_sync(0xffffffffu, send, 16);
-        keep += __shfl_xor_sync(0xffffffffu, keep, 8);
-        keep += __shfl_xor_sync(0xffffffffu, keep, 4);
-        keep += __shfl_xor_sync(0xffffffffu, keep, 2);
-        keep += __shfl_xor_sync(0xffffffffu, keep, 1);
-        return keep;
-      };
-      auto half16_sum = [&](float v) {
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
+      // heads + loss terms; dl0..dl3 = dL/dlatent of this unit for the four rows
+      float dl0 = 0.f, dl1 = 0.f, dl2 = 0.f, dl3 = 0.f;
+      auto oct_sum = [&](float v) {
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 2);
         v += __shfl_xor_sync(0xffffffffu, v, 1);
         return v;
       };
-      if (net == 1) {
+      if (cnet == 1) {
+        // value head: four sums over the 32 units, transposed on the way so that octet rr ends with row r0 + rr's
         const float wvj = jl ? Pm[PL.wv + j] : 0.f;
-        const float p0 = lat0 * wvj, p1 = lat1 * wvj;
-        const float val = half_reduce(rr ? p1 : p0, rr ? p0 : p1) + Pm[PL.bv];
+        const float p0 = lat0 * wvj, p1 = lat1 * wvj, p2 = lat2 * wvj, p3 = lat3 * wvj;
+        const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0;
+        float k0 = up16 ? p2 : p0, k1 = up16 ? p3 : p1;
+        k0 += __shfl_xor_sync(0xffffffffu, up16 ? p0 : p2, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, up16 ? p1 : p3, 16);
+        float kk = up8 ? k1 : k0;
+        kk += __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+        const float val = oct_sum(kk) + Pm[PL.bv];
         const float dv = val - row[col_ret];
         const float dval = live ? A.hp.vf_coef * 2.0f * dv * inv_nb : 0.f;
         if (la == 0) {
           if (live) l_v = dv * dv;
           DVAL[r0 + rr] = dval;
         }
-        const float other = __shfl_xor_sync(0xffffffffu, dval, 16);
-        dl0 = (rr ? other : dval) * wvj;
-        dl1 = (rr ? dval : other) * wvj;
+        dl0 = __shfl_sync(0xffffffffu, dval, 0) * wvj;
+        dl1 = __shfl_sync(0xffffffffu, dval, 8) * wvj;
+        dl2 = __shfl_sync(0xffffffffu, dval, 16) * wvj;
+        dl3 = __shfl_sync(0xffffffffu, dval, 24) * wvj;
       } else {
         const float* Wa = Pm + PL.wa;
-        // action means / logits from the latent tile in shared memory: lane = (action a0 + o / 2, row o % 2, half of
-        // the units); 16-term dot + one shuffle (Wa rows have the odd stride ldh: no bank conflicts)
+        // action means / logits from the latent tile in shared memory: lane = (action a0 + lane / 4, row lane % 4),
+        // a dot over the HP units (pad units hold zeros; Wa rows have the odd stride ldh: no bank conflicts)
         __syncwarp();
         {
-          const int o16 = lane & 15, part = lane >> 4, rrr = o16 & 1;
-          for (int a0 = 0; a0 < Da; a0 += 8) {
-            const int a = a0 + (o16 >> 1), ac = a < Da ? a : 0;
-            const float* wr = Wa + ac * ldh + part * 16;
-            const float* lr = LAT + part * 16 * RL + r0 + rrr;
-            float s0 = 0.f, s1 = 0.f;
+          const int asub = lane >> 2, rrr = lane & 3;
+          for (int ab = 0; ab < Da; ab += 8) {
+            const int a = ab + asub, ac = a < Da ? a : 0;
+            const float* wr = Wa + ac * ldh;
+            const float* lr = cLAT + r0 + rrr;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < 16; jj += 2) {
+            for (int jj = 0; jj < HP; jj += 4) {
               s0 = fmaf(wr[jj], lr[jj * RL], s0);
               s1 = fmaf(wr[jj + 1], lr[(jj + 1) * RL], s1);
+              s2 = fmaf(wr[jj + 2], lr[(jj + 2) * RL], s2);
+              s3 = fmaf(wr[jj + 3], lr[(jj + 3) * RL], s3);
             }
-            float m = s0 + s1;
-            m += __shfl_xor_sync(0xffffffffu, m, 16);
-            if (part == 0 && a < Da) MEAN[a * RL + r0 + rrr] = m + Pm[PL.ba + a];
+            if (a < Da) MEAN[a * RL + r0 + rrr] = ((s0 + s1) + (s2 + s3)) + Pm[PL.ba + a];
           }
         }
         __syncwarp();
@@ -526,7 +556,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
           }
         } else if (!pd.discrete) {
           const float* lstd = Pm + PL.ls;
-          for (int a = la; a < Da; a += 16) {
+          for (int a = la; a < Da; a += 8) {
             const float ls = lstd[a], ivar = __expf(-2.0f * ls);
             const float diff = row[Do + a] - MEAN[a * RL + r0 + rr];
             const float d2 = diff * diff * ivar;
@@ -537,25 +567,24 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
           }
         } else {
           float mx = -INFINITY;
-          for (int a = la; a < Da; a += 16) mx = fmaxf(mx, MEAN[a * RL + r0 + rr]);
-          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+          for (int a = la; a < Da; a += 8) mx = fmaxf(mx, MEAN[a * RL + r0 + rr]);
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
           mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
           float se = 0.f;
-          for (int a = la; a < Da; a += 16) se += expf(MEAN[a * RL + r0 + rr] - mx);
-          const float lse = mx + logf(half16_sum(se));
+          for (int a = la; a < Da; a += 8) se += expf(MEAN[a * RL + r0 + rr] - mx);
+          const float lse = mx + logf(oct_sum(se));
           act = (int)row[Do];
-          for (int a = la; a < Da; a += 16) {
+          for (int a = la; a < Da; a += 8) {
             const float lp = MEAN[a * RL + r0 + rr] - lse;
             if (a == act) logp = lp;
             ent -= expf(lp) * lp;
             DLS[a * RL + r0 + rr] = lp;  // temporarily: log p_a
           }
         }
-        logp = half16_sum(logp);
+        logp = oct_sum(logp);
         PPO_WCLK(6);
-        if (pd.discrete || loss_log) ent = half16_sum(ent);  // (Gaussian: the entropy only feeds the loss log)
+        if (pd.discrete || loss_log) ent = oct_sum(ent);  // (Gaussian: the entropy only feeds the loss log)
         const float ratio = __expf(logp - logp_old);
         const float lo = 1.0f - A.hp.clip_range, hi = 1.0f + A.hp.clip_range;
         const float pl1 = adv * ratio, pl2 = adv * fminf(fmaxf(ratio, lo), hi);
@@ -577,12 +606,12 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
             DM[la * RL + r0 + rr] = dl_dlogp * r_dm;
           }
         } else if (!pd.discrete) {
-          for (int a = la; a < Da; a += 16) {
+          for (int a = la; a < Da; a += 8) {
             DLS[a * RL + r0 + rr] = dl_dlogp * DLS[a * RL + r0 + rr] + dent;  // dH/dlog_std = 1
             DM[a * RL + r0 + rr] = dl_dlogp * DM[a * RL + r0 + rr];
           }
         } else {
-          for (int a = la; a < Da; a += 16) {
+          for (int a = la; a < Da; a += 8) {
             const float lp = DLS[a * RL + r0 + rr], pp = expf(lp);
             DM[a * RL + r0 + rr] = dl_dlogp * (((a == act) ? 1.f : 0.f) - pp) + dent * (-pp * (lp + ent));
             DLS[a * RL + r0 + rr] = 0.f;
@@ -593,30 +622,37 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
 #pragma unroll 4
         for (int a = 0; a < Da; ++a) {
           const float waj = Wa[a * ldh + jc];
-          const float2 d = *reinterpret_cast<const float2*>(DM + a * RL + r0);
+          const float4 d = ld4(DM + a * RL + r0);
           dl0 = fmaf(d.x, waj, dl0);
           dl1 = fmaf(d.y, waj, dl1);
+          dl2 = fmaf(d.z, waj, dl2);
+          dl3 = fmaf(d.w, waj, dl3);
         }
       }
       PPO_WCLK(2);
       // dL/dz2, backward through layer 2 (lane = input unit i: dH1[i] = sum_j DZ2[j] W2[j][i]), dL/dz1
-      *reinterpret_cast<float2*>(DZ2 + j * RL + r0) =
-          make_float2(jl ? dl0 * (1.0f - lat0 * lat0) : 0.f, jl ? dl1 * (1.0f - lat1 * lat1) : 0.f);
+      st4(cDZ2 + j * RL + r0,
+          make_float4(jl ? dl0 * (1.0f - lat0 * lat0) : 0.f, jl ? dl1 * (1.0f - lat1 * lat1) : 0.f,
+                      jl ? dl2 * (1.0f - lat2 * lat2) : 0.f, jl ? dl3 * (1.0f - lat3 * lat3) : 0.f));
       __syncwarp();
-      a0 = a1 = 0.f;
+      a0 = a1 = a2 = a3 = 0.f;
       {
-        const float* wp = W2 + jc;
+        const float* wp = cW2 + jc;
 #pragma unroll 8
         for (int jj = 0; jj < h; ++jj) {
           const float w = wp[jj * ldh];
-          const float2 d = *reinterpret_cast<const float2*>(DZ2 + jj * RL + r0);
+          const float4 d = ld4(cDZ2 + jj * RL + r0);
           a0 = fmaf(d.x, w, a0);
           a1 = fmaf(d.y, w, a1);
+          a2 = fmaf(d.z, w, a2);
+          a3 = fmaf(d.w, w, a3);
         }
       }
-      *reinterpret_cast<float2*>(DZ1 + j * RL + r0) =
-          make_float2(jl ? a0 * (1.f - h10 * h10) : 0.f, jl ? a1 * (1.f - h11 * h11) : 0.f);
+      st4(cDZ1 + j * RL + r0,
+          make_float4(jl ? a0 * (1.f - h10 * h10) : 0.f, jl ? a1 * (1.f - h11 * h11) : 0.f,
+                      jl ? a2 * (1.f - h12 * h12) : 0.f, jl ? a3 * (1.f - h13 * h13) : 0.f));
     }
+    if (pd.has_norm && gs + 1 < n_steps) run_count += min(mb, Ni - start_next);
     PPO_WCLK(0);
     // partial loss sums of this CTA -> CTA 0 (distributed shared memory)
     if (loss_log) {  // (uniform) loss terms are only reduced when the caller asked for the log
@@ -643,7 +679,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       if (wq == 0) GP[o_b2 + gj] = sum8(dz);
       load8(dz, DZ1 + gj * RL);
 #pragma unroll 4
-      for (int k = wq; k < Do; k += NWQ) GP[o_w1 + gj * ldo + k] = dot8r(dz, XNo + k * RL);
+      for (int k = wq; k < Do; k += NWQ) GP[o_w1 + gj * ldo + k] = dot8r(dz, XNc + k * RL);
       if (wq == NWQ - 1) GP[o_b1 + gj] = sum8(dz);
       load8(dz, LAT + gj * RL);
       if (net == 0) {
@@ -695,10 +731,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
       loss_log[gs * 4 + 3] = pg + A.hp.ent_coef * el + A.hp.vf_coef * vl;
     }
     PPO_TICK(8);
-    // While the partials travel: the NEXT step's minibatch statistics and own-row tile (they do not depend on the
-    // parameters).  Then wait until the 8 partials of the owned slice have landed.
-    if (gs + 1 < n_steps) minibatch_stats(gs + 1, min(mb, Ni - start_next));
-    PPO_TICK(1);
+    // wait until the 8 partials of the owned slice have landed
     mbar_wait(&xbar[0], (uint32_t)(gs & 1));
     if (tid == 0) mbar_expect_tx(&xbar[0], xbytes);  // re-arm for the next step
     PPO_TICK(9);
@@ -888,8 +921,8 @@ static size_t ppo_smem_floats(const PpoArgs& A) {
   const int DAP = (Da + 3) / 4 * 4;
   size_t o = 0;
   o += 5 * (size_t)al(CL * S) + 32;
-  o += 2 * (size_t)al(PR * A.RS2);
-  o += al(KP * RL) + (size_t)8 * HP * RL + (size_t)3 * DAP * RL + 32;
+  o += 3 * (size_t)al(PR * A.RS2);
+  o += 2 * (size_t)al(KP * RL) + (size_t)8 * HP * RL + (size_t)3 * DAP * RL + 32;
   o += al(2 * 64 + 4);
   return o;
 }
