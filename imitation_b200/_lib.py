@@ -42,7 +42,8 @@ class DiscDesc(C.Structure):
 
 
 class Adam(C.Structure):
-    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("weight_decay", C.c_float)]  # > 0: torch.optim.AdamW's decoupled decay
 
 
 class PolicyDesc(C.Structure):
@@ -85,7 +86,7 @@ SYMBOLS = [
     "imb_rollout_advance", "imb_env_reset", "imb_ppo_update", "imb_policy_logp", "imb_state_init",
     "imb_sync_buffer_doubles", "imb_sync_snapshot", "imb_sync_pack", "imb_sync_unpack",
     "imb_disc_sample_gather", "imb_sample_advance2", "imb_disc_reduce_adam", "imb_norm_batch_stats", "imb_norm_fold",
-    "imb_disc_set_rows", "imb_stats_publish",
+    "imb_disc_set_rows", "imb_stats_publish", "imb_pref_loss",
 ]
 
 
@@ -113,7 +114,7 @@ _KERNELS_PER_CALL = {
     "imb_ring_advance": 1, "imb_sample_indices": 2, "imb_gather_rows": 1, "imb_rollout": 1, "imb_gae": 1,
     "imb_rollout_advance": 1, "imb_env_reset": 1, "imb_ppo_update": 1, "imb_policy_logp": 1,
     "imb_disc_sample_gather": 1, "imb_sample_advance2": 1, "imb_disc_reduce_adam": 1, "imb_norm_batch_stats": 1,
-    "imb_norm_fold": 1, "imb_disc_set_rows": 1, "imb_stats_publish": 1,
+    "imb_norm_fold": 1, "imb_disc_set_rows": 1, "imb_stats_publish": 1, "imb_pref_loss": 1,
 }
 
 
@@ -235,6 +236,16 @@ def reward_forward(d, params, norm_state, batch, ld, n, out_mode, out):
     _check(lib().imb_reward_forward(C.byref(d), _p(params, th.float32), _p(norm_state, th.float32),
                                     _p(batch, th.float32), C.c_int64(ld), C.c_int64(n), C.c_int(out_mode),
                                     _p(out, th.float32), _stream()), "imb_reward_forward")
+
+
+def pref_loss(rews, n_pairs, frag_len, prefs, noise_prob, discount, threshold, grad_scale, grad_rews, probs_out, stats_acc,
+              stats_slot=0):
+    """Boltzmann preference probabilities + cross entropy (+ d loss / d rews) of one minibatch of fragment pairs;
+    stats_acc: float32 [4 * n_slots] accumulators, slot k = (sum of minibatch losses, sum of accuracies, n minibatches, -)."""
+    _check(lib().imb_pref_loss(_p(rews, th.float32), C.c_int64(n_pairs), C.c_int32(frag_len), _p(prefs, th.float32),
+                               C.c_float(noise_prob), C.c_float(discount), C.c_float(threshold), C.c_float(grad_scale),
+                               _p(grad_rews), _p(probs_out), _p(stats_acc), C.c_int32(stats_slot), _stream()),
+           "imb_pref_loss")
 
 
 def reward_norm_scan(rews, n_envs, n_steps, step_stride, env_stride, norm_state2, norm_count, eps, update_stats):

@@ -769,7 +769,8 @@ __global__ void __launch_bounds__(1024) k_disc_adam(int P, imb_adam opt, float* 
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + opt.eps;
-    params[i] -= step_size * (mi / denom);
+    const float pw = opt.weight_decay > 0.f ? params[i] * (1.0f - opt.lr * opt.weight_decay) : params[i];  // AdamW
+    params[i] = pw - step_size * (mi / denom);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && stats_out) {
     const float n = (float)meta[1], n_exp = (float)meta[2], n_gen = n - n_exp;
@@ -838,7 +839,8 @@ __global__ void __launch_bounds__(256) k_disc_reduce_adam(int P, int G, const fl
     m[i] = mi;
     v[i] = vi;
     const float denom = sqrtf(vi) / bc2_sqrt + opt.eps;
-    params[i] -= step_size * (mi / denom);
+    const float pw = opt.weight_decay > 0.f ? params[i] * (1.0f - opt.lr * opt.weight_decay) : params[i];  // AdamW
+    params[i] = pw - step_size * (mi / denom);
   }
   if (threadIdx.x == 0 && stats_out) {
     const float n = (float)meta[1], n_exp = (float)meta[2], n_gen = n - n_exp;
@@ -854,6 +856,73 @@ __global__ void __launch_bounds__(256) k_disc_reduce_adam(int P, int G, const fl
     stats_out[6] = n > 0 ? c_pred / n : nanv;
     stats_out[7] = n_exp;
     stats_out[8] = n_gen;
+  }
+}
+
+// ---- preference comparisons: fragment returns -> Boltzmann probability -> cross entropy (+ its gradient) -------------
+// Warp per fragment pair: lanes stride over the L time steps (coalesced: a fragment's rewards are contiguous), shuffle
+// reduction of the discounted difference, lane-parallel write of the 2 L gradient entries.  The minibatch sums (loss,
+// accuracy) are accumulated per CTA and added to the statistics accumulator with one atomic each; a minibatch is a few
+// hundred pairs, so the order-dependent rounding of those atomics only touches the logged means (1e-7 relative).
+__global__ void __launch_bounds__(256) k_pref_loss(const float* __restrict__ rews, int P, int L,
+                                                  const float* __restrict__ prefs, float noise_prob, float discount,
+                                                  float threshold, float grad_scale, float* __restrict__ grad_rews,
+                                                  float* __restrict__ probs_out, float* __restrict__ stats_acc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __shared__ float s_loss[8], s_acc[8];
+  float w_loss = 0.f, w_acc = 0.f;
+  const float inv_P = 1.0f / (float)P;
+  for (int pr = blockIdx.x * nw + warp; pr < P; pr += gridDim.x * nw) {
+    const float* r1 = rews + (int64_t)pr * L;
+    const float* r2 = rews + ((int64_t)P + pr) * L;
+    float s = 0.f;
+    if (discount == 1.0f) {
+      for (int t = lane; t < L; t += 32) s += r2[t] - r1[t];
+    } else {
+      for (int t = lane; t < L; t += 32) s = fmaf(powf(discount, (float)t), r2[t] - r1[t], s);
+    }
+    s = warp_sum(s);
+    const bool clipped = s < -threshold || s > threshold;  // th.clip passes the gradient on [min, max] only
+    const float d = fminf(fmaxf(s, -threshold), threshold);
+    const float m = 1.0f / (1.0f + expf(d));
+    const float p = noise_prob * 0.5f + (1.0f - noise_prob) * m;
+    const float y = prefs[pr];
+    // F.binary_cross_entropy: logs clamped at -100; backward (p - y) / max(p (1 - p), 1e-12)
+    const float lp = fmaxf(logf(p), -100.0f), l1p = fmaxf(log1pf(-p), -100.0f);
+    const float loss = -(y * lp + (1.0f - y) * l1p);
+    const float dl_dp = (p - y) / fmaxf(p * (1.0f - p), 1e-12f) * inv_P;
+    const float dp_dd = -(1.0f - noise_prob) * m * (1.0f - m);
+    const float g = clipped ? 0.f : grad_scale * dl_dp * dp_dd;  // d loss / d (returns difference)
+    if (grad_rews) {
+      float* g1 = grad_rews + (int64_t)pr * L;
+      float* g2 = grad_rews + ((int64_t)P + pr) * L;
+      for (int t = lane; t < L; t += 32) {
+        const float w = discount == 1.0f ? g : g * powf(discount, (float)t);
+        g1[t] = -w;
+        g2[t] = w;
+      }
+    }
+    if (lane == 0) {
+      if (probs_out) probs_out[pr] = p;
+      w_loss += loss;
+      w_acc += ((p > 0.5f) == (y > 0.5f)) ? 1.f : 0.f;
+    }
+  }
+  if (!stats_acc) return;
+  if (lane == 0) {
+    s_loss[warp] = w_loss;
+    s_acc[warp] = w_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < nw; ++w) {
+      a += s_loss[w];
+      b += s_acc[w];
+    }
+    atomicAdd(stats_acc + 0, a * inv_P);
+    atomicAdd(stats_acc + 1, b * inv_P);
+    if (blockIdx.x == 0) atomicAdd(stats_acc + 2, 1.0f);
   }
 }
 
@@ -1343,6 +1412,20 @@ extern "C" int imb_reward_norm_scan(float* rews, int64_t n_envs, int64_t n_steps
   k_reward_norm_scan<<<1, threads, 0, (cudaStream_t)stream>>>(rews, n_envs, n_steps, step_stride, env_stride,
                                                               norm_state2, norm_count, eps, update_stats);
   IMB_CHECK_LAUNCH("k_reward_norm_scan");
+  return 0;
+}
+
+extern "C" int imb_pref_loss(const float* rews, int64_t n_pairs, int32_t frag_len, const float* prefs, float noise_prob,
+                             float discount, float threshold, float grad_scale, float* grad_rews, float* probs_out,
+                             float* stats_acc, int32_t stats_slot, void* stream) {
+  IMB_REQUIRE(n_pairs >= 1 && n_pairs < (1ll << 30) && frag_len >= 1, "imb_pref_loss: bad sizes");
+  IMB_REQUIRE(stats_slot >= 0, "imb_pref_loss: bad statistics slot");
+  int64_t blocks = (n_pairs + 7) / 8;
+  if (blocks > 4 * imb_num_sms()) blocks = 4 * imb_num_sms();
+  k_pref_loss<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(rews, (int)n_pairs, frag_len, prefs, noise_prob, discount,
+                                                             threshold, grad_scale, grad_rews, probs_out,
+                                                             stats_acc ? stats_acc + 4 * stats_slot : nullptr);
+  IMB_CHECK_LAUNCH("k_pref_loss");
   return 0;
 }
 

@@ -12,6 +12,7 @@
 // Also: imb_policy_logp = ActorCriticPolicy.evaluate_actions()[1] for the AIRL discriminator
 // batch (common.py:476-519).
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 #include "imb_common.cuh"
 #include "imb_tile.cuh"
@@ -913,6 +914,8 @@ __global__ void __launch_bounds__(128) k_policy_logp(const imb_policy_desc pd, c
   }
 }
 
+#include "imb_ppo_gen.cuh"
+
 }  // namespace
 
 static size_t ppo_smem_floats(const PpoArgs& A) {
@@ -927,29 +930,22 @@ static size_t ppo_smem_floats(const PpoArgs& A) {
   return o;
 }
 
-static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* norm_count, float* m, float* v,
-                      const float* rollout, const int64_t* perm, float* loss_log, int64_t* state, cudaStream_t st) {
-  PpoArgs A = A0;
-  IMB_REQUIRE(A.hp.batch_size >= 1 && A.hp.batch_size <= PR, "PPO minibatch size must be in [1, %d]", PR);
-  IMB_REQUIRE(A.pol.hidden <= 32, "PPO update kernel: tower width %d > 32 does not fit the shared-memory resident design", A.pol.hidden);
-  A.HP = 32;
-  A.KP = A.pol.d_obs <= 32 ? 32 : 64;
-  A.S = ((make_play(A.pol).total + CL - 1) / CL + 3) / 4 * 4;
-  IMB_REQUIRE(A.S / 4 <= PT, "policy too large for the PPO update kernel (%d parameters per slice)", A.S);
-  IMB_REQUIRE(A.rw % 4 == 0, "rollout row width must be a multiple of 4 floats (bulk row copies)");
-  A.RS2 = ((A.rw + 4) % 8 == 4) ? A.rw + 4 : A.rw + 8;
-  const size_t fl = ppo_smem_floats(A);
-  IMB_REQUIRE(fl * 4 <= IMB_SMEM_MAX, "PPO kernel needs %zu B of shared memory per CTA", fl * 4);
-  static size_t attr_bytes = 0;
-  if (fl * 4 > attr_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(k_ppo_update<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fl * 4));
-    if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_bytes = fl * 4;
+// cluster launch of one of the two PPO kernels (CL CTAs of PT threads, one cluster)
+template <typename K>
+static int launch_cluster(K kernel, const char* name, size_t smem_bytes, size_t* attr_bytes, cudaStream_t st, const PpoArgs& A,
+                          float* params, float* norm, int32_t* norm_count, float* m, float* v, const float* rollout,
+                          const int64_t* perm, float* loss_log, int64_t* state) {
+  IMB_REQUIRE(smem_bytes <= IMB_SMEM_MAX, "%s needs %zu B of shared memory per CTA (policy / minibatch too large)", name,
+              smem_bytes);
+  if (smem_bytes > *attr_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) IMB_FAIL(-2, "cudaFuncSetAttribute(%s): %s", name, cudaGetErrorString(e));
+    *attr_bytes = smem_bytes;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL);
   cfg.blockDim = dim3(PT);
-  cfg.dynamicSmemBytes = fl * 4;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -958,10 +954,41 @@ static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* no
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, k_ppo_update<32>, A, params, norm, norm_count, m, v, rollout, perm, loss_log,
-                                     state);
-  if (e != cudaSuccess) IMB_FAIL(-2, "k_ppo_update (cluster launch): %s", cudaGetErrorString(e));
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, A, params, norm, norm_count, m, v, rollout, perm, loss_log, state);
+  if (e != cudaSuccess) IMB_FAIL(-2, "%s (cluster launch): %s", name, cudaGetErrorString(e));
   return 0;
+}
+
+static int launch_ppo(const PpoArgs& A0, float* params, float* norm, int32_t* norm_count, float* m, float* v,
+                      const float* rollout, const int64_t* perm, float* loss_log, int64_t* state, cudaStream_t st) {
+  PpoArgs A = A0;
+  IMB_REQUIRE(A.hp.batch_size >= 1 && A.hp.batch_size <= GEN_MAX_MB, "PPO minibatch size must be in [1, %d]", GEN_MAX_MB);
+  IMB_REQUIRE(A.rw % 4 == 0, "rollout row width must be a multiple of 4 floats (bulk row copies)");
+  A.KP = A.pol.d_obs <= 32 ? 32 : 64;
+  A.S = ((make_play(A.pol).total + CL - 1) / CL + 3) / 4 * 4;
+  A.RS2 = ((A.rw + 4) % 8 == 4) ? A.rw + 4 : A.rw + 8;
+  // IMB_PPO_FORCE_GENERAL=1 (tests): run the general kernel on shapes the specialised one covers
+  const char* force = getenv("IMB_PPO_FORCE_GENERAL");
+  const bool general = A.pol.hidden > 32 || A.hp.batch_size > PR || (force && force[0] == '1');
+  if (!general) {
+    // 64-row minibatch resident in shared memory, one lane per hidden unit (k_ppo_update)
+    A.HP = 32;
+    IMB_REQUIRE(A.S / 4 <= PT, "policy too large for the PPO update kernel (%d parameters per slice)", A.S);
+    static size_t attr_bytes = 0;
+    return launch_cluster(k_ppo_update<32>, "k_ppo_update", ppo_smem_floats(A) * 4, &attr_bytes, st, A, params, norm,
+                          norm_count, m, v, rollout, perm, loss_log, state);
+  }
+  // tower width up to 64 and / or minibatches of more than 64 rows (k_ppo_update_gen)
+  A.HP = A.pol.hidden <= 32 ? 32 : 64;
+  const size_t bytes = (size_t)gen_layout(A.S, A.HP, A.KP, A.pol.d_act, A.hp.batch_size).total * 4;
+  if (A.HP == 32) {
+    static size_t attr_bytes = 0;
+    return launch_cluster(k_ppo_update_gen<1>, "k_ppo_update_gen<1>", bytes, &attr_bytes, st, A, params, norm, norm_count, m,
+                          v, rollout, perm, loss_log, state);
+  }
+  static size_t attr_bytes2 = 0;
+  return launch_cluster(k_ppo_update_gen<2>, "k_ppo_update_gen<2>", bytes, &attr_bytes2, st, A, params, norm, norm_count, m,
+                        v, rollout, perm, loss_log, state);
 }
 
 extern "C" int imb_rollout_row_width(const imb_policy_desc* pol);

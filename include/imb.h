@@ -75,9 +75,11 @@ typedef struct imb_disc_desc {
   int32_t n_params;                           /* total floats in the flat parameter vector */
 } imb_disc_desc;
 
-/* Adam hyper-parameters (torch.optim.Adam defaults: adversarial/common.py:123). */
+/* Adam hyper-parameters (torch.optim.Adam defaults: adversarial/common.py:123).  weight_decay > 0 = torch.optim.AdamW's
+ * decoupled decay, param *= 1 - lr * weight_decay before the step (the reward trainer of preference comparisons,
+ * algorithms/preference_comparisons.py:1182-1185); 0 = plain Adam. */
 typedef struct imb_adam {
-  float lr, beta1, beta2, eps;
+  float lr, beta1, beta2, eps, weight_decay;
 } imb_adam;
 
 /* Device-resident counters (int64 words) so that captured graphs replay correctly. */
@@ -278,8 +280,11 @@ int imb_env_reset(float* env_obs, int64_t n_envs, const imb_env_desc* env, const
 
 /* PPO.train as ONE persistent launch of an 8-CTA thread-block cluster: n_epochs x (N/batch)
  * sequential minibatch steps (gather by permutation, evaluate_actions, clipped surrogate + value +
- * entropy loss, backward, clip_grad_norm_, Adam); batch_size <= 64, tower width <= 32.  perm == NULL -> device Feistel permutations.
- * loss_log (optional) [n_steps_total][4] = pg_loss, value_loss, entropy_loss, total. */
+ * entropy loss, backward, clip_grad_norm_, Adam).  Two kernels behind this entry point: k_ppo_update for tower width <= 32
+ * and batch_size <= 64 (the reference's FeedForward32Policy with SB3's default minibatch: the minibatch is resident in
+ * shared memory, one lane per hidden unit), k_ppo_update_gen for tower widths up to 64 (SB3 MlpPolicy 64x64) and
+ * minibatches up to 4096 rows (tuned_hps airl_seals_walker: 128, airl_seals_hopper: 512).  perm == NULL -> device Feistel
+ * permutations.  loss_log (optional) [n_steps_total][4] = pg_loss, value_loss, entropy_loss, total. */
 int imb_ppo_update(const imb_policy_desc* pol, float* pol_params, float* pol_norm,
                    int32_t* pol_norm_count, float* exp_avg, float* exp_avg_sq,
                    const float* rollout, int64_t n_rows, const imb_ppo_hparams* hp,
@@ -296,6 +301,19 @@ int imb_policy_logp(const imb_policy_desc* pol, const float* pol_params, const f
 int imb_disc_reduce_adam(const imb_disc_desc* d, const imb_adam* opt, float* params, float* exp_avg,
                          float* exp_avg_sq, float grad_div, float* ws, int64_t* state,
                          float* stats_out, void* stream);
+
+/* ---- preference comparisons --------------------------------------------------
+ * One minibatch of P fragment pairs of L transitions each: rews[2][P][L] are the reward network's outputs for the first
+ * fragments, then the second fragments (row f * L + t).  PreferenceModel.probability (algorithms/preference_comparisons.py:
+ * 487-530): d = clip(sum_t discount^t (r2 - r1), -threshold, threshold), p = noise_prob / 2 + (1 - noise_prob) / (1 + e^d);
+ * CrossEntropyRewardLoss (:1043-1090): loss = mean_P BCE(p, pref) with torch's log clamp at -100, accuracy = mean((p > .5)
+ * == (pref > .5)).  Outputs (each optional): grad_rews[2][P][L] = grad_scale * d loss / d rews (autograd's result, incl.
+ * the zero gradient of clipped pairs and torch's BCE backward denominator clamp 1e-12) -- the upstream gradient for
+ * imb_disc_fwd_bwd(grad_out=...); probs_out[P]; stats_acc[0] += loss, [1] += accuracy, [2] += 1 (so an epoch's per-minibatch
+ * means are read back once).  The reference computes this with a Python loop over the pairs (:441-454). */
+int imb_pref_loss(const float* rews, int64_t n_pairs, int32_t frag_len, const float* prefs, float noise_prob,
+                  float discount, float threshold, float grad_scale, float* grad_rews, float* probs_out,
+                  float* stats_acc, int32_t stats_slot, void* stream);
 
 /* ---- multi-GPU: replica state around the ONE all-reduce of a round ---------------------------
  * (the reference is single-process, so there is no reference interface to

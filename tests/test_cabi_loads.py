@@ -25,7 +25,7 @@ def test_struct_sizes_match_header_layout():
 
     assert C.sizeof(_lib.Mlp) == 40
     assert C.sizeof(_lib.DiscDesc) == 24 + 40 + 4 + 40 + 12
-    assert C.sizeof(_lib.Adam) == 16
+    assert C.sizeof(_lib.Adam) == 20
     assert C.sizeof(_lib.EnvDesc) == 32
     assert C.sizeof(_lib.PpoHparams) == 44
     assert C.sizeof(_lib.PolicyDesc) == 4 * 20

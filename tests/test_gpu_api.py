@@ -13,7 +13,8 @@ pytestmark = pytest.mark.gpu
 
 
 def _mk(Do=17, Da=6, E=16, T=8, H=1000, discrete=False, B=64, mb=None, algo="gail", net_kwargs=None, seed=0,
-        sampling="device", cap=None, n_disc=2, norm_features=False, **gen_kw):
+        sampling="device", cap=None, n_disc=2, norm_features=False, policy="FeedForward32Policy", ppo_batch=32,
+        **gen_kw):
     from imitation_b200.algorithms import ppo
     from imitation_b200.algorithms.adversarial import airl, gail
     from imitation_b200.envs import synth
@@ -22,7 +23,7 @@ def _mk(Do=17, Da=6, E=16, T=8, H=1000, discrete=False, B=64, mb=None, algo="gai
 
     th.manual_seed(seed)
     venv = synth.DeviceVecEnv(Do, Da, E, discrete=discrete, horizon=H, seed=seed)
-    gen = ppo.DevicePPO("FeedForward32Policy", venv, n_steps=T, batch_size=32, n_epochs=2, seed=seed,
+    gen = ppo.DevicePPO(policy, venv, n_steps=T, batch_size=ppo_batch, n_epochs=2, seed=seed,
                         policy_kwargs=dict(normalize_features=norm_features), **gen_kw)
     kw = dict(normalize_input_layer=networks.RunningNorm) if net_kwargs is None else net_kwargs
     cls = reward_nets.BasicShapedRewardNet if algo == "airl" else reward_nets.BasicRewardNet

@@ -590,10 +590,22 @@ def test_rollout_gae_matches_oracle(L, cfg):
     dict(Do=4, Da=2, discrete=True, hidden=32, norm=False, N=200, mb=64, epochs=2),
     dict(Do=9, Da=3, discrete=False, hidden=20, norm=False, N=256, mb=32, epochs=2),  # width < 32: zero padding
     dict(Do=30, Da=8, discrete=False, hidden=32, norm=True, N=128, mb=48, epochs=2),  # Ant-shaped, ragged last batch
+    # k_ppo_update_gen: tower width 64 (SB3 MlpPolicy default) and / or minibatches of more than 64 rows (tuned
+    # airl_seals_walker: 128, airl_seals_hopper: 512)
+    dict(Do=17, Da=6, discrete=False, hidden=64, norm=True, N=512, mb=64, epochs=2),
+    dict(Do=11, Da=3, discrete=False, hidden=32, norm=True, N=1024, mb=512, epochs=2),   # Hopper-shaped, 4 passes per step
+    dict(Do=4, Da=2, discrete=True, hidden=64, norm=False, N=600, mb=200, epochs=2),     # ragged passes, ragged last batch
+    dict(Do=27, Da=8, discrete=False, hidden=64, norm=True, N=256, mb=128, epochs=2),    # Ant-shaped 64x64
+    dict(Do=9, Da=3, discrete=False, hidden=40, norm=True, N=256, mb=96, epochs=2),      # width between 32 and 64: padding
+    dict(Do=17, Da=6, discrete=False, hidden=32, norm=True, N=512, mb=64, epochs=3, force_general=True),
+    dict(Do=4, Da=2, discrete=True, hidden=32, norm=False, N=200, mb=64, epochs=2, force_general=True),
 ])
-def test_ppo_update_matches_oracle(L, cfg):
+def test_ppo_update_matches_oracle(L, cfg, monkeypatch):
     from imitation_b200 import _desc
     from oracle import ppo_port
+
+    if cfg.get("force_general"):  # the general kernel on a shape the specialised one covers
+        monkeypatch.setenv("IMB_PPO_FORCE_GENERAL", "1")
 
     Do, Da, discrete, N, mb, epochs = cfg["Do"], cfg["Da"], cfg["discrete"], cfg["N"], cfg["mb"], cfg["epochs"]
     th.manual_seed(5)

@@ -25,12 +25,13 @@ pytestmark = pytest.mark.gpu
 HP = dict(learning_rate=3e-4, gamma=0.99, gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5)
 
 
-def _pair(Do, Da, discrete, E, T, H, B, mb, cap, n_disc, norm_features, seed, n_rounds):
+def _pair(Do, Da, discrete, E, T, H, B, mb, cap, n_disc, norm_features, seed, n_rounds, policy="FeedForward32Policy",
+          ppo_batch=32):
     from imitation_b200.algorithms.adversarial import common
     from oracle import gail_port, nets_port, ppo_port, synth_env
 
     tr, demos = _mk(Do=Do, Da=Da, E=E, T=T, H=H, discrete=discrete, B=B, mb=mb, cap=cap, n_disc=n_disc,
-                    norm_features=norm_features, seed=seed, sampling="host_compat")
+                    norm_features=norm_features, seed=seed, sampling="host_compat", policy=policy, ppo_batch=ppo_batch)
     gen = tr.gen_algo
     N = E * T
     rng = np.random.default_rng(seed + 100)
@@ -41,7 +42,8 @@ def _pair(Do, Da, discrete, E, T, H, B, mb, cap, n_disc, norm_features, seed, n_
     # ---- the CPU twin, same weights ----------------------------------------------------------------------------
     spec = synth_env.SynthEnvSpec(Do, Da, discrete=discrete, horizon=H, seed=seed)
     venv = synth_env.SynthVecEnv(spec, E)
-    pol = ppo_port.ActorCriticPort(Do, Da, discrete=discrete, normalize_features=norm_features)
+    pol = ppo_port.ActorCriticPort(Do, Da, discrete=discrete, hidden=(tr.policy.hidden,) * 2,
+                                   normalize_features=norm_features)
     psd = {k: v.detach().cpu().clone() for k, v in tr.policy.state_dict().items()}
     sd = {"pi.0.weight": psd["mlp_extractor.policy_net.0.weight"], "pi.0.bias": psd["mlp_extractor.policy_net.0.bias"],
           "pi.2.weight": psd["mlp_extractor.policy_net.2.weight"], "pi.2.bias": psd["mlp_extractor.policy_net.2.bias"],
@@ -94,6 +96,10 @@ def _run_port(port, n_rounds, seed):
     dict(Do=17, Da=6, discrete=False, E=16, T=8, H=20, B=64, mb=32, cap=96, n_disc=2, norm_features=True),
     # CartPole-shaped (4 / Discrete(2)), plain policy, whole-batch minibatches, ring larger than a rollout (wrap-around)
     dict(Do=4, Da=2, discrete=True, E=8, T=6, H=1000, B=32, mb=None, cap=80, n_disc=3, norm_features=False),
+    # SB3's MlpPolicy (64x64 towers) with a 96-row PPO minibatch (128 rows per rollout: one full and one ragged step per
+    # epoch): the generator update runs k_ppo_update_gen
+    dict(Do=11, Da=3, discrete=False, E=16, T=8, H=50, B=64, mb=None, cap=200, n_disc=2, norm_features=True,
+         policy="MlpPolicy", ppo_batch=96),
 ])
 def test_whole_rounds_match_adversarial_port(cfg):
     from imitation_b200 import _lib
