@@ -390,6 +390,33 @@ class FragmentPool:
     def row_index(self, slots: th.Tensor) -> th.Tensor:
         return (slots[:, None] * self.L + th.arange(self.L, device=self.device)[None, :]).reshape(-1)
 
+    def dataset_rows(self, dataset) -> Optional[Tuple[th.Tensor, th.Tensor, th.Tensor, bool]]:
+        """(R1, R2, prefs, has_gt) of a dataset of fragment pairs: R1[i] / R2[i] = the L pool rows of item i's first /
+        second fragment (device int64 [N, L]), prefs = its preferences (device float32 [N]), has_gt = the fragments carry
+        ground-truth rewards.  Built once per dataset state and reused by every epoch and every ensemble member; None if
+        the fragments do not all have the pool's length."""
+        if isinstance(dataset, PreferenceDataset):
+            f1, f2, prefs = dataset.fragments1, dataset.fragments2, dataset.preferences
+        else:
+            items = [dataset[i] for i in range(len(dataset))]
+            f1, f2 = [it[0][0] for it in items], [it[0][1] for it in items]
+            prefs = np.asarray([it[1] for it in items])
+        n = len(f1)
+        key = (id(dataset), n, id(f1[0]), id(f1[-1]), id(f2[-1]))
+        hit = self.__dict__.get("_ds_cache")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        L = self.L if self.L is not None else len(f1[0])
+        if any(len(f) != L for f in f1) or any(len(f) != L for f in f2):
+            return None
+        slots = self.slots(list(f1) + list(f2))
+        ar = th.arange(self.L, device=self.device)[None, :]
+        out = ((slots[:n, None] * self.L + ar).contiguous(), (slots[n:, None] * self.L + ar).contiguous(),
+               th.as_tensor(np.ascontiguousarray(prefs, dtype=np.float32)).to(self.device),
+               all(isinstance(f, TrajectoryWithRew) for f in (f1[0], f2[0], f1[-1], f2[-1])))
+        self._ds_cache = (key, out)
+        return out
+
 
 class PreferenceModel(nn.Module):
     """Fragment rewards -> probability that the first fragment is preferred (:345-530)."""
@@ -414,7 +441,7 @@ class PreferenceModel(nn.Module):
         self._pool: Optional[FragmentPool] = None
         if self.ensemble_model is not None:
             for m in self.member_pref_models:
-                m._pool_owner = self
+                m.__dict__["_pool_owner"] = self  # (not a submodule: a member's parameters() are its own network's only)
 
     _pool_owner = None
 
@@ -571,6 +598,37 @@ class RewardTrainer(abc.ABC):
         """Train the reward model."""
 
 
+_PERM_FAST: Optional[bool] = None
+
+
+def _epoch_permutation(n: int) -> th.Tensor:
+    """The item order of ONE pass of `DataLoader(<n items>, shuffle=True)` (the reference's minibatch source,
+    preference_comparisons.py:1207-1216), drawn with exactly that iterator's consumption of torch's global RNG: one
+    int64 for the iterator's base seed, one for the RandomSampler's generator seed, then `randperm` on that generator.
+    Producing the whole permutation at once lets an epoch upload its indices in one copy instead of collating every
+    minibatch on the host.  The shortcut mirrors torch internals, so it is verified against a real DataLoader (on a
+    saved / restored RNG state) the first time it is used; on any mismatch the DataLoader itself is iterated."""
+    global _PERM_FAST
+
+    def fast(k):
+        th.empty((), dtype=th.int64).random_()
+        g = th.Generator()
+        g.manual_seed(int(th.empty((), dtype=th.int64).random_().item()))
+        return th.randperm(k, generator=g)
+
+    def slow(k):
+        return th.cat([b for b in data_th.DataLoader(range(k), batch_size=max(1, min(k, 64)), shuffle=True)])
+
+    if _PERM_FAST is None:
+        state = th.get_rng_state()
+        a, sa = fast(11), th.get_rng_state()
+        th.set_rng_state(state)
+        b, sb = slow(11), th.get_rng_state()
+        th.set_rng_state(state)
+        _PERM_FAST = bool(th.equal(a, b) and th.equal(sa, sb))
+    return fast(n) if _PERM_FAST else slow(n)
+
+
 class BasicRewardTrainer(RewardTrainer):
     """Minibatch gradient accumulation with AdamW over a `PreferenceDataset` (:1139-1323)."""
 
@@ -599,10 +657,145 @@ class BasicRewardTrainer(RewardTrainer):
     def requires_regularizer_update(self) -> bool:
         return False
 
+    # -- the fused step: a minibatch never leaves the device ------------------------------------------------------------
+    use_fused_step = True
+
+    def _fused_target(self, dataset):
+        """(net, pool, base dataset, item indices | None) when the whole training step can run as kernels on the device:
+        cross-entropy loss on a single fused network, every parameter trained by a plain AdamW, equal-length fragments.
+        Otherwise None: the per-minibatch autograd path below covers everything else."""
+        pm = self._preference_model
+        if not (self.use_fused_step and type(self.loss) is CrossEntropyRewardLoss and pm.ensemble_model is None
+                and pm.use_fragment_pool and type(self.optim) is th.optim.AdamW and len(self.optim.param_groups) == 1):
+            return None
+        g = self.optim.param_groups[0]
+        if g.get("amsgrad") or g.get("maximize") or g.get("capturable") or g.get("differentiable"):
+            return None
+        net = pm._fused_target()
+        if net is None or net.engine().device().type != "cuda":
+            return None
+        e = net.engine()
+        plist = e._param_list()
+        if ({id(p) for p in g["params"]} != {id(p) for p in plist} or not all(p.requires_grad for p in plist)
+                or len(dataset) == 0):
+            return None
+        index = None
+        while isinstance(dataset, data_th.Subset):  # bagging subsets of the ensemble: resolve to the shared base dataset
+            ind = np.asarray(dataset.indices, dtype=np.int64)
+            index = ind if index is None else ind[index]
+            dataset = dataset.dataset
+        pool = pm._get_pool(net)
+        rows = pool.dataset_rows(dataset)
+        if rows is None:
+            return None
+        return net, pool, rows, index
+
+    def _fused_optimizer_state(self, e):
+        """Adam moments as flat device vectors next to the flat parameter vector, ALIASED by the torch optimiser's
+        per-parameter state (so `optim.state_dict()`, and the autograd path should it run later, see the same moments)."""
+        plist = e._param_list()
+        fo = self.__dict__.get("_fused_opt")
+        if fo is None or fo["ptr"] != e.params.data_ptr():
+            n, dev = e.desc.n_params, e.params.device
+            m, v = th.zeros(n, device=dev), th.zeros(n, device=dev)
+            off = 0
+            for p in plist:
+                k = p.numel()
+                st = self.optim.state.get(p)
+                if st:
+                    m[off:off + k] = st["exp_avg"].reshape(-1)
+                    v[off:off + k] = st["exp_avg_sq"].reshape(-1)
+                self.optim.state[p] = {"step": th.tensor(float(st["step"]) if st else 0.0),
+                                       "exp_avg": m[off:off + k].view(p.shape), "exp_avg_sq": v[off:off + k].view(p.shape)}
+                off += k
+            fo = dict(ptr=e.params.data_ptr(), m=m, v=v, state=th.zeros(_lib.ST_WORDS, dtype=th.int64, device=dev))
+            self._fused_opt = fo
+        g = self.optim.param_groups[0]
+        fo["hp"] = _lib.Adam(lr=g["lr"], beta1=g["betas"][0], beta2=g["betas"][1], eps=g["eps"],
+                             weight_decay=g["weight_decay"])
+        fo["step"] = int(self.optim.state[plist[0]]["step"])
+        fo["state"][_lib.ST_DISC_STEP] = fo["step"]
+        return fo
+
+    def _train_fused(self, target, n_items: int, epochs: int) -> None:
+        """The reference's loop (:1218-1323) with every minibatch as device work only: row-index gather from the fragment
+        pool -> imb_reward_forward -> imb_pref_loss (returns, Boltzmann probability, cross entropy, d loss / d rewards)
+        -> imb_disc_fwd_bwd with that upstream gradient (accumulating over the minibatches of a batch) -> reduction +
+        AdamW in one launch.  Minibatch composition is the reference's DataLoader(shuffle=True) order (same consumption of
+        torch's global RNG, `_epoch_permutation`); losses and accuracies are accumulated on the device and read back once
+        after the last epoch."""
+        net, pool, (R1, R2, prefs_all, has_gt), index = target
+        pm = self._preference_model
+        e = net.engine()
+        e.sync()
+        fo = self._fused_optimizer_state(e)
+        dev, L = e.params.device, pool.L
+        index_t = None if index is None else th.as_tensor(index)
+        stats = th.zeros(8 * epochs, device=dev)  # per epoch: slot 2k = model loss / accuracy / count, 2k + 1 = ground truth
+        train_norm = bool(net.training and e.has_norm)
+        bufs: Dict[int, Tuple[th.Tensor, int, th.Tensor, th.Tensor]] = {}
+        n_steps = 0
+        for epoch_num in range(epochs):
+            accumulated = 0
+            perm = _epoch_permutation(n_items)
+            perm = (perm if index_t is None else index_t[perm]).to(dev)  # the epoch's item order: one upload
+            for s0 in range(0, n_items, self.minibatch_size):
+                ids = perm[s0:s0 + self.minibatch_size]
+                P = int(ids.numel())
+                idx = th.cat([R1.index_select(0, ids), R2.index_select(0, ids)]).reshape(-1)
+                n = 2 * P * L
+                if n not in bufs:
+                    b, ld = e.new_batch(n)
+                    bufs[n] = (b, ld, th.empty(n, device=dev), th.empty(n, device=dev))
+                batch, ld, rews, grad = bufs[n]
+                _lib.gather_rows(pool.table, pool.table.shape[0], pool.tw, idx, n, batch, ld, 0)
+                if train_norm:
+                    e.norm_update(batch, ld, n)
+                if train_norm and e.desc.shaped:  # the training-mode forward of a shaped net reads the mid-update snapshot
+                    rews = reward_nets._FusedForward._fwd_train(e, batch, ld, n)
+                else:
+                    _lib.reward_forward(e.desc, e.params, e.norm_state, batch, ld, n, 0, rews)
+                y = prefs_all.index_select(0, ids)
+                # (an incomplete batch gets proportionally smaller gradients: loss * len / batch_size, :1288-1291)
+                _lib.pref_loss(rews, P, L, y, pm.noise_prob, pm.discount_factor, pm.threshold, P / self.batch_size, grad,
+                               None, stats, 2 * epoch_num)
+                if has_gt:
+                    _lib.pref_loss(pool.rews.index_select(0, idx), P, L, y, pm.noise_prob, pm.discount_factor, pm.threshold,
+                                   0.0, None, None, stats, 2 * epoch_num + 1)
+                e.fwd_bwd(batch, ld, n, n, 0.0, grad, None, accumulated == 0, train_norm and bool(e.desc.shaped))
+                accumulated += P
+                if accumulated >= self.batch_size:
+                    _lib.disc_reduce_adam(e.desc, fo["hp"], e.params, fo["m"], fo["v"], 1.0, e.ws, fo["state"], None)
+                    n_steps += 1
+                    accumulated = 0
+                else:
+                    e.reduce(None)
+            if accumulated != 0:  # an incomplete batch remains
+                _lib.disc_adam(e.desc, fo["hp"], e.params, fo["m"], fo["v"], None, 1.0, e.ws, fo["state"], None)
+                n_steps += 1
+        for p in e._param_list():
+            self.optim.state[p]["step"] = th.tensor(float(fo["step"] + n_steps))
+        st = stats.cpu().numpy().reshape(epochs, 2, 4)  # the one read-back of the training call
+        with self.logger.accumulate_means("reward"):
+            for k in range(epochs):
+                nb = max(float(st[k, 0, 2]), 1.0)
+                self.logger.record(f"epoch-{k}/train/loss", float(st[k, 0, 0]) / nb)
+                self.logger.record(f"epoch-{k}/train/accuracy", float(st[k, 0, 1]) / nb)
+                if has_gt:
+                    self.logger.record(f"epoch-{k}/train/gt_reward_loss", float(st[k, 1, 0]) / nb)
+            nb = max(float(st[-1, 0, 2]), 1.0)
+            self.last_epoch_stats = {"loss": float(st[-1, 0, 0]) / nb, "accuracy": float(st[-1, 0, 1]) / nb}
+        for k, v in self.last_epoch_stats.items():
+            self.logger.record(f"reward/final/train/{k}", v)
+
     def _train(self, dataset, epoch_multiplier: float = 1.0) -> None:
-        dataloader = self._make_data_loader(dataset)
         epochs = round(self.epochs * epoch_multiplier)
         assert epochs > 0, "Must train for at least one epoch."
+        target = self._fused_target(dataset)
+        if target is not None:
+            self._train_fused(target, len(dataset), epochs)
+            return
+        dataloader = self._make_data_loader(dataset)
         with self.logger.accumulate_means("reward"):
             for epoch_num in range(epochs):
                 train_loss, accumulated_size, n_batches, acc, loss_sum = 0.0, 0, 0, 0.0, 0.0

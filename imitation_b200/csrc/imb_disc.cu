@@ -884,14 +884,15 @@ __global__ void __launch_bounds__(256) k_pref_loss(const float* __restrict__ rew
     s = warp_sum(s);
     const bool clipped = s < -threshold || s > threshold;  // th.clip passes the gradient on [min, max] only
     const float d = fminf(fmaxf(s, -threshold), threshold);
-    const float m = 1.0f / (1.0f + expf(d));
+    const float ed = expf(d);
+    const float m = 1.0f / (1.0f + ed);
     const float p = noise_prob * 0.5f + (1.0f - noise_prob) * m;
     const float y = prefs[pr];
     // F.binary_cross_entropy: logs clamped at -100; backward (p - y) / max(p (1 - p), 1e-12)
     const float lp = fmaxf(logf(p), -100.0f), l1p = fmaxf(log1pf(-p), -100.0f);
     const float loss = -(y * lp + (1.0f - y) * l1p);
     const float dl_dp = (p - y) / fmaxf(p * (1.0f - p), 1e-12f) * inv_P;
-    const float dp_dd = -(1.0f - noise_prob) * m * (1.0f - m);
+    const float dp_dd = -(1.0f - noise_prob) * m * m * ed;  // = -(1 - noise) m (1 - m), without the cancellation in 1 - m
     const float g = clipped ? 0.f : grad_scale * dl_dp * dp_dd;  // d loss / d (returns difference)
     if (grad_rews) {
       float* g1 = grad_rews + (int64_t)pr * L;

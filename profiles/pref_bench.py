@@ -80,20 +80,18 @@ def main(args):
     prefs = (rng.random(P) < 0.5).astype(np.float32)
     obs_space, act_space = spaces.Box(-np.inf, np.inf, (Do,)), spaces.Box(-1.0, 1.0, (Da,))
     members = [reward_nets.BasicRewardNet(obs_space, act_space, hid_sizes=(32, 32)).cuda() for _ in range(M)]
-    loss_fn = pc.CrossEntropyRewardLoss()
-    pms = [pc.PreferenceModel(m) for m in members]
-    opts = [th.optim.AdamW(m.parameters(), lr=1e-3) for m in members]
+    ens = reward_nets.RewardEnsemble(obs_space, act_space, members)
+    dataset = pc.PreferenceDataset()
+    dataset.push(frags, prefs)
+    trainer = pc.EnsembleTrainer(pc.PreferenceModel(ens), pc.CrossEntropyRewardLoss(), rng=np.random.default_rng(1),
+                                 batch_size=MB, epochs=1, lr=1e-3)
+    if os.environ.get("IMB_PREF_AUTOGRAD") == "1":  # the per-minibatch autograd + torch AdamW path, for comparison
+        for t in trainer.member_trainers:
+            t.use_fused_step = False
 
     def epoch():
-        last = None
-        for pm, opt in zip(pms, opts):
-            for s in range(0, P, MB):
-                out = loss_fn(frags[s:s + MB], prefs[s:s + MB], pm)
-                opt.zero_grad()
-                out.loss.backward()
-                opt.step()
-                last = out.loss
-        return float(last)  # the D2H read of the epoch's result
+        trainer.train(dataset)  # one epoch of every member on its own bagging subset (reads back the epoch's statistics)
+        return trainer.last_epoch_stats["loss"]
 
     W, K = max(3, args.warmup), max(1, min(args.steps, 10))
     for _ in range(W):
@@ -110,26 +108,30 @@ def main(args):
     launches = _lib.LAUNCHES["count"] - l0
     v = world * K * P * M / (ms / 1e3)
     rows = K * M * 2 * P * L
-    h2d = M * 8 * 2 * 256 * 8  # per epoch: 40 minibatches x 512 slot indices (int64); the pool uploads happened in warm-up
+    config["fused_step"] = all("_fused_opt" in t.__dict__ for t in trainer.member_trainers)
+    h2d = M * P * 8  # per epoch and member: the minibatches' item indices (int64); the pool uploads happened in warm-up
     if rank == 0:
         print(json.dumps({"metric": "preference reward-model training, fragment-pair evaluations/sec", "value": v,
                           "unit": "pair-evaluations/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": config,
-                          "e2e": {"value": v, "unit": "pair-evaluations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                                  "path": "CrossEntropyRewardLoss(fragment_pairs: host TrajectoryWithRew, preferences, "
-                                          "PreferenceModel) -> loss.backward() -> AdamW.step(); every call starts from host "
-                                          "fragment objects and ends with a host float, so value == e2e for this row (the "
-                                          "fragments' transitions are uploaded on their first use and gathered on the device "
-                                          "afterwards; the warm-up epochs contain those uploads)"},
+                          "e2e": {"value": v, "unit": "pair-evaluations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": M * 32,
+                                  "path": "EnsembleTrainer.train(PreferenceDataset of host TrajectoryWithRew pairs): bagging "
+                                          "subsets + DataLoader index stream on the host, every minibatch as device work "
+                                          "(gather from the fragment pool -> imb_reward_forward -> imb_pref_loss -> "
+                                          "imb_disc_fwd_bwd -> reduce + AdamW), one read-back of the epoch's statistics per "
+                                          "member; every call starts from the host dataset and ends with host floats, so "
+                                          "value == e2e for this row (the fragments' transitions are uploaded on their first "
+                                          "use; the warm-up epochs contain those uploads)"},
                           "gpu_launches": launches,
                           "roofline": {"kernel": "k_disc_fwdbwd / k_reward_fwd over 2 * 256 * 100 = 51 200 transition rows per "
                                                  "minibatch", "bound": "hbm",
                                        "achieved": rows * (4 * (Do + Da) + 4) / (ms / 1e3) / 1e9, "peak": None, "unit": "GB/s",
                                        "frac": None, "traffic": None,
-                                       "note": "fragments are device-resident after their first use (FragmentPool); what remains per "
-                                               "minibatch is host work: the slot lookup of 512 fragment objects, the Boltzmann / "
-                                               "BCE torch ops and the eager AdamW step; transition rows/s = "
+                                       "note": "fragments are device-resident after their first use (FragmentPool) and a minibatch "
+                                               "is ~10 launches without a host round trip; what remains is the host's launch "
+                                               "rate (the members are trained one after the other like the reference's); "
+                                               "transition rows/s = "
                                                f"{rows / (ms / 1e3) / 1e6:.1f} M"},
                           "cpu_baseline": None}))
 

@@ -190,3 +190,121 @@ def test_agent_trainer_on_device_generator():
                                    transition_oversampling=1, initial_comparison_frac=0.5, initial_epoch_multiplier=1.0, rng=rng)
     res = pcs.train(total_timesteps=2 * E * H, total_comparisons=8)
     assert np.isfinite(res["reward_loss"]) and 0.0 <= res["reward_accuracy"] <= 1.0
+
+
+def test_index_dataloader_consumes_the_rng_like_the_fragment_dataloader():
+    """The fused reward-trainer step draws its minibatches from DataLoader(range(n), shuffle=True): the same batches, in
+    the same order, with the same consumption of torch's global RNG as the reference's DataLoader over the fragment pairs
+    (algorithms/preference_comparisons.py:1207-1216)."""
+    from torch.utils import data as data_th
+
+    from imitation_b200.algorithms import preference_comparisons as pc
+
+    z, (Do, Da, L, P), trajs, pairs = _golden()
+    ds = pc.PreferenceDataset()
+    ds.push([(_as_traj(a), _as_traj(b)) for a, b in pairs], np.arange(P, dtype=np.float32))
+    th.manual_seed(21)
+    want = [prefs.tolist() for _ in range(2)
+            for _, prefs in data_th.DataLoader(ds, batch_size=3, shuffle=True, collate_fn=pc.preference_collate_fn)]
+    after_want = th.rand(2)
+    th.manual_seed(21)
+    got = [ids.tolist() for _ in range(2) for ids in data_th.DataLoader(range(len(ds)), batch_size=3, shuffle=True)]
+    after_got = th.rand(2)
+    assert got == [[int(v) for v in b] for b in want]
+    assert th.equal(after_want, after_got)
+    # and the whole-epoch shortcut the trainer uses (one upload per epoch instead of a host collate per minibatch)
+    th.manual_seed(21)
+    perms = [pc._epoch_permutation(len(ds)).tolist() for _ in range(2)]
+    after_perm = th.rand(2)
+    assert pc._PERM_FAST is True, "torch's DataLoader draws its seeds differently now: update _epoch_permutation"
+    assert perms == [[i for b in want[e * 4:(e + 1) * 4] for i in (int(v) for v in b)] for e in range(2)]
+    assert th.equal(after_want, after_perm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("noise,discount,threshold", [(0.0, 1.0, 50.0), (0.1, 0.95, 50.0), (0.2, 0.9, 1.5)])
+def test_pref_loss_kernel_matches_torch_autograd(noise, discount, threshold):
+    """imb_pref_loss = PreferenceModel.probability + F.binary_cross_entropy + autograd's d loss / d rewards
+    (:487-530, :1043-1090), including clipped pairs (zero gradient), soft preferences and the statistics accumulator."""
+    from imitation_b200 import _lib
+
+    th.manual_seed(0)
+    P, L, scale = 77, 13, 0.25
+    rews = (th.randn(2, P, L) * 2.0).cuda().requires_grad_()
+    y = (th.rand(P) < 0.5).float()
+    y[::5] = th.rand(len(y[::5]))
+    y = y.cuda()
+    w = discount ** th.arange(L, device="cuda")
+    d = th.clip(((rews[1] - rews[0]) * w).sum(1), -threshold, threshold)
+    p = noise * 0.5 + (1 - noise) / (1 + d.exp())
+    loss = th.nn.functional.binary_cross_entropy(p, y)
+    (loss * scale).backward()
+    grad, probs, stats = th.zeros(2 * P * L, device="cuda"), th.zeros(P, device="cuda"), th.zeros(8, device="cuda")
+    for _ in range(2):  # two minibatches accumulate
+        _lib.pref_loss(rews.detach().reshape(-1).contiguous(), P, L, y, noise, discount, threshold, scale, grad, probs, stats, 1)
+    th.cuda.synchronize()
+    np.testing.assert_allclose(probs.cpu().numpy(), p.detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
+    g = rews.grad.reshape(-1).cpu().numpy()
+    np.testing.assert_allclose(grad.cpu().numpy(), g, rtol=2e-5, atol=1e-9 + 1e-6 * float(np.abs(g).max()))
+    acc = float(((p > 0.5) == (y > 0.5)).float().mean())
+    np.testing.assert_allclose(stats.cpu().numpy(), [0, 0, 0, 0, 2 * float(loss), 2 * acc, 2, 0], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_fused_reward_trainer_step_equals_the_autograd_path():
+    """BasicRewardTrainer's device-only step (imb_gather_rows -> imb_reward_forward -> imb_pref_loss -> imb_disc_fwd_bwd
+    -> reduce + AdamW) against the per-minibatch autograd + torch.optim.AdamW path on the same data and seeds: same
+    minibatches, same statistics, same weights and optimiser state; then the ensemble trainer on bagging subsets."""
+    from imitation_b200 import spaces
+    from imitation_b200.algorithms import preference_comparisons as pc
+    from imitation_b200.rewards import reward_nets
+    from imitation_b200.util import networks
+
+    z, (Do, Da, L, P), trajs, pairs = _golden()
+    obs_space, act_space = spaces.Box(-np.inf, np.inf, (Do,)), spaces.Box(-1.0, 1.0, (Da,))
+    frags = [(_as_traj(a), _as_traj(b)) for a, b in pairs]
+    ds = pc.PreferenceDataset()
+    ds.push(frags, z["prefs_sampled"].astype(np.float32))
+    nets, trainers = [], []
+    for fused in (True, False):
+        th.manual_seed(4)
+        net = reward_nets.BasicRewardNet(obs_space, act_space, hid_sizes=(32, 32),
+                                         normalize_input_layer=networks.RunningNorm).cuda()
+        pm = pc.PreferenceModel(net, noise_prob=0.05, discount_factor=0.97)
+        tr = pc.BasicRewardTrainer(pm, pc.CrossEntropyRewardLoss(), rng=np.random.default_rng(5), batch_size=6,
+                                   minibatch_size=3, epochs=3, lr=2e-3)
+        tr.use_fused_step = fused
+        th.manual_seed(10)
+        before = __import__("imitation_b200")._lib.LAUNCHES["count"]
+        tr.train(ds)
+        tr.launches = __import__("imitation_b200")._lib.LAUNCHES["count"] - before
+        nets.append(net)
+        trainers.append(tr)
+    a, b = trainers
+    assert a._fused_target(ds) is not None and "_fused_opt" in a.__dict__ and "_fused_opt" not in b.__dict__
+    for k in ("loss", "accuracy"):
+        np.testing.assert_allclose(a.last_epoch_stats[k], b.last_epoch_stats[k], rtol=1e-4, atol=1e-6)
+    for key in ("mean/reward/epoch-0/train/loss", "mean/reward/epoch-2/train/gt_reward_loss",
+                "mean/reward/epoch-1/train/accuracy"):
+        np.testing.assert_allclose(a.logger.name_to_value[key], b.logger.name_to_value[key], rtol=1e-4, atol=1e-6)
+    sa, sb = nets[0].state_dict(), nets[1].state_dict()
+    for k in sa:
+        if k == "mlp.dense_final.bias":  # gradient = rounding noise (cancels in r2 - r1); Adam turns it into +-lr steps
+            continue
+        np.testing.assert_allclose(sa[k].cpu().numpy(), sb[k].cpu().numpy(), rtol=2e-4, atol=2e-6, err_msg=k)
+    pa, pb = list(nets[0].parameters()), list(nets[1].parameters())
+    for x, y in zip(pa[:-1], pb[:-1]):
+        assert float(a.optim.state[x]["step"]) == float(b.optim.state[y]["step"]) > 0
+        np.testing.assert_allclose(a.optim.state[x]["exp_avg"].cpu().numpy(), b.optim.state[y]["exp_avg"].cpu().numpy(),
+                                   rtol=1e-3, atol=1e-7)
+    # an ensemble: every member on its own bagging subset, all on the fused step, the fragment pool shared
+    members = [reward_nets.BasicRewardNet(obs_space, act_space, hid_sizes=(32, 32)).cuda() for _ in range(3)]
+    ens = reward_nets.RewardEnsemble(obs_space, act_space, members)
+    et = pc.EnsembleTrainer(pc.PreferenceModel(ens), pc.CrossEntropyRewardLoss(), rng=np.random.default_rng(2),
+                            batch_size=4, epochs=2, lr=1e-3)
+    w0 = [m.mlp.dense0.weight.detach().clone() for m in members]
+    et.train(ds)
+    assert all("_fused_opt" in t.__dict__ for t in et.member_trainers)
+    assert all(not th.equal(m.mlp.dense0.weight, w) for m, w in zip(members, w0))
+    assert np.isfinite(et.last_epoch_stats["loss"]) and 0.0 <= et.last_epoch_stats["accuracy"] <= 1.0
+    assert et._preference_model._pool is not None and et._preference_model._pool.table is not None
