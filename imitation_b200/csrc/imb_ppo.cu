@@ -20,7 +20,7 @@
 #ifdef IMB_PPO_TIMING
 // phase timing for profiles/: CTA 0 / thread 0 accumulates clock64() deltas per phase of the optimiser step
 __device__ long long g_ppo_clk[24];
-__device__ long long g_ppo_wclk[64];  // [slot][warp]: cycles since the top barrier at points of the warp chain (CTA 0)
+__device__ long long g_ppo_wclk[80];  // [slot][warp]: cycles since the top barrier at points of the warp chain (CTA 0)
 #define PPO_TICK(i)                                  \
   do {                                               \
     if (tid == 0) {                                  \
@@ -43,7 +43,7 @@ __device__ long long g_ppo_wclk[64];  // [slot][warp]: cycles since the top barr
 
 namespace {
 
-constexpr int PT = 256;   // threads per CTA: 0..127 = policy tower, 128..255 = value tower
+constexpr int PT = 256;   // threads per CTA: warps 0, 1 = policy chain, 2, 3 = value chain, 4-7 = statistics / prefetch
 constexpr int CL = 8;     // CTAs per cluster: each owns RL rows of every minibatch and 1/CL of the gradient reduction
 constexpr int RL = 8;     // minibatch rows per CTA  (CL * RL = 64 >= SB3 batch_size)
 constexpr int PR = CL * RL;
@@ -152,6 +152,86 @@ __device__ __forceinline__ float sum8(const float (&d)[8]) {
   return ((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7]));
 }
 
+// Weight gradients of ONE tower over the CTA's RL = 8 rows -> GP (P-layout, local shared memory), by NQ warps: thread =
+// (unit gj = lane, every NQ-th input); the unit's dL/dz rows live in registers, the input rows are warp-uniform
+// broadcasts, the scattered GP stores have odd lane strides (conflict free).  The head biases / log_std (plain row sums)
+// ride with the last input group.  The dot products of a group are all computed into registers BEFORE the group's
+// stores: the compiler cannot prove that GP and the activation tiles do not alias, and with a store between two dots it
+// serialises them (load latency + FMA chain per dot, ~55 cycles each; the phase is latency bound).
+struct WgradOff {
+  int w1, b1, w2, b2, wa, ba, wv, bv, ls, ldo, ldh;
+};
+template <int NQ, int HPx>
+__device__ __forceinline__ void tower_wgrad(const int tnet, const int gj, const int wq, const int h, const int Do, const int Da,
+                                            const bool discrete, const WgradOff o, float* __restrict__ GP,
+                                            const float* __restrict__ tH1, const float* __restrict__ tLAT,
+                                            const float* __restrict__ tDZ2, const float* __restrict__ tDZ1,
+                                            const float* __restrict__ XNc, const float* __restrict__ DM,
+                                            const float* __restrict__ DLS, const float* __restrict__ DVAL) {
+  constexpr int RLc = 8;
+  constexpr int T2 = (HPx + NQ - 1) / NQ;  // layer-2 inputs per thread
+  float dz2[8], dz1[8], lt[8];
+  if (gj < h) {
+    load8(dz2, tDZ2 + gj * RLc);
+    load8(dz1, tDZ1 + gj * RLc);
+    load8(lt, tLAT + gj * RLc);
+    {  // dW2[gj][i], i = wq + NQ t
+      float r[T2];
+#pragma unroll
+      for (int t = 0; t < T2; ++t) {
+        const int i = wq + NQ * t;
+        r[t] = dot8r(dz2, tH1 + (i < HPx ? i : 0) * RLc);
+      }
+#pragma unroll
+      for (int t = 0; t < T2; ++t) {
+        const int i = wq + NQ * t;
+        if (i < h) GP[o.w2 + gj * o.ldh + i] = r[t];
+      }
+    }
+    for (int k0 = wq; k0 < Do; k0 += 4 * NQ) {  // dW1[gj][k], four at a time
+      float r[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int k = k0 + NQ * t;
+        r[t] = dot8r(dz1, XNc + (k < Do ? k : 0) * RLc);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int k = k0 + NQ * t;
+        if (k < Do) GP[o.w1 + gj * o.ldo + k] = r[t];
+      }
+    }
+    if (tnet == 0) {
+      for (int a0 = wq; a0 < Da; a0 += 2 * NQ) {
+        const int a1 = a0 + NQ;
+        const float ra = dot8r(lt, DM + a0 * RLc), rb = dot8r(lt, DM + (a1 < Da ? a1 : a0) * RLc);
+        GP[o.wa + a0 * o.ldh + gj] = ra;
+        if (a1 < Da) GP[o.wa + a1 * o.ldh + gj] = rb;
+      }
+    } else if (wq == 0) {
+      GP[o.wv + gj] = dot8r(lt, DVAL);
+    }
+    if (wq == 0) GP[o.b2 + gj] = sum8(dz2);
+    if (wq == NQ - 1) GP[o.b1 + gj] = sum8(dz1);
+  }
+  if (wq == NQ - 1) {
+    if (tnet == 0) {  // ba, log_std
+      for (int t = gj; t < 2 * Da; t += HPx) {
+        if (t < Da) {
+          load8(dz2, DM + t * RLc);
+          GP[o.ba + t] = sum8(dz2);
+        } else if (!discrete) {
+          load8(dz2, DLS + (t - Da) * RLc);
+          GP[o.ls + t - Da] = sum8(dz2);
+        }
+      }
+    } else if (gj == 0) {  // bv
+      load8(dz2, DVAL);
+      GP[o.bv] = sum8(dz2);
+    }
+  }
+}
+
 // PPO.train for one rollout: n_epochs x ceil(N / batch) optimiser steps, ONE cluster of CL CTAs.
 // Data flow of one optimiser step (64-row minibatch, CTA c owns rows 8c..8c+7, every CTA holds all parameters):
 //   * the minibatch rows are staged row-major in shared memory by asynchronous 16-byte row copies issued TWO
@@ -162,11 +242,13 @@ __device__ __forceinline__ float sum8(const float (&d)[8]) {
 //     hidden unit; only __syncwarp() between layers (the two towers interact through the summed loss only), so
 //     the ~8 dependent stages of the chain cost no CTA barrier, and every weight read from shared memory
 //     feeds four FMAs (with 2 rows per warp on all 8 warps the chain was bound by shared-memory wavefronts);
-//   * weight gradients over the CTA's 8 rows: thread = (tower, unit, input subset), staged in local shared
-//     memory in the parameter layout, pushed to the slice owners through distributed shared memory with
-//     16-byte stores; owners sum the CL partials in fixed order, exchange the squared slice norms, run
-//     clip_grad_norm_ + Adam on their slice (the moments never leave their owner) and all-gather the new
-//     parameters into every CTA's copy.
+//   * weight gradients over the CTA's 8 rows: thread = (unit, input subset) of one tower, staged in local shared
+//     memory in the parameter layout.  The VALUE tower's are computed early by warps 2-7 (its chain ends ~1 k cycles
+//     before the policy tower's: no action head, no loss terms) while warps 0, 1 finish the policy chain; the policy
+//     tower's by all eight warps after the step's second barrier.  The staged vector is pushed to the slice owners
+//     through distributed shared memory with 16-byte stores; owners sum the CL partials in fixed order, exchange the
+//     squared slice norms, run clip_grad_norm_ + Adam on their slice (the moments never leave their owner) and
+//     all-gather the new parameters into every CTA's copy.
 // No cluster barrier inside the step loop (the exchanged data signals mbarriers at the receivers), three CTA
 // barriers per optimiser step; the only global-memory traffic inside a step is the asynchronous minibatch prefetch.
 template <int HP>
@@ -193,7 +275,6 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   const int da_store = pd.discrete ? 1 : Da;
   const int col_logp = Do + da_store, col_adv = col_logp + 3, col_ret = col_logp + 4;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int net = tid >> 7, tt = tid & 127;  // tower, thread within tower
   const int rw = A.rw, RS2 = A.RS2;          // rollout row width (multiple of 4) / staged row stride (= 4 mod 8)
   auto al = [](int x) { return (x + 31) / 32 * 32; };
 
@@ -220,13 +301,6 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   float* MEAN = smem + o; o += DAP * RL;        // action means / logits [a][RL]
   float* DVAL = smem + o; o += 32;              // [RL] dL/dvalue
   float* rstat = smem + o; o += al(2 * 64 + 4); // running mean | var of the policy's feature RunningNorm
-  float* H1 = TH1 + net * HP * RL;
-  float* LAT = TLAT + net * HP * RL;
-  float* DZ2 = TDZ2 + net * HP * RL;
-  float* DZ1 = TDZ1 + net * HP * RL;
-  // (selects, not PL.x[net]: a dynamically indexed member would put the whole struct in local memory)
-  const int o_w1 = net ? PL.w1[1] : PL.w1[0], o_b1 = net ? PL.b1[1] : PL.b1[0];
-  const int o_w2 = net ? PL.w2[1] : PL.w2[0], o_b2 = net ? PL.b2[1] : PL.b2[0];
 
   for (int i = tid; i < CL * S; i += PT) Pm[i] = Ms[i] = Vs[i] = GP[i] = RECV[i] = 0.f;
   for (int i = tid; i < 3 * rsz; i += PT) ROWS[i] = 0.f;
@@ -263,10 +337,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   const int64_t perm_draw0 = state[IMB_ST_PPO_EPOCH];
   double b1pow = pow(0.9, (double)adam_step), b2pow = pow(0.999, (double)adam_step);  // beta^t, kept incrementally
   const int row0 = crank * RL;        // first minibatch row owned by this CTA
-  // weight-gradient mapping: unit gj, every NWQ-th input
-  constexpr int NWQ = 128 / HP;
-  const int gj = tt % HP, wq = tt / HP;
-  const bool jlive = gj < h;
+  const WgradOff wo_p = {PL.w1[0], PL.b1[0], PL.w2[0], PL.b2[0], PL.wa, PL.ba, PL.wv, PL.bv, PL.ls, ldo, ldh};
+  const WgradOff wo_v = {PL.w1[1], PL.b1[1], PL.w2[1], PL.b2[1], PL.wa, PL.ba, PL.wv, PL.bv, PL.ls, ldo, ldh};
 
   // Asynchronous row gather of one minibatch (epoch ep, first row start) into buffer `buf` by warps 4-7: two
   // threads per row draw the row index and copy half of the 16-byte aligned rollout row each with 16-byte
@@ -378,7 +450,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
 
 #ifdef IMB_PPO_TIMING
   long long clk_acc[16] = {0}, clk_last = clock64();
-  long long wacc[8] = {0};  // per-warp chain clocks, kept in registers (a global RMW per sample stalls the chain)
+  long long wacc[10] = {0};  // per-warp chain clocks, kept in registers (a global RMW per sample stalls the chain)
 #endif
   int ep_now = 0, start = 0;  // epoch and first row of the current step
   for (int64_t gs = 0; gs < n_steps; ++gs) {
@@ -520,24 +592,35 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
         dl3 = __shfl_sync(0xffffffffu, dval, 24) * wvj;
       } else {
         const float* Wa = Pm + PL.wa;
-        // action means / logits from the latent tile in shared memory: lane = (action a0 + lane / 4, row lane % 4),
-        // a dot over the HP units (pad units hold zeros; Wa rows have the odd stride ldh: no bank conflicts)
+        // action means / logits from the latent tile in shared memory: lane = (action ab + lane / 4, units q + 4 i of
+        // quarter q = lane % 4): one 16-byte load brings a unit's four rows, so a weight and a latent load feed four FMAs
+        // (one lane per (action, row) cost two loads per FMA: 64 loads per lane, ~700 cycles of the chain); the four
+        // row sums are then reduced over the quad by a transposing butterfly (3 shuffles) that leaves row r0 + q in
+        // lane q.  Pad units hold zeros; Wa rows have the odd stride ldh.
         __syncwarp();
         {
-          const int asub = lane >> 2, rrr = lane & 3;
+          const int asub = lane >> 2, q = lane & 3;
+          const bool b0 = (lane & 1) != 0, b1 = (lane & 2) != 0;
           for (int ab = 0; ab < Da; ab += 8) {
             const int a = ab + asub, ac = a < Da ? a : 0;
-            const float* wr = Wa + ac * ldh;
-            const float* lr = cLAT + r0 + rrr;
+            const float* wr = Wa + ac * ldh + q;
+            const float* lr = cLAT + q * RL + r0;
             float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-            for (int jj = 0; jj < HP; jj += 4) {
-              s0 = fmaf(wr[jj], lr[jj * RL], s0);
-              s1 = fmaf(wr[jj + 1], lr[(jj + 1) * RL], s1);
-              s2 = fmaf(wr[jj + 2], lr[(jj + 2) * RL], s2);
-              s3 = fmaf(wr[jj + 3], lr[(jj + 3) * RL], s3);
+            for (int i = 0; i < HP / 4; ++i) {
+              const float w = wr[4 * i];
+              const float4 l4 = ld4(lr + 4 * i * RL);
+              s0 = fmaf(w, l4.x, s0);
+              s1 = fmaf(w, l4.y, s1);
+              s2 = fmaf(w, l4.z, s2);
+              s3 = fmaf(w, l4.w, s3);
             }
-            if (a < Da) MEAN[a * RL + r0 + rrr] = ((s0 + s1) + (s2 + s3)) + Pm[PL.ba + a];
+            float ka = b0 ? s1 : s0, kb = b0 ? s3 : s2;
+            ka += __shfl_xor_sync(0xffffffffu, b0 ? s0 : s1, 1);
+            kb += __shfl_xor_sync(0xffffffffu, b0 ? s2 : s3, 1);
+            float kk = b1 ? kb : ka;
+            kk += __shfl_xor_sync(0xffffffffu, b1 ? ka : kb, 2);
+            if (a < Da) MEAN[a * RL + r0 + q] = kk + Pm[PL.ba + a];
           }
         }
         __syncwarp();
@@ -655,6 +738,15 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     }
     if (pd.has_norm && gs + 1 < n_steps) run_count += min(mb, Ni - start_next);
     PPO_WCLK(0);
+    // ---- 1c. the VALUE tower's weight gradients, early: its chain (warps 2, 3) finishes ~1 k cycles before the policy
+    //          tower's (no action head, no loss terms) and the statistics / prefetch warps are done by then as well, so
+    //          warps 2-7 meet on a named barrier and compute them while warps 0, 1 are still in the policy chain ------
+    if (warp >= 2) {
+      asm volatile("bar.sync 1, 192;" ::: "memory");
+      tower_wgrad<6, HP>(1, lane, warp - 2, h, Do, Da, pd.discrete != 0, wo_v, GP, TH1 + HP * RL, TLAT + HP * RL,
+                         TDZ2 + HP * RL, TDZ1 + HP * RL, XNc, DM, DLS, DVAL);
+    }
+    PPO_WCLK(8);
     // partial loss sums of this CTA -> CTA 0 (distributed shared memory)
     if (loss_log) {  // (uniform) loss terms are only reduced when the caller asked for the log
       const float s_pg = block_sum(l_pg, red);
@@ -669,43 +761,8 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
     }
     __syncthreads();
     PPO_TICK(3);
-    // ---- 2. partial gradients (own RL rows) -> GP (P-layout, local shared memory): thread = (tower, unit gj,
-    //         every NWQ-th input); the unit's dL/dz rows live in registers, the input rows are warp-uniform
-    //         broadcasts, the scattered GP stores have odd lane strides (conflict free) -------------------------------
-    if (jlive) {
-      float dz[8];
-      load8(dz, DZ2 + gj * RL);
-#pragma unroll 4
-      for (int i = wq; i < h; i += NWQ) GP[o_w2 + gj * ldh + i] = dot8r(dz, H1 + i * RL);
-      if (wq == 0) GP[o_b2 + gj] = sum8(dz);
-      load8(dz, DZ1 + gj * RL);
-#pragma unroll 4
-      for (int k = wq; k < Do; k += NWQ) GP[o_w1 + gj * ldo + k] = dot8r(dz, XNc + k * RL);
-      if (wq == NWQ - 1) GP[o_b1 + gj] = sum8(dz);
-      load8(dz, LAT + gj * RL);
-      if (net == 0) {
-        for (int a = wq; a < Da; a += NWQ) GP[PL.wa + a * ldh + gj] = dot8r(dz, DM + a * RL);
-      } else if (wq == 0) {
-        GP[PL.wv + gj] = dot8r(dz, DVAL);
-      }
-    }
-    if (net == 1 && wq == NWQ - 1) {  // ba, log_std, bv: plain row sums
-      for (int t = gj; t <= 2 * Da; t += HP) {
-        float dz[8];
-        if (t < Da) {
-          load8(dz, DM + t * RL);
-          GP[PL.ba + t] = sum8(dz);
-        } else if (t < 2 * Da) {
-          if (!pd.discrete) {
-            load8(dz, DLS + (t - Da) * RL);
-            GP[PL.ls + t - Da] = sum8(dz);
-          }
-        } else {
-          load8(dz, DVAL);
-          GP[PL.bv] = sum8(dz);
-        }
-      }
-    }
+    // ---- 2. the POLICY tower's weight gradients (and the action head's) by all eight warps ------------------------------
+    tower_wgrad<PT / 32, HP>(0, lane, warp, h, Do, Da, pd.discrete != 0, wo_p, GP, TH1, TLAT, TDZ2, TDZ1, XNc, DM, DLS, DVAL);
     __syncthreads();
     PPO_TICK(7);
     // ---- 3. push the partials to the slice owners: RECV[this CTA][i], one 16-byte DSMEM store per quad ----------
@@ -803,7 +860,7 @@ __global__ void __launch_bounds__(PT, 1) k_ppo_update(const PpoArgs A, float* __
   if (crank == 0 && tid == 0)
     for (int i = 0; i < 16; ++i) g_ppo_clk[i] = clk_acc[i];
   if (crank == 0 && lane == 0)
-    for (int i = 0; i < 8; ++i) g_ppo_wclk[i * 8 + warp] = wacc[i];
+    for (int i = 0; i < 10; ++i) g_ppo_wclk[i * 8 + warp] = wacc[i];
 #endif
 
   // ---- write back (CTA 0): parameters and moments in torch order, norm state, counters ------------------------------
@@ -1052,8 +1109,8 @@ extern "C" __attribute__((visibility("default"))) int imb_debug_ppo_clocks(long 
   return (int)cudaMemcpyFromSymbol(out, g_ppo_clk, 16 * sizeof(long long));
 }
 extern "C" __attribute__((visibility("default"))) int imb_debug_ppo_warp_clocks(long long* out, int reset) {
-  static const long long zero[64] = {0};
+  static const long long zero[80] = {0};
   if (reset) return (int)cudaMemcpyToSymbol(g_ppo_wclk, zero, sizeof(zero));
-  return (int)cudaMemcpyFromSymbol(out, g_ppo_wclk, 64 * sizeof(long long));
+  return (int)cudaMemcpyFromSymbol(out, g_ppo_wclk, 80 * sizeof(long long));
 }
 #endif

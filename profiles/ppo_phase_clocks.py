@@ -45,9 +45,9 @@ for n, c in zip(NAMES, out):
     print(f"{n:<18s} {c / steps:9.0f} cycles/step  {100.0 * c / tot:5.1f} %")
 print(f"{'total':<18s} {tot / steps:9.0f} cycles/step")
 
-w = (ctypes.c_longlong * 64)()
+w = (ctypes.c_longlong * 80)()
 assert _lib.lib().imb_debug_ppo_warp_clocks(w, 0) == 0
 print("per-warp cycles/step since the top barrier (CTA 0; warps 0,1 policy tower, 2,3 value tower; warps 4-7: slot 1 = next-step stats done, slot 3 = prefetch issued):")
 for slot, name in ((1, "stats done (w4-7)"), (3, "after layer 1 | prefetch"), (4, "after layer 2"), (5, "after means (policy)"), (6, "after logp reduce"), (7, "after dM/dlogstd"),
-                   (2, "after heads/loss"), (0, "chain end")):
+                   (2, "after heads/loss"), (0, "chain end"), (8, "early value wgrad done (w2-7)")):
     print(f"  {name:<22s}", [round(w[slot * 8 + i] / steps) for i in range(8)])
