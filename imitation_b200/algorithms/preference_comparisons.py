@@ -842,14 +842,65 @@ class EnsembleTrainer(BasicRewardTrainer):
                                custom_logger=self.logger, regularizer_factory=regularizer_factory, rng=self.rng)
             for mp in self._preference_model.member_pref_models]
 
+    # -- members over GPUs ("RewardEnsemble ... could place members on different GPUs"; BASELINE config 5) ----
+    _dist = None
+
+    def set_distributed(self, group=None) -> None:
+        """Member-parallel training over the ranks of a `torch.distributed` group (one process per GPU, every rank
+        constructed with the same seeds and fed the same dataset): member k is trained by rank k % W, on exactly the
+        bagging subset and minibatch order it has in a single-process run -- every rank draws every member's subset and
+        consumes the torch-RNG draws of the members it skips -- and after the last member the owners broadcast their
+        members' parameters, RunningNorm statistics and AdamW state.  Every rank ends with all members, bit-identical to
+        the single-process result.  Additive API: the reference trains the members one after the other in one process
+        (:1417-1424)."""
+        import torch.distributed as dist
+
+        self._dist = (dist.get_world_size(group), dist.get_rank(group), group)
+
+    def _sync_members(self) -> None:
+        import torch.distributed as dist
+
+        W, rank, group = self._dist
+        trainers = self.member_trainers
+        states = []
+        for t in trainers:
+            net = t._preference_model._fused_target()
+            if net is None or not t.use_fused_step:
+                raise NotImplementedError("member-parallel ensemble training needs members on the device-only step "
+                                          "(fused reward networks, cross-entropy loss, AdamW)")
+            e = net.engine()
+            e.sync()
+            states.append((e, t._fused_optimizer_state(e)))  # (creates the flat moments on the ranks that skipped it)
+        meta = th.zeros(len(trainers), 3, dtype=th.float64, device=states[0][0].params.device)
+        for k, (t, (e, fo)) in enumerate(zip(trainers, states)):
+            src = k % W if group is None else dist.get_global_rank(group, k % W)
+            for x in (e.params, fo["m"], fo["v"]) + ((e.norm_state, e.norm_count) if e.has_norm else ()):
+                dist.broadcast(x, src=src, group=group)
+            if k % W == rank:
+                meta[k, 0], meta[k, 1] = t.last_epoch_stats["loss"], t.last_epoch_stats["accuracy"]
+                meta[k, 2] = float(t.optim.state[e._param_list()[0]]["step"])
+        dist.all_reduce(meta, group=group)
+        meta = meta.cpu()
+        for k, (t, (e, fo)) in enumerate(zip(trainers, states)):
+            t.last_epoch_stats = {"loss": float(meta[k, 0]), "accuracy": float(meta[k, 1])}
+            for p in e._param_list():
+                t.optim.state[p]["step"] = th.tensor(float(meta[k, 2]))
+
     def _train(self, dataset, epoch_multiplier: float = 1.0) -> None:
         sampler = data_th.RandomSampler(dataset, replacement=True, num_samples=len(dataset),
                                         generator=th.Generator().manual_seed(make_seeds(self.rng)))
         stats = defaultdict(list)
+        W, rank = (self._dist[0], self._dist[1]) if self._dist is not None else (1, 0)
         for member_idx, trainer in enumerate(self.member_trainers):
             bagging_dataset = data_th.Subset(dataset, list(sampler))
-            trainer.train(bagging_dataset, epoch_multiplier=epoch_multiplier)
-            del member_idx
+            if member_idx % W == rank:
+                trainer.train(bagging_dataset, epoch_multiplier=epoch_multiplier)
+            else:  # another rank's member: consume the draws its epochs make from torch's global RNG
+                for _ in range(round(trainer.epochs * epoch_multiplier)):
+                    _epoch_permutation(len(bagging_dataset))
+        if W > 1:
+            self._sync_members()
+        for trainer in self.member_trainers:
             for k, v in trainer.last_epoch_stats.items():
                 stats[k].append(v)
         self.last_epoch_stats = {k: float(np.mean(v)) for k, v in stats.items()}

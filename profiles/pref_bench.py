@@ -38,8 +38,11 @@ def main(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     config = {"workload": "preference comparisons reward training, Hopper-shaped (obs11/act3), 2048 fragment pairs x length "
                           "100, 5-member ensemble of BasicRewardNet 32x32, minibatch 256 pairs", "name": "pref",
-              "pairs": P, "fragment_length": L, "members": M, "parallelism": f"replicas x{world} (members are trained "
-              "serially on each GPU; no cross-GPU exchange)"}
+              "pairs": P, "fragment_length": L, "members": M,
+              "parallelism": ("one GPU: the members are trained one after the other" if world == 1 else
+                              f"members over {world} GPUs (member k on rank k % {world}: {-(-M // world)} members on the busiest "
+                              "rank; owners broadcast parameters + AdamW state after every training call; result "
+                              "bit-identical to the single-GPU run)")}
     rng = np.random.default_rng(0)
     if args.impl == "reference":
         if rank != 0:
@@ -72,6 +75,10 @@ def main(args):
         return
     local = int(os.environ.get("LOCAL_RANK", "0"))
     th.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=th.device("cuda", local))
     from imitation_b200 import _lib, spaces
     from imitation_b200.algorithms import preference_comparisons as pc
     from imitation_b200.rewards import reward_nets
@@ -85,6 +92,8 @@ def main(args):
     dataset.push(frags, prefs)
     trainer = pc.EnsembleTrainer(pc.PreferenceModel(ens), pc.CrossEntropyRewardLoss(), rng=np.random.default_rng(1),
                                  batch_size=MB, epochs=1, lr=1e-3)
+    if world > 1:
+        trainer.set_distributed()
     if os.environ.get("IMB_PREF_AUTOGRAD") == "1":  # the per-minibatch autograd + torch AdamW path, for comparison
         for t in trainer.member_trainers:
             t.use_fused_step = False
@@ -97,6 +106,8 @@ def main(args):
     for _ in range(W):
         epoch()
     th.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     l0 = _lib.LAUNCHES["count"]
     a, b = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
     a.record()
@@ -105,16 +116,20 @@ def main(args):
     b.record()
     b.synchronize()
     ms = a.elapsed_time(b)
+    if world > 1:  # max over ranks (device time)
+        t = th.tensor([ms], device="cuda", dtype=th.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
     launches = _lib.LAUNCHES["count"] - l0
-    v = world * K * P * M / (ms / 1e3)
+    v = K * P * M / (ms / 1e3)  # whole job: the ONE ensemble all ranks train together
     rows = K * M * 2 * P * L
     config["fused_step"] = all("_fused_opt" in t.__dict__ for t in trainer.member_trainers)
     h2d = M * P * 8  # per epoch and member: the minibatches' item indices (int64); the pool uploads happened in warm-up
     if rank == 0:
         print(json.dumps({"metric": "preference reward-model training, fragment-pair evaluations/sec", "value": v,
                           "unit": "pair-evaluations/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": config,
+                          "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "config": config,
                           "e2e": {"value": v, "unit": "pair-evaluations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": M * 32,
                                   "path": "EnsembleTrainer.train(PreferenceDataset of host TrajectoryWithRew pairs): bagging "
                                           "subsets + DataLoader index stream on the host, every minibatch as device work "
@@ -134,6 +149,8 @@ def main(args):
                                                "transition rows/s = "
                                                f"{rows / (ms / 1e3) / 1e6:.1f} M"},
                           "cpu_baseline": None}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

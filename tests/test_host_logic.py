@@ -215,3 +215,124 @@ def test_demo_ingest_reads_reference_rollouts(rel):
         pytest.skip("reference checkout not present")
     trajs = _check_fixture(path)
     assert len(trajs) > 50
+
+
+# ---- preference comparisons: ensemble members over ranks (host logic on CPU, kernels replaced by stand-ins) ------------
+def _install_cpu_stand_ins():
+    """Replace the CUDA-only pieces by CPU stand-ins whose 'optimiser step' depends on the member's own parameters and on
+    exactly which fragment rows, in which order, each minibatch gathered -- so any slip in member assignment, bagging
+    subsets, minibatch order (torch RNG bookkeeping for skipped members) or the broadcasts changes the result."""
+    from imitation_b200 import _lib
+    from imitation_b200.rewards import reward_nets
+
+    E = reward_nets.FusedEngine
+
+    class _Dev:
+        type = "cuda"
+
+    def sync(self):
+        if getattr(self, "params", None) is not None and getattr(self, "_cpu_synced", False):
+            return
+        plist = self._param_list()
+        flat = th.cat([p.detach().reshape(-1) for p in plist])
+        off = 0
+        for p in plist:
+            p.data = flat[off:off + p.numel()].view(p.shape)
+            off += p.numel()
+        self.params, self.norm_state, self.norm_count = flat, th.zeros(2), th.zeros(2, dtype=th.int32)
+        self.ws = th.zeros(8)
+        self._cpu_synced = True
+
+    E.sync = sync
+    E.device = lambda self: _Dev()
+    E.new_batch = lambda self, n: (th.zeros(4, n), n)
+    st = {"h": 0.0}
+
+    def gather_rows(table, cap, tw, idx, n, batch, ld, col0):
+        w = th.arange(1, idx.numel() + 1, dtype=th.float64)
+        st["h"] = float((idx.double() * w).sum() % 9973) / 9973.0
+
+    def reduce_adam(desc, hp, params, m, v, div, ws, state, out):
+        params.mul_(1.0 - hp.lr * hp.weight_decay).add_(1e-3 * st["h"] * (1.0 + params.abs().mean()))
+        m.add_(st["h"])
+        v.add_(1.0)
+        state[_lib.ST_DISC_STEP] += 1
+
+    _lib.gather_rows = gather_rows
+    _lib.disc_reduce_adam = reduce_adam
+    _lib.disc_adam = lambda desc, hp, params, m, v, g, div, ws, state, out: reduce_adam(desc, hp, params, m, v, div, ws,
+                                                                                      state, out)
+    for name in ("table_store", "reward_forward", "pref_loss", "disc_fwd_bwd", "disc_reduce", "disc_norm_update"):
+        setattr(_lib, name, lambda *a, **k: None)
+
+
+def _ensemble_run(world_rank=None):
+    """Two PreferenceComparisons-style reward-training calls of a 3-member ensemble; returns every member's parameters."""
+    from imitation_b200 import spaces
+    from imitation_b200.algorithms import preference_comparisons as pc
+    from imitation_b200.data import types
+    from imitation_b200.rewards import reward_nets
+
+    Do, Da, L, P = 5, 2, 4, 14
+    rng = np.random.default_rng(0)
+    obs_space, act_space = spaces.Box(-np.inf, np.inf, (Do,)), spaces.Box(-1.0, 1.0, (Da,))
+
+    def frag():
+        return types.TrajectoryWithRew(obs=rng.standard_normal((L + 1, Do)).astype(np.float32),
+                                       acts=rng.uniform(-1, 1, (L, Da)).astype(np.float32), infos=None, terminal=False,
+                                       rews=rng.standard_normal(L).astype(np.float32))
+
+    ds = pc.PreferenceDataset()
+    ds.push([(frag(), frag()) for _ in range(P)], (rng.random(P) < 0.5).astype(np.float32))
+    th.manual_seed(3)
+    members = [reward_nets.BasicRewardNet(obs_space, act_space, hid_sizes=(32, 32)) for _ in range(3)]
+    ens = reward_nets.RewardEnsemble(obs_space, act_space, members)
+    pm = pc.PreferenceModel(ens)
+    pm._pool = pc.FragmentPool(Do, Da, False, "cpu")
+    et = pc.EnsembleTrainer(pm, pc.CrossEntropyRewardLoss(), rng=np.random.default_rng(1), batch_size=4, epochs=2, lr=1e-2)
+    if world_rank is not None:
+        et.set_distributed()
+    th.manual_seed(11)
+    et.train(ds)
+    et.train(ds, epoch_multiplier=1.5)
+    probe = float(th.rand(1))  # torch's global RNG must end in the same state on every rank
+    return ([m.mlp.dense0.weight.detach().clone() for m in members],
+            [float(t.optim.state[m.mlp.dense0.weight]["step"]) for t, m in zip(et.member_trainers, members)],
+            [t.optim.state[m.mlp.dense0.weight]["exp_avg"].detach().clone() for t, m in zip(et.member_trainers, members)], probe)
+
+
+def _ensemble_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+
+    sys.path.insert(0, ROOT)
+    _install_cpu_stand_ins()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out[rank] = _ensemble_run(world_rank=rank)
+    dist.destroy_process_group()
+
+
+def _ensemble_single(_i, out):
+    sys.path.insert(0, ROOT)
+    _install_cpu_stand_ins()
+    out["single"] = _ensemble_run()
+
+
+def test_member_parallel_ensemble_equals_single_process_world2_gloo():
+    """EnsembleTrainer.set_distributed(): member k on rank k % 2, same bagging subsets / minibatch orders as the
+    single-process run, owners broadcast parameters + AdamW state: every rank ends bit-identical to the single process."""
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_ensemble_single, args=(out,), nprocs=1, join=True)
+    mp.spawn(_ensemble_worker, args=(world, port, out), nprocs=world, join=True)
+    w0, s0, m0, p0 = out["single"]
+    assert len({float(w.sum()) for w in w0}) == 3 and all(s > 0 for s in s0)  # the members really trained, differently
+    for r in range(world):
+        w, s, m, p = out[r]
+        assert s == s0 and p == p0, (r, s, s0, p, p0)
+        for a, b in zip(w, w0):
+            assert th.equal(a, b), f"rank {r}: member parameters differ from the single-process run"
+        for a, b in zip(m, m0):
+            assert th.equal(a, b), f"rank {r}: AdamW moments differ from the single-process run"
