@@ -74,7 +74,7 @@ for _c in CONFIGS.values():
     _c.setdefault("n_expert_episodes", 60)
     _c.setdefault("seed", 0)
 
-PPO_DRAM_BYTES_NCU = 599552 + 0        # bytes per launch, profiles/ncu_ppo_r01m_selected.csv (read + write), hc config
+PPO_DRAM_BYTES_NCU = 611584 + 0        # bytes per launch, profiles/ncu_ppo_r02c_selected.csv (read + write), hc config
 DISC_TC_NCU = dict(source="profiles/ncu_disc_tc_r02_selected.csv (k_disc_fwdbwd_tc<8>, 2^20 rows, --set full)",
                    dram_bytes=96830208 + 4711424, tensor_pipe_pct_of_elapsed=37.4, issue_active_pct=53.4)
 
@@ -672,7 +672,8 @@ def main():
                           "minibatch steps)",
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at the hc
-                # configuration (profiles/ncu_ppo_r01m_selected.csv): the rollout table stays in L2
+                # configuration (profiles/ncu_ppo_r02c_selected.csv, the kernel as it is at the end of round 2): the rollout
+                # table stays in L2
                 "traffic": PPO_DRAM_BYTES_NCU if args.config == "hc" else None,
                 "peak_source": peak_src, "ms_per_launch": ms_ppo, "share_of_step": ms_ppo / (ms / K),
                 "algorithmic_bytes_per_launch": ppo_bytes,
