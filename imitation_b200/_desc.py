@@ -3,7 +3,7 @@
 Parameter layout = torch nn.Linear order (weight [out][in] row-major, then bias) so that
 nn.Parameters can alias slices of the flat vectors the kernels read.
 """
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 

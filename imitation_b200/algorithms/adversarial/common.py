@@ -17,7 +17,7 @@ the reference's NumPy/torch RNG streams for bit-exact index parity), `seed`.
 import abc
 import contextlib
 import itertools
-from typing import Callable, Dict, Iterator, Mapping, Optional, Type
+from typing import Callable, Mapping, Optional, Type
 
 import numpy as np
 import torch as th
@@ -25,9 +25,8 @@ from torch.nn import functional as F
 
 from ... import _desc, _lib
 from ...data import buffer, types, wrappers
-from ...policies import base as policies
 from ...rewards import reward_nets, reward_wrapper
-from ...util import logger, networks
+from ...util import networks
 from .. import base
 
 STAT_KEYS = ("disc_loss", "disc_acc", "disc_acc_expert", "disc_acc_gen", "disc_entropy",

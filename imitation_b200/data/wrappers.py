@@ -12,7 +12,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import torch as th
 
-from .. import _desc, _lib
+from .. import _desc
 from . import buffer as buffer_mod
 from . import types
 

@@ -5,8 +5,6 @@ fixed horizon with SB3-VecEnv auto-reset semantics; state lives SoA [d_obs][E] i
 stepped by csrc/imb_rollout.cu.  One slice of the global env index space per rank
 (`env_id_offset`) so that N GPUs roll out disjoint environments.
 """
-from typing import Optional
-
 import numpy as np
 import torch as th
 

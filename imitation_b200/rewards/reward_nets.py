@@ -16,7 +16,7 @@ raises.
 """
 import abc
 import collections
-from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Type
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Type
 
 import numpy as np
 import torch as th

@@ -14,7 +14,6 @@ import json
 import os
 import sys
 
-import numpy as np
 import torch as th
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
