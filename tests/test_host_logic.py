@@ -336,3 +336,66 @@ def test_member_parallel_ensemble_equals_single_process_world2_gloo():
             assert th.equal(a, b), f"rank {r}: member parameters differ from the single-process run"
         for a, b in zip(m, m0):
             assert th.equal(a, b), f"rank {r}: AdamW moments differ from the single-process run"
+
+
+def _fused_bookkeeping(_i, out):
+    sys.path.insert(0, ROOT)
+    _install_cpu_stand_ins()
+    from imitation_b200 import _lib, spaces
+    from imitation_b200.algorithms import preference_comparisons as pc
+    from imitation_b200.data import types
+    from imitation_b200.rewards import reward_nets
+
+    calls = []
+    for name in ("gather_rows", "reward_forward", "pref_loss", "disc_fwd_bwd", "disc_reduce", "disc_reduce_adam", "disc_adam"):
+        orig = getattr(_lib, name)
+        setattr(_lib, name, (lambda nm, f: (lambda *a, **k: (calls.append(nm), f(*a, **k))[1]))(name, orig))
+    Do, Da, L, P = 5, 2, 4, 10
+    rng = np.random.default_rng(0)
+    obs_space, act_space = spaces.Box(-np.inf, np.inf, (Do,)), spaces.Box(-1.0, 1.0, (Da,))
+
+    def frag(n=L):
+        return types.TrajectoryWithRew(obs=rng.standard_normal((n + 1, Do)).astype(np.float32),
+                                       acts=rng.uniform(-1, 1, (n, Da)).astype(np.float32), infos=None, terminal=False,
+                                       rews=rng.standard_normal(n).astype(np.float32))
+
+    ds = pc.PreferenceDataset()
+    ds.push([(frag(), frag()) for _ in range(P)], (rng.random(P) < 0.5).astype(np.float32))
+    net = reward_nets.BasicRewardNet(obs_space, act_space, hid_sizes=(32, 32))
+    pm = pc.PreferenceModel(net, noise_prob=0.05, discount_factor=0.97)
+    pm._pool = pc.FragmentPool(Do, Da, False, "cpu")
+    tr = pc.BasicRewardTrainer(pm, pc.CrossEntropyRewardLoss(), rng=np.random.default_rng(5), batch_size=6, minibatch_size=3,
+                               epochs=3, lr=2e-3)
+    res = {"target": tr._fused_target(ds) is not None}
+    tr.train(ds)
+    res["calls"] = {c: calls.count(c) for c in sorted(set(calls))}
+    res["step"] = float(tr.optim.state[net.mlp.dense0.weight]["step"])
+    res["aliased"] = (tr.optim.state[net.mlp.dense0.weight]["exp_avg"].data_ptr() == tr._fused_opt["m"].data_ptr())
+    res["keys"] = sorted(k for k in tr.logger.name_to_value if k.startswith("mean/reward/epoch-2"))
+    # outside the envelope: ragged fragments, another optimiser, the switch -> the autograd path is chosen
+    ragged = pc.PreferenceDataset()
+    ragged.push([(frag(), frag(L + 1))], np.ones(1, np.float32))
+    res["ragged"] = tr._fused_target(ragged) is None
+    tr.optim = th.optim.Adam(net.parameters())
+    res["other_optimizer"] = tr._fused_target(ds) is None
+    tr.optim = th.optim.AdamW(net.parameters())
+    tr.use_fused_step = False
+    res["switch"] = tr._fused_target(ds) is None
+    out["r"] = res
+
+
+def test_fused_reward_trainer_bookkeeping_with_stand_in_kernels():
+    """The device-only reward-training step (algorithms/preference_comparisons.BasicRewardTrainer._train_fused), host side:
+    10 pairs, minibatch 3, batch 6, 3 epochs -> per epoch minibatches of 3, 3, 3, 1 pairs = one full-batch optimiser step
+    (reduce + AdamW in one launch), then an incomplete batch stepped at the end of the epoch; the torch optimiser's state
+    aliases the flat moments and counts the steps; the envelope checks fall back to the autograd path."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fused_bookkeeping, args=(out,), nprocs=1, join=True)
+    r = out["r"]
+    assert r["target"] and r["ragged"] and r["other_optimizer"] and r["switch"]
+    assert r["calls"] == {"disc_adam": 3, "disc_fwd_bwd": 12, "disc_reduce": 9, "disc_reduce_adam": 3, "gather_rows": 12,
+                          "pref_loss": 24, "reward_forward": 12}
+    assert r["step"] == 6.0 and r["aliased"]
+    assert r["keys"] == ["mean/reward/epoch-2/train/accuracy", "mean/reward/epoch-2/train/gt_reward_loss",
+                         "mean/reward/epoch-2/train/loss"]
