@@ -433,6 +433,7 @@ def main():
         spec = importlib.util.spec_from_file_location("pref_bench", os.path.join(ROOT, "profiles", "pref_bench.py"))
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
+        args.hbm_peak, args.hbm_peak_source = peaks()
         return mod.main(args)
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

@@ -124,6 +124,8 @@ def main(args):
     v = K * P * M / (ms / 1e3)  # whole job: the ONE ensemble all ranks train together
     rows = K * M * 2 * P * L
     config["fused_step"] = all("_fused_opt" in t.__dict__ for t in trainer.member_trainers)
+    ach = rows * (2 * 4 * (Do + Da) + 8) / (ms / 1e3) / 1e9
+    peak, peak_src = getattr(args, "hbm_peak", None), getattr(args, "hbm_peak_source", None)
     h2d = M * P * 8  # per epoch and member: the minibatches' item indices (int64); the pool uploads happened in warm-up
     if rank == 0:
         print(json.dumps({"metric": "preference reward-model training, fragment-pair evaluations/sec", "value": v,
@@ -141,8 +143,11 @@ def main(args):
                           "gpu_launches": launches,
                           "roofline": {"kernel": "k_disc_fwdbwd / k_reward_fwd over 2 * 256 * 100 = 51 200 transition rows per "
                                                  "minibatch", "bound": "hbm",
-                                       "achieved": rows * (4 * (Do + Da) + 4) / (ms / 1e3) / 1e9, "peak": None, "unit": "GB/s",
-                                       "frac": None, "traffic": None,
+                                       "achieved": ach, "peak": peak, "unit": "GB/s",
+                                       "frac": (ach / peak) if peak else None, "traffic": None, "peak_source": peak_src,
+                                       "algorithmic_bytes": "per transition row: 4 (Do + Da) read by the forward + the same "
+                                                            "again by the fused forward/backward + 4 reward + 4 gradient "
+                                                            "= 2 x 56 + 8 = 120 B at 11/3",
                                        "note": "fragments are device-resident after their first use (FragmentPool) and a minibatch "
                                                "is ~10 launches without a host round trip; what remains is the host's launch "
                                                "rate (the members are trained one after the other like the reference's); "
