@@ -309,8 +309,9 @@ int imb_disc_reduce_adam(const imb_disc_desc* d, const imb_adam* opt, float* par
  * CrossEntropyRewardLoss (:1043-1090): loss = mean_P BCE(p, pref) with torch's log clamp at -100, accuracy = mean((p > .5)
  * == (pref > .5)).  Outputs (each optional): grad_rews[2][P][L] = grad_scale * d loss / d rews (autograd's result, incl.
  * the zero gradient of clipped pairs and torch's BCE backward denominator clamp 1e-12) -- the upstream gradient for
- * imb_disc_fwd_bwd(grad_out=...); probs_out[P]; stats_acc[0] += loss, [1] += accuracy, [2] += 1 (so an epoch's per-minibatch
- * means are read back once).  The reference computes this with a Python loop over the pairs (:441-454). */
+ * imb_disc_fwd_bwd(grad_out=...); probs_out[P]; statistics slot `stats_slot` = the four floats at stats_acc + 4 * stats_slot:
+ * [0] += loss, [1] += accuracy, [2] += 1 (so the per-minibatch means of an epoch -- one slot per epoch and per quantity
+ * group -- are read back once).  The reference computes this with a Python loop over the pairs (:441-454). */
 int imb_pref_loss(const float* rews, int64_t n_pairs, int32_t frag_len, const float* prefs, float noise_prob,
                   float discount, float threshold, float grad_scale, float* grad_rews, float* probs_out,
                   float* stats_acc, int32_t stats_slot, void* stream);
