@@ -1,27 +1,34 @@
 """Demonstration ingest: trajectories on disk -> `types.Trajectory[WithRew]` -> (via `flatten_trajectories`) the
 device-resident expert table the discriminator samples from.
 
-Mirror of imitation.data.serialize (serialize.py:27-93): `load` understands the legacy compressed `.npz` layout
-(concatenated `obs`/`acts`/`infos`/`rews` split at `indices`, one extra observation per trajectory), the older
-pickle of a trajectory sequence, and -- when the optional `datasets` package is importable -- a HuggingFace
-datasets directory.  `save` writes the `.npz` layout (readable by the reference's `load`); the reference itself
-writes a datasets directory, which needs the `datasets` package that this offline image does not ship.
+Mirror of imitation.data.serialize (serialize.py:15-93): `save` writes a HuggingFace `datasets` directory like the
+reference's (one row per trajectory, `huggingface_utils.trajectories_to_dataset`) -- or, for a path ending in `.npz`,
+the legacy compressed layout the reference still reads; `load` understands the datasets directory, the legacy `.npz`
+layout (concatenated `obs`/`acts`/`infos`/`rews` split at `indices`, one extra observation per trajectory) and the older
+pickle of a trajectory sequence.
 """
+import logging
 import os
 import warnings
 from typing import Mapping, Sequence
 
 import numpy as np
 
+from . import huggingface_utils
 from .types import Trajectory, TrajectoryWithRew
 
 
 def save(path, trajectories: Sequence[Trajectory]) -> None:
-    """Save trajectories in the `.npz` layout `load` (and the reference's `load`) reads."""
+    """Save a sequence of trajectories: a HuggingFace datasets directory (serialize.py:15-24), or the legacy `.npz`
+    layout when `path` ends in `.npz`."""
+    path = os.fspath(path)
+    if not path.endswith(".npz"):
+        huggingface_utils.trajectories_to_dataset(trajectories).save_to_disk(path)
+        logging.info(f"Dumped demonstrations to {path}.")
+        return
     trajectories = list(trajectories)
     if not trajectories:
         raise ValueError("no trajectories to save")
-    path = os.fspath(path)
     os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
     lens = np.asarray([len(t) for t in trajectories])
     out = dict(obs=np.concatenate([t.obs for t in trajectories]), acts=np.concatenate([t.acts for t in trajectories]),
@@ -38,11 +45,14 @@ def load(path) -> Sequence[Trajectory]:
     path = os.fspath(path)
     if os.path.isdir(path):  # huggingface datasets format (serialize.py:37-45)
         try:
-            import datasets  # noqa: F401
+            import datasets
         except ImportError as e:
             raise ImportError("loading a HuggingFace-datasets demonstration directory needs the `datasets` package; "
                               "convert it to the .npz layout with the reference's tooling first") from e
-        return _load_hf(path)
+        dataset = datasets.load_from_disk(path)
+        if not isinstance(dataset, datasets.Dataset):
+            raise ValueError(f"Expected to load a `datasets.Dataset` but got {type(dataset)}")
+        return huggingface_utils.TrajectoryDatasetSequence(dataset)
     data = np.load(path, allow_pickle=True)  # works for both .npz and .pkl
     if isinstance(data, Sequence):  # pickle format
         warnings.warn("Loading old pickle version of Trajectories", DeprecationWarning)
@@ -64,20 +74,6 @@ def load(path) -> Sequence[Trajectory]:
         return out
     raise ValueError("Expected either an .npz file or a pickled sequence of trajectories; "
                      f"got a pickled object of type {type(data).__name__}")
-
-
-def _load_hf(path) -> Sequence[Trajectory]:
-    import datasets
-
-    ds = datasets.load_from_disk(str(path))
-    out = []
-    for row in ds:
-        kw = dict(obs=np.asarray(row["obs"]), acts=np.asarray(row["acts"]), infos=None, terminal=bool(row["terminal"]))
-        if "rews" in row:
-            out.append(TrajectoryWithRew(rews=np.asarray(row["rews"], dtype=np.float32), **kw))
-        else:
-            out.append(Trajectory(**kw))
-    return out
 
 
 def load_with_rewards(path) -> Sequence[TrajectoryWithRew]:

@@ -399,3 +399,57 @@ def test_fused_reward_trainer_bookkeeping_with_stand_in_kernels():
     assert r["step"] == 6.0 and r["aliased"]
     assert r["keys"] == ["mean/reward/epoch-2/train/accuracy", "mean/reward/epoch-2/train/gt_reward_loss",
                          "mean/reward/epoch-2/train/loss"]
+
+
+def test_demo_ingest_huggingface_directory_round_trip(tmp_path):
+    """data/serialize + data/huggingface_utils: `save` writes the reference's on-disk format (a HuggingFace datasets
+    directory, one row per trajectory: serialize.py:15-24, huggingface_utils.py:91-157), `load` returns a lazy sequence of
+    trajectories over it (serialize.py:37-45); Box and Discrete actions, infos, missing infos, rewards / no rewards,
+    slicing, and the error paths of the reference."""
+    datasets = pytest.importorskip("datasets")
+    from imitation_b200.data import huggingface_utils, serialize, types
+
+    rng = np.random.default_rng(0)
+
+    def traj(n, term, discrete, infos, rew=True):
+        kw = dict(obs=rng.standard_normal((n + 1, 4)).astype(np.float32),
+                  acts=rng.integers(0, 2, n) if discrete else rng.uniform(-1, 1, (n, 3)).astype(np.float32),
+                  infos=np.array([{"t": i, "tag": "x"} for i in range(n)]) if infos else None, terminal=term)
+        return types.TrajectoryWithRew(rews=rng.standard_normal(n).astype(np.float32), **kw) if rew else types.Trajectory(**kw)
+
+    for discrete in (True, False):
+        trajs = [traj(5, True, discrete, True), traj(3, False, discrete, False), traj(7, True, discrete, True)]
+        p = tmp_path / f"demos_{int(discrete)}"
+        serialize.save(p, trajs)
+        assert sorted(os.listdir(p)) == ["data-00000-of-00001.arrow", "dataset_info.json", "state.json"]
+        raw = datasets.load_from_disk(str(p))  # the reference's schema: one row per trajectory
+        assert set(raw.features) == {"obs", "acts", "infos", "terminal", "rews"} and len(raw) == 3
+        assert raw[0]["infos"][2] in ('{"t": 2, "tag": "x"}', '{"tag": "x", "t": 2}') and raw[1]["infos"] == ["{}"] * 3
+        back = serialize.load_with_rewards(p)
+        assert isinstance(back, huggingface_utils.TrajectoryDatasetSequence) and len(back) == 3
+        for a, b in zip(trajs, back):
+            assert type(b) is types.TrajectoryWithRew and b.terminal == a.terminal
+            np.testing.assert_array_equal(b.obs, a.obs)
+            assert b.obs.dtype == np.float32
+            np.testing.assert_array_equal(b.acts, a.acts)
+            np.testing.assert_array_equal(b.rews, a.rews)
+            assert list(b.infos) == (list(a.infos) if a.infos is not None else [{}] * len(a))
+        assert [len(t) for t in back[1:]] == [3, 7] and len(back[-1]) == 7
+        flat = types.flatten_trajectories(list(back))  # what the device expert table is built from
+        assert len(flat) == 15 and flat.dones.sum() == 2 and flat.obs.dtype == np.float32
+        np.testing.assert_array_equal(flat.next_obs[:5], trajs[0].obs[1:])
+        arrays = types.as_transition_arrays(back)  # what GAIL / AIRL(demonstrations=<loaded sequence>) uploads
+        assert set(arrays) == {"obs", "acts", "next_obs", "dones"} and arrays["obs"].shape == (15, 4)
+        # saving the loaded sequence again writes the same dataset
+        q = tmp_path / f"again_{int(discrete)}"
+        serialize.save(q, back)
+        np.testing.assert_array_equal(serialize.load(q)[2].obs, trajs[2].obs)
+    # without rewards: plain trajectories; load_with_rewards refuses them; mixed sequences cannot be saved
+    plain = [traj(4, True, False, False, rew=False), traj(2, False, False, True, rew=False)]
+    serialize.save(tmp_path / "plain", plain)
+    got = serialize.load(tmp_path / "plain")
+    assert type(got[0]) is types.Trajectory and len(got[1]) == 2
+    with pytest.raises(ValueError, match="TrajectoryWithRew"):
+        serialize.load_with_rewards(tmp_path / "plain")
+    with pytest.raises(ValueError, match="rewards but not all"):
+        serialize.save(tmp_path / "mixed", [plain[0], traj(2, True, False, False)])
