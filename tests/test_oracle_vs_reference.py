@@ -61,3 +61,46 @@ def test_reference_modules_used_are_the_real_ones():
     from imitation.algorithms.adversarial import common
 
     assert common.__file__ == "/root/reference/src/imitation/algorithms/adversarial/common.py"
+
+
+def test_huggingface_demonstration_format_is_interchangeable_with_the_reference(tmp_path):
+    """f3: a demonstration directory written by the REFERENCE's `data.serialize.save` (its `huggingface_utils` over the real
+    `datasets` package; `jsonpickle` through the names-only shim) is read by `imitation_b200.data.serialize.load`, and a
+    directory written by this repo's `save` is read by the reference's `load` -- same trajectories both ways."""
+    pytest.importorskip("datasets")
+    refimport.load()
+    from imitation.data import serialize as ref_serialize
+    from imitation.data import types as ref_types
+
+    from imitation_b200.data import serialize, types
+
+    rng = np.random.default_rng(3)
+    spec = [(6, True, [{"step": i} for i in range(6)]), (2, False, None), (4, True, [{} for _ in range(4)])]
+
+    def make(T, discrete):
+        out = []
+        for n, term, infos in spec:
+            out.append(T.TrajectoryWithRew(obs=rng.standard_normal((n + 1, 5)).astype(np.float32),
+                                           acts=rng.integers(0, 3, n) if discrete else rng.uniform(-1, 1, (n, 2)).astype(np.float32),
+                                           infos=None if infos is None else np.array(infos), terminal=term,
+                                           rews=rng.standard_normal(n).astype(np.float32)))
+        return out
+
+    def same(a, b):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(np.asarray(x.obs, dtype=np.float32), np.asarray(y.obs, dtype=np.float32))
+            np.testing.assert_array_equal(np.asarray(x.acts), np.asarray(y.acts))
+            np.testing.assert_array_equal(np.asarray(x.rews, dtype=np.float32), np.asarray(y.rews, dtype=np.float32))
+            assert bool(x.terminal) == bool(y.terminal)
+            xi = [{}] * len(x.acts) if x.infos is None else list(x.infos)
+            yi = [{}] * len(y.acts) if y.infos is None else list(y.infos)
+            assert xi == yi
+
+    for discrete in (False, True):
+        theirs = make(ref_types, discrete)
+        ref_serialize.save(tmp_path / f"ref_{int(discrete)}", theirs)          # the reference writes ...
+        same(theirs, serialize.load_with_rewards(tmp_path / f"ref_{int(discrete)}"))  # ... this repo reads
+        ours = make(types, discrete)
+        serialize.save(tmp_path / f"ours_{int(discrete)}", ours)              # this repo writes ...
+        same(ours, ref_serialize.load_with_rewards(tmp_path / f"ours_{int(discrete)}"))  # ... the reference reads
