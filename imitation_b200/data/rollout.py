@@ -106,10 +106,18 @@ def generate_trajectories(policy, venv, sample_until: GenTrajTerminationFn, rng:
 
 
 def rollout_stats(trajectories: Sequence[types.TrajectoryWithRew]) -> Mapping[str, float]:
+    """n_traj plus min / mean / std / max of the episode returns (`return_*`, from the trajectories' rewards), of the
+    lengths (`len_*`) and -- for trajectories whose last info carries a Monitor record -- of the Monitor-captured returns
+    (`monitor_return_*`, `monitor_return_len` of them); data/rollout.py:509-560."""
     assert len(trajectories) > 0
     out: Dict[str, float] = {"n_traj": len(trajectories)}
     desc = {"return": np.asarray([sum(t.rews) for t in trajectories]),
             "len": np.asarray([len(t.rews) for t in trajectories])}
+    monitored = [t.infos[-1].get("episode", {}).get("r") for t in trajectories if t.infos is not None]
+    monitored = [r for r in monitored if r is not None]
+    if monitored:  # (possibly fewer than n_traj: trajectories without infos are skipped)
+        desc["monitor_return"] = np.asarray(monitored)
+        out["monitor_return_len"] = len(monitored)
     for name, vals in desc.items():
         for stat in ("min", "mean", "std", "max"):
             out[f"{name}_{stat}"] = getattr(np, stat)(vals).item()

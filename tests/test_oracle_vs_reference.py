@@ -104,3 +104,53 @@ def test_huggingface_demonstration_format_is_interchangeable_with_the_reference(
         ours = make(types, discrete)
         serialize.save(tmp_path / f"ours_{int(discrete)}", ours)              # this repo writes ...
         same(ours, ref_serialize.load_with_rewards(tmp_path / f"ours_{int(discrete)}"))  # ... the reference reads
+
+
+def test_host_side_rollout_helpers_agree_with_the_reference():
+    """f4: `rollout_stats` (with and without Monitor infos), `discounted_sum`, the sample-until predicates and
+    `flatten_trajectories_with_rew` of imitation_b200.data.rollout against the reference's own functions
+    (data/rollout.py:193-286, 509-621, 728-745) on the same random trajectories."""
+    refimport.load()
+    from imitation.data import rollout as ref_rollout
+    from imitation.data import types as ref_types
+
+    from imitation_b200.data import rollout, types
+
+    rng = np.random.default_rng(5)
+    lens = [4, 9, 1, 6, 6]
+
+    def make(T, monitor):
+        out = []
+        for k, n in enumerate(lens):
+            rews = rng.standard_normal(n).astype(np.float32)
+            infos = None
+            if monitor and k != 2:  # one trajectory without infos: it is skipped by the Monitor statistics
+                infos = np.array([{} for _ in range(n - 1)] + [{"episode": {"r": float(rews.sum()) + 0.5 * k, "l": n}}])
+            out.append(T.TrajectoryWithRew(obs=rng.standard_normal((n + 1, 3)).astype(np.float32), acts=rng.integers(0, 2, n),
+                                           infos=infos, terminal=bool(k % 2), rews=rews))
+        return out
+
+    for monitor in (False, True):
+        state = rng.bit_generator.state
+        theirs = make(ref_types, monitor)
+        rng.bit_generator.state = state
+        ours = make(types, monitor)
+        want, got = ref_rollout.rollout_stats(theirs), rollout.rollout_stats(ours)
+        assert set(got) == set(want) and ("monitor_return_mean" in want) == monitor
+        for k in want:
+            assert got[k] == want[k] and type(got[k]) is type(want[k]), k
+        fw, fg = ref_rollout.flatten_trajectories_with_rew(theirs), rollout.flatten_trajectories_with_rew(ours)
+        for field in ("obs", "acts", "next_obs", "dones", "rews"):
+            np.testing.assert_array_equal(getattr(fg, field), getattr(fw, field), err_msg=field)
+        for kw in (dict(min_timesteps=20), dict(min_episodes=5), dict(min_timesteps=27, min_episodes=2), dict(min_episodes=6)):
+            assert rollout.make_sample_until(**kw)(ours) == ref_rollout.make_sample_until(**kw)(theirs), kw
+    for kw in (dict(), dict(min_timesteps=0), dict(min_episodes=-1)):
+        with pytest.raises(ValueError) as e1:
+            ref_rollout.make_sample_until(**kw)
+        with pytest.raises(ValueError) as e2:
+            rollout.make_sample_until(**kw)
+        assert str(e1.value) == str(e2.value)
+    arr = rng.standard_normal((7, 3))
+    for gamma in (1.0, 0.9):
+        np.testing.assert_allclose(rollout.discounted_sum(arr, gamma), ref_rollout.discounted_sum(arr, gamma), rtol=1e-12)
+        np.testing.assert_allclose(rollout.discounted_sum(arr[:, 0], gamma), ref_rollout.discounted_sum(arr[:, 0], gamma), rtol=1e-12)
