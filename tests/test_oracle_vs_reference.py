@@ -154,3 +154,36 @@ def test_host_side_rollout_helpers_agree_with_the_reference():
     for gamma in (1.0, 0.9):
         np.testing.assert_allclose(rollout.discounted_sum(arr, gamma), ref_rollout.discounted_sum(arr, gamma), rtol=1e-12)
         np.testing.assert_allclose(rollout.discounted_sum(arr[:, 0], gamma), ref_rollout.discounted_sum(arr[:, 0], gamma), rtol=1e-12)
+
+
+def test_fixed_horizon_check_agrees_with_the_reference():
+    """a21: BaseImitationAlgorithm._check_fixed_horizon (algorithms/base.py:69-108): same accept / reject decisions, same
+    remembered horizon and the same error text as the reference's class over sequences of episode lengths."""
+    refimport.load()
+    from imitation.algorithms import base as ref_base
+
+    from imitation_b200.algorithms import base
+
+    class Ours(base.BaseImitationAlgorithm):
+        pass
+
+    class Theirs(ref_base.BaseImitationAlgorithm):
+        pass
+
+    scripts = [[[5, 5], [5], [], [6]], [[3], [3, 3, 4]], [[], [7], [7, 7], [7]], [[2, 9]]]
+    for allow in (False, True):
+        for script in scripts:
+            a, b = Ours(allow_variable_horizon=allow), Theirs(allow_variable_horizon=allow)
+            for horizons in script:
+                errs = []
+                for algo in (a, b):
+                    try:
+                        algo._check_fixed_horizon(horizons)
+                        errs.append(None)
+                    except ValueError as e:
+                        errs.append(str(e))
+                assert (errs[0] is None) == (errs[1] is None), (allow, script, horizons)
+                if errs[0] is not None:
+                    assert errs[0] == errs[1]
+                    break
+                assert a._horizon == b._horizon
