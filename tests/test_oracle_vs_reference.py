@@ -187,3 +187,35 @@ def test_fixed_horizon_check_agrees_with_the_reference():
                     assert errs[0] == errs[1]
                     break
                 assert a._horizon == b._horizon
+
+
+def test_trajectory_and_transition_validation_agrees_with_the_reference():
+    """data/types.py:61-330: the same inputs are rejected with the same messages by this repo's Trajectory / TrajectoryWithRew /
+    Transitions and by the reference's."""
+    refimport.load()
+    from imitation.data import types as R
+
+    from imitation_b200.data import types as M
+
+    z = np.zeros
+    traj = {"len": dict(obs=z((3, 2)), acts=z(3), infos=None, terminal=True),
+            "infos": dict(obs=z((4, 2)), acts=z(3), infos=np.array([{}] * 2), terminal=True),
+            "empty": dict(obs=z((1, 2)), acts=z(0), infos=None, terminal=True)}
+    rews = {"shape": z((3, 1), np.float32), "dtype": z(3, np.int64)}
+    ok = dict(obs=z((3, 2)), acts=z(3), infos=np.array([{}] * 3), next_obs=z((3, 2)), dones=z(3, bool))
+    trans = {"next_obs": {**ok, "next_obs": z((3, 3))}, "dones_dtype": {**ok, "dones": z(3)},
+             "dones_shape": {**ok, "dones": z((3, 1), bool)}, "acts": {**ok, "acts": z(2)}, "infos": {**ok, "infos": np.array([{}] * 2)}}
+
+    def message(fn):
+        with pytest.raises(ValueError) as e:
+            fn()
+        return str(e.value)
+
+    for name, kw in traj.items():
+        assert message(lambda: M.Trajectory(**kw)) == message(lambda: R.Trajectory(**kw)), name
+    for name, r in rews.items():
+        kw = dict(obs=z((4, 2)), acts=z(3), infos=None, terminal=True, rews=r)
+        assert message(lambda: M.TrajectoryWithRew(**kw)) == message(lambda: R.TrajectoryWithRew(**kw)), name
+    for name, kw in trans.items():
+        assert message(lambda: M.Transitions(**kw)) == message(lambda: R.Transitions(**kw)), name
+    assert len(M.Transitions(**ok)) == len(R.Transitions(**ok)) == 3
