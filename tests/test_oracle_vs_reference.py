@@ -219,3 +219,33 @@ def test_trajectory_and_transition_validation_agrees_with_the_reference():
     for name, kw in trans.items():
         assert message(lambda: M.Transitions(**kw)) == message(lambda: R.Transitions(**kw)), name
     assert len(M.Transitions(**ok)) == len(R.Transitions(**ok)) == 3
+
+
+def test_comparison_schedule_helpers_agree_with_the_reference():
+    """f1: the per-iteration comparison counts of PreferenceComparisons.train (preference_comparisons.py:1622-1636) --
+    `util.oric` rounding of the query-schedule shares -- and the named query schedules (:1465-1479)."""
+    refimport.load()
+    from imitation.algorithms import preference_comparisons as ref_pc
+    from imitation.util import util as ref_util
+
+    from imitation_b200.algorithms import preference_comparisons as pc
+
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        n, total = int(rng.integers(1, 12)), int(rng.integers(0, 300))
+        v = rng.random(n) + 1e-3
+        x = v / v.sum() * total
+        np.testing.assert_array_equal(pc._round_keep_sum(x), ref_util.oric(x))
+    assert set(pc.QUERY_SCHEDULES) == set(ref_pc.QUERY_SCHEDULES)
+    for name, fn in pc.QUERY_SCHEDULES.items():
+        for t in np.linspace(0, 1, 7):
+            assert fn(t) == ref_pc.QUERY_SCHEDULES[name](t), (name, t)
+    # the whole schedule of a run: initial comparisons + oric(shares), as PreferenceComparisons.train computes it
+    for name in pc.QUERY_SCHEDULES:
+        for total, iters, frac in ((500, 5, 0.1), (77, 3, 0.25), (1000, 12, 0.1)):
+            initial = int(total * frac)
+            vec = np.array([pc.QUERY_SCHEDULES[name](t) for t in np.linspace(0, 1, iters)])
+            ours = [initial] + [int(v) for v in pc._round_keep_sum(vec / vec.sum() * (total - initial))]
+            rvec = np.array([ref_pc.QUERY_SCHEDULES[name](t) for t in np.linspace(0, 1, iters)])
+            theirs = [initial] + ref_util.oric(rvec / rvec.sum() * (total - initial)).tolist()
+            assert ours == theirs and sum(ours) == total
