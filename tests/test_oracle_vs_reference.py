@@ -249,3 +249,29 @@ def test_comparison_schedule_helpers_agree_with_the_reference():
             rvec = np.array([ref_pc.QUERY_SCHEDULES[name](t) for t in np.linspace(0, 1, iters)])
             theirs = [initial] + ref_util.oric(rvec / rvec.sum() * (total - initial)).tolist()
             assert ours == theirs and sum(ours) == total
+
+
+def test_reward_net_preprocess_and_registry_agree_with_the_reference():
+    """a8 / f4: `RewardNet.preprocess` (reward_nets.py:74-118: float conversion, one-hot Discrete actions) on CPU tensors and
+    the registered reward-loader names of rewards/serialize.py:230-260 against the reference's."""
+    refimport.load()
+    import gymnasium
+    import torch as th
+    from imitation.rewards import reward_nets as ref_rn
+    from imitation.rewards import serialize as ref_ser
+
+    from imitation_b200 import spaces
+    from imitation_b200.rewards import reward_nets, serialize
+
+    assert sorted(serialize.reward_registry.keys()) == sorted(ref_ser.reward_registry.keys())
+    rng = np.random.default_rng(0)
+    for discrete in (True, False):
+        theirs = ref_rn.BasicRewardNet(gymnasium.spaces.Box(-1, 1, (4,)),
+                                       gymnasium.spaces.Discrete(3) if discrete else gymnasium.spaces.Box(-1, 1, (2,)))
+        ours = reward_nets.BasicRewardNet(spaces.Box(-1, 1, (4,)), spaces.Discrete(3) if discrete else spaces.Box(-1, 1, (2,)))
+        obs, nobs = rng.standard_normal((6, 4)), rng.standard_normal((6, 4)).astype(np.float32)
+        acts = rng.integers(0, 3, 6) if discrete else rng.uniform(-1, 1, (6, 2))
+        done = rng.random(6) < 0.5
+        for a, b in zip(ours.preprocess(obs, acts, nobs, done), theirs.preprocess(obs, acts, nobs, done)):
+            assert a.dtype == b.dtype and th.equal(a, b)
+        assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
