@@ -275,3 +275,53 @@ def test_reward_net_preprocess_and_registry_agree_with_the_reference():
         for a, b in zip(ours.preprocess(obs, acts, nobs, done), theirs.preprocess(obs, acts, nobs, done)):
             assert a.dtype == b.dtype and th.equal(a, b)
         assert {k: tuple(v.shape) for k, v in ours.state_dict().items()} == {k: tuple(v.shape) for k, v in theirs.state_dict().items()}
+
+
+def test_trajectory_dataset_and_preference_dataset_agree_with_the_reference(tmp_path):
+    """f1 host side: `TrajectoryDataset.sample` (preference_comparisons.py:99-124: shuffled selection with the caller's
+    generator), `PreferenceDataset` FIFO / pickling (:909-997) against the reference's classes for the same seeds."""
+    refimport.load()
+    from imitation.algorithms import preference_comparisons as ref_pc
+    from imitation.data import types as ref_types
+
+    from imitation_b200.algorithms import preference_comparisons as pc
+    from imitation_b200.data import types
+
+    lens = [5, 9, 3, 7, 7, 4, 11]
+
+    def make(T):
+        r = np.random.default_rng(1)
+        return [T.TrajectoryWithRew(obs=r.standard_normal((n + 1, 3)).astype(np.float32), acts=r.integers(0, 2, n), infos=None,
+                                    terminal=True, rews=r.standard_normal(n).astype(np.float32)) for n in lens]
+
+    theirs, ours = make(ref_types), make(types)
+    a, b = ref_pc.TrajectoryDataset(theirs, np.random.default_rng(7)), pc.TrajectoryDataset(ours, np.random.default_rng(7))
+    for steps in (10, 25, 46, 1):
+        ta, tb = a.sample(steps), b.sample(steps)
+        assert [len(t) for t in ta] == [len(t) for t in tb]
+        assert all(np.array_equal(x.obs, y.obs) for x, y in zip(ta, tb))
+    with pytest.raises(RuntimeError) as e1:
+        a.sample(100)
+    with pytest.raises(RuntimeError) as e2:
+        b.sample(100)
+    assert str(e1.value) == str(e2.value)
+    da, db = ref_pc.PreferenceDataset(max_size=3), pc.PreferenceDataset(max_size=3)
+    for d, f in ((da, theirs), (db, ours)):
+        d.push([(f[0], f[1]), (f[2], f[3])], np.array([1.0, 0.0], np.float32))
+        d.push([(f[4], f[5]), (f[6], f[0])], np.array([0.5, 1.0], np.float32))
+    assert len(da) == len(db) == 3
+    np.testing.assert_array_equal(da.preferences, db.preferences)
+    for i in range(3):
+        (xa, ya), pa = da[i]
+        (xb, yb), pb = db[i]
+        assert pa == pb and np.array_equal(xa.obs, xb.obs) and np.array_equal(ya.acts, yb.acts)
+    db.save(tmp_path / "prefs.pkl")
+    back = pc.PreferenceDataset.load(tmp_path / "prefs.pkl")
+    assert len(back) == 3 and np.array_equal(back.preferences, db.preferences) and back.max_size == 3
+    for bad in (np.array([1.0], np.float32), np.array([1.0, 0.0], np.float64)):
+        msgs = []
+        for d, f in ((da, theirs), (db, ours)):
+            with pytest.raises(ValueError) as e:
+                d.push([(f[0], f[1]), (f[2], f[3])], bad)
+            msgs.append(str(e.value))
+        assert msgs[0] == msgs[1]
