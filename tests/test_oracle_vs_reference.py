@@ -325,3 +325,36 @@ def test_trajectory_dataset_and_preference_dataset_agree_with_the_reference(tmp_
                 d.push([(f[0], f[1]), (f[2], f[3])], bad)
             msgs.append(str(e.value))
         assert msgs[0] == msgs[1]
+
+
+def test_running_norm_module_and_mode_helpers_agree_with_the_reference():
+    """a10: the torch-level `RunningNorm` module (util/networks.py:19-134; the API path and the policy's
+    NormalizeFeaturesExtractor use it on whatever device the tensors are on) is bit-identical to the reference's over a
+    sequence of training batches and in eval mode; `training()` / `evaluating()` context managers restore the mode."""
+    refimport.load()
+    import torch as th
+    from imitation.util import networks as ref_networks
+
+    from imitation_b200.util import networks
+
+    a, b = ref_networks.RunningNorm(5), networks.RunningNorm(5)
+    g = th.Generator().manual_seed(0)
+    for step in range(5):
+        x = th.randn(7 + step, 5, generator=g) * (1 + step) + step
+        assert th.equal(a(x), b(x))
+        assert int(a.count) == int(b.count) and th.equal(a.running_mean, b.running_mean) and th.equal(a.running_var, b.running_var)
+    for m in (a, b):
+        m.eval()
+    x = th.randn(3, 5, generator=g)
+    assert th.equal(a(x), b(x)) and int(a.count) == int(b.count) == 45
+    assert {k: v.dtype for k, v in a.state_dict().items()} == {k: v.dtype for k, v in b.state_dict().items()}
+    b.load_state_dict(a.state_dict())
+    for ctx, want in ((networks.training, True), (networks.evaluating, False)):
+        b.eval()
+        with ctx(b):
+            assert b.training is want
+        assert b.training is False
+        b.train()
+        with ctx(b):
+            assert b.training is want
+        assert b.training is True
