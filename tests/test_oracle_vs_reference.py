@@ -236,6 +236,8 @@ def test_comparison_schedule_helpers_agree_with_the_reference():
         v = rng.random(n) + 1e-3
         x = v / v.sum() * total
         np.testing.assert_array_equal(pc._round_keep_sum(x), ref_util.oric(x))
+    for n in (None, 1, 5):  # seeds handed to samplers / DataLoaders come from the caller's generator the same way
+        assert pc.make_seeds(np.random.default_rng(9), n) == ref_util.make_seeds(np.random.default_rng(9), n)
     assert set(pc.QUERY_SCHEDULES) == set(ref_pc.QUERY_SCHEDULES)
     for name, fn in pc.QUERY_SCHEDULES.items():
         for t in np.linspace(0, 1, 7):
