@@ -360,3 +360,38 @@ def test_running_norm_module_and_mode_helpers_agree_with_the_reference():
         with ctx(b):
             assert b.training is want
         assert b.training is True
+
+
+def test_preference_probability_and_loss_agree_with_the_reference():
+    """f1: `PreferenceModel.probability` (preference_comparisons.py:487-530: discounting, clipping at the threshold, noise
+    floor) and the cross-entropy / accuracy arithmetic of `CrossEntropyRewardLoss` (:1043-1090) on CPU tensors against the
+    reference's classes, for several (noise_prob, discount_factor, threshold) settings incl. clipped return differences."""
+    refimport.load()
+    import gymnasium
+    import torch as th
+    from imitation.algorithms import preference_comparisons as ref_pc
+    from imitation.rewards import reward_nets as ref_rn
+
+    from imitation_b200 import spaces
+    from imitation_b200.algorithms import preference_comparisons as pc
+    from imitation_b200.rewards import reward_nets
+
+    theirs_net = ref_rn.BasicRewardNet(gymnasium.spaces.Box(-1, 1, (4,)), gymnasium.spaces.Box(-1, 1, (2,)))
+    ours_net = reward_nets.BasicRewardNet(spaces.Box(-1, 1, (4,)), spaces.Box(-1, 1, (2,)))
+    g = th.Generator().manual_seed(0)
+    for noise, discount, threshold in ((0.0, 1.0, 50.0), (0.1, 0.95, 50.0), (0.3, 0.9, 2.0)):
+        a = ref_pc.PreferenceModel(theirs_net, noise_prob=noise, discount_factor=discount, threshold=threshold)
+        b = pc.PreferenceModel(ours_net, noise_prob=noise, discount_factor=discount, threshold=threshold)
+        for scale in (0.3, 3.0):
+            r1, r2 = th.randn(12, generator=g) * scale, th.randn(12, generator=g) * scale
+            pa, pb = a.probability(r1, r2), b.probability(r1, r2)
+            assert pa.shape == pb.shape == () and th.equal(pa, pb)
+        # a batch of pairs the way the fused path lays it out: [P, L] rewards, time on axis 1
+        R1, R2 = th.randn(9, 12, generator=g) * 2, th.randn(9, 12, generator=g) * 2
+        batch = b._probability(R1, R2, time_axis=1)
+        single = th.stack([a.probability(x, y) for x, y in zip(R1, R2)])
+        th.testing.assert_close(batch, single, rtol=1e-6, atol=1e-7)
+        prefs = (th.rand(9, generator=g) < 0.5).float()
+        want = th.nn.functional.binary_cross_entropy(single, prefs)
+        th.testing.assert_close(th.nn.functional.binary_cross_entropy(batch, prefs), want, rtol=1e-6, atol=1e-7)
+        assert ((batch > 0.5) == (prefs > 0.5)).float().mean() == ((single > 0.5) == (prefs > 0.5)).float().mean()
