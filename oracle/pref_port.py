@@ -52,3 +52,33 @@ def cross_entropy_loss_port(probs: th.Tensor, gt_probs: th.Tensor, preferences: 
     accuracy = ((probs > 0.5) == (prefs > 0.5)).float().mean()
     gt_loss = th.nn.functional.binary_cross_entropy(gt_probs, prefs)
     return th.nn.functional.binary_cross_entropy(probs, prefs), accuracy, gt_loss
+
+
+def pref_loss_closed_form(rews: np.ndarray, prefs: np.ndarray, noise_prob=0.0, discount_factor=1.0, threshold=50.0,
+                          grad_scale=1.0):
+    """NumPy (float32) twin of the `imb_pref_loss` kernel: the closed forms the kernel evaluates for one minibatch of P
+    pairs, rews[2][P][L] -> (probs[P], mean BCE loss, accuracy, grad_scale * d loss / d rews[2][P][L]).  What autograd
+    computes for probability_port + binary_cross_entropy (:487-530, :1043-1090):
+      d = clip(sum_t g^t (r2 - r1)),  m = 1 / (1 + e^d),  p = noise / 2 + (1 - noise) m
+      d loss / d p = (p - y) / max(p (1 - p), 1e-12) / P           (torch's BCE backward, incl. its clamp)
+      d p / d d    = -(1 - noise) m^2 e^d                          (= -(1 - noise) m (1 - m) without the cancellation in 1 - m)
+      d d / d r2_t = g^t = -d d / d r1_t, and 0 where the return difference was clipped."""
+    f = np.float32
+    r = np.asarray(rews, dtype=f)
+    P, L = r.shape[1], r.shape[2]
+    w = (f(discount_factor) ** np.arange(L, dtype=f)).astype(f)
+    s = ((r[1] - r[0]) * w).sum(axis=1, dtype=f)
+    clipped = (s < -threshold) | (s > threshold)
+    d = np.clip(s, -threshold, threshold).astype(f)
+    ed = np.exp(d, dtype=f)
+    m = (f(1) / (f(1) + ed)).astype(f)
+    p = (f(noise_prob) * f(0.5) + (f(1) - f(noise_prob)) * m).astype(f)
+    y = np.asarray(prefs, dtype=f)
+    with np.errstate(divide="ignore"):
+        lp, l1p = np.maximum(np.log(p), f(-100)), np.maximum(np.log1p(-p), f(-100))
+    loss = float(np.mean(-(y * lp + (f(1) - y) * l1p)))
+    acc = float(np.mean((p > 0.5) == (y > 0.5)))
+    g = np.where(clipped, f(0), f(grad_scale) * (p - y) / np.maximum(p * (f(1) - p), f(1e-12)) / f(P)
+                 * (-(f(1) - f(noise_prob)) * m * m * ed)).astype(f)
+    grad = np.stack([-(g[:, None] * w[None, :]), g[:, None] * w[None, :]]).astype(f)
+    return p, loss, acc, grad

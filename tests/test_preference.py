@@ -221,6 +221,30 @@ def test_index_dataloader_consumes_the_rng_like_the_fragment_dataloader():
     assert th.equal(after_want, after_perm)
 
 
+@pytest.mark.parametrize("noise,discount,threshold", [(0.0, 1.0, 50.0), (0.1, 0.95, 50.0), (0.2, 0.9, 1.5), (0.0, 1.0, 5.0)])
+def test_pref_loss_closed_form_matches_torch_autograd(noise, discount, threshold):
+    """The closed forms the `imb_pref_loss` kernel evaluates (oracle/pref_port.pref_loss_closed_form, a NumPy float32 twin)
+    against torch autograd through probability_port + binary_cross_entropy: probabilities, loss, accuracy and the gradient
+    with respect to every transition reward, including clipped pairs and soft preferences."""
+    from oracle import pref_port
+
+    th.manual_seed(1)
+    P, L, scale = 41, 11, 0.5
+    rews = (th.randn(2, P, L) * 2.5).requires_grad_()
+    y = (th.rand(P) < 0.5).float()
+    y[::5] = th.rand(len(y[::5]))
+    probs = th.stack([pref_port.probability_port(rews[0, k], rews[1, k], noise, discount, threshold) for k in range(P)])
+    loss = th.nn.functional.binary_cross_entropy(probs, y)
+    (loss * scale).backward()
+    p, l, acc, grad = pref_port.pref_loss_closed_form(rews.detach().numpy(), y.numpy(), noise, discount, threshold, scale)
+    np.testing.assert_allclose(p, probs.detach().numpy(), rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(l, float(loss.detach()), rtol=1e-5)
+    assert abs(acc - float(((probs > 0.5) == (y > 0.5)).float().mean())) < 1e-6
+    g = rews.grad.numpy()
+    np.testing.assert_allclose(grad, g, rtol=3e-5, atol=1e-9 + 1e-6 * float(np.abs(g).max()))
+    assert (grad[:, np.abs(((rews[1] - rews[0]).detach().numpy() * discount ** np.arange(L)).sum(1)) > threshold] == 0).all()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("noise,discount,threshold", [(0.0, 1.0, 50.0), (0.1, 0.95, 50.0), (0.2, 0.9, 1.5)])
 def test_pref_loss_kernel_matches_torch_autograd(noise, discount, threshold):
